@@ -1,0 +1,270 @@
+"""Block builders of the equivariant backbone, fused for the B200 kernels.
+
+Mirror of SPConvNets/utils/base_so3conv.py:21-221 (preprocess_input, IntraSO3ConvBlock,
+InterSO3ConvBlock, BasicSO3ConvBlock, SeparableSO3ConvBlock) and of the backbone part of
+SPConvNets/models/cls_so3net_pn.py:43-168 (build_model): same constructor arguments, same
+parameter dictionaries, same module / parameter names (so a reference state_dict loads), same
+returned tuples.  The difference is the execution: features stay channels-last, the grouping
+runs in the fused sm_100a kernels, the contractions on tcgen05, and BatchNorm / InstanceNorm +
+leaky_relu (+ the residual add) are single fused passes instead of separate torch ops.
+
+The reference's own, unmodified base_so3conv.py also runs on top of the `vgtk` modules of this
+package (module-level drop-in); this file is the faster block-level path the benchmark uses.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import equi_articulated_pose_b200 as _pkg
+
+_pkg.install()
+import vgtk.spconv as zptk  # noqa: E402
+import vgtk.so3conv as sptk  # noqa: E402
+from . import ops as _ops  # noqa: E402
+
+
+def preprocess_input(x, na, add_center=True):
+    """[nb,np,3] -> SphericalPointCloud(xyz [nb,3,np], ones [nb,1,np,na])  (base_so3conv.py:21-28)."""
+    has_normals = x.shape[2] == 6
+    if add_center and not has_normals:
+        center = x.mean(1, keepdim=True)
+        x = torch.cat((center, x), dim=1)[:, :-1]
+    xyz = x[:, :, :3]
+    return zptk.SphericalPointCloud(xyz.permute(0, 2, 1).contiguous(), sptk.get_occupancy_features(x, na, add_center), None)
+
+
+def _slope(activation):
+    if activation in ('leaky_relu',):
+        return 0.01
+    if activation in ('relu',):
+        return 0.0
+    if activation is None:
+        return 1.0
+    raise NotImplementedError(f"activation {activation}")
+
+
+def _rows(feats):
+    """logical [B,C,P,A] -> ([B*P*A, C] channels-last rows, (B,P,A,C))."""
+    b, c, p, a = feats.shape
+    return feats.permute(0, 2, 3, 1).reshape(b * p * a, c), (b, p, a, c)
+
+
+def _unrows(rows, b, p, a):
+    return rows.view(b, p, a, rows.shape[-1]).permute(0, 3, 1, 2)
+
+
+class FusedBatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d (identical parameters / buffers) whose forward on channels-last rows is one
+    statistics pass + one normalise-activate pass (vgtkb_norm_stats / vgtkb_norm_act_forward)."""
+
+    def forward_rows(self, rows, slope, residual=None):
+        training = self.training or not self.track_running_stats
+        if training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked += 1
+        mom = 0.1 if self.momentum is None else self.momentum
+        return _ops.norm_act(rows.unsqueeze(0), self.weight, self.bias, None if residual is None else residual.unsqueeze(0),
+                             self.running_mean if training else self.running_mean,
+                             self.running_var if training else self.running_var,
+                             mom, self.eps, slope, use_running=not training).squeeze(0)
+
+
+class FusedInstanceNorm2d(nn.InstanceNorm2d):
+    """nn.InstanceNorm2d(affine=False): per-(sample, channel) statistics over (points, anchors)."""
+
+    def forward_rows(self, rows, batch, slope, residual=None):
+        m, c = rows.shape
+        res = None if residual is None else residual.view(batch, m // batch, c)
+        return _ops.norm_act(rows.view(batch, m // batch, c), None, None, res, None, None, 0.1, self.eps, slope).view(m, c)
+
+
+def _make_norm(norm, dim):
+    if norm is None:
+        return FusedInstanceNorm2d(dim, affine=False)
+    if norm == 'BatchNorm2d':
+        return FusedBatchNorm2d(dim)
+    raise NotImplementedError(f"norm {norm}")
+
+
+def _apply_norm(norm, rows, batch, slope, residual=None):
+    if isinstance(norm, FusedBatchNorm2d):
+        return norm.forward_rows(rows, slope, residual)
+    return norm.forward_rows(rows, batch, slope, residual)
+
+
+class IntraSO3ConvBlock(nn.Module):
+    """base_so3conv.py:37-67"""
+
+    def __init__(self, dim_in, dim_out, norm=None, activation='relu', dropout_rate=0):
+        super().__init__()
+        self.conv = sptk.IntraSO3Conv(dim_in, dim_out)
+        self.norm = _make_norm(norm, dim_out)
+        self.slope = _slope(activation)
+        self.dropout = nn.Dropout(dropout_rate) if dropout_rate > 0 else None
+
+    def forward(self, x, residual_rows=None):
+        y = self.conv(x)
+        rows, (b, p, a, _) = _rows(y.feats)
+        rows = _apply_norm(self.norm, rows, b, self.slope, residual_rows)
+        if self.training and self.dropout is not None:
+            rows = self.dropout(rows)
+        return zptk.SphericalPointCloud(y.xyz, _unrows(rows, b, p, a), y.anchors)
+
+
+class InterSO3ConvBlock(nn.Module):
+    """base_so3conv.py:93-132"""
+
+    def __init__(self, dim_in, dim_out, kernel_size, stride, radius, sigma, n_neighbor, multiplier, kanchor=60,
+                 lazy_sample=None, norm=None, activation='relu', pooling='none', dropout_rate=0):
+        super().__init__()
+        if lazy_sample is None:
+            lazy_sample = True
+        pooling_method = None if pooling == 'none' else pooling
+        self.conv = sptk.InterSO3Conv(dim_in, dim_out, kernel_size, stride, radius, sigma, n_neighbor,
+                                      kanchor=kanchor, lazy_sample=lazy_sample, pooling=pooling_method)
+        self.norm = _make_norm(norm, dim_out)
+        self.slope = _slope(activation)
+        self.dropout = nn.Dropout(dropout_rate) if dropout_rate > 0 else None
+
+    def forward(self, x, inter_idx=None, inter_w=None):
+        inter_idx, inter_w, sample_idx, y = self.conv(x, inter_idx, inter_w)
+        rows, (b, p, a, _) = _rows(y.feats)
+        rows = _apply_norm(self.norm, rows, b, self.slope)
+        if self.training and self.dropout is not None:
+            rows = self.dropout(rows)
+        return inter_idx, inter_w, sample_idx, zptk.SphericalPointCloud(y.xyz, _unrows(rows, b, p, a), y.anchors)
+
+
+class SeparableSO3ConvBlock(nn.Module):
+    """inter conv -> intra conv, plus a 1x1-conv skip branch (base_so3conv.py:174-221)."""
+
+    def __init__(self, params):
+        super().__init__()
+        dim_in, dim_out = params['dim_in'], params['dim_out']
+        self.use_intra = params['kanchor'] > 1
+        self.inter_conv = InterSO3ConvBlock(**params)
+        if self.use_intra:
+            self.intra_conv = IntraSO3ConvBlock(dim_in=dim_out, dim_out=dim_out, dropout_rate=params['dropout_rate'],
+                                                activation=params['activation'])
+        self.stride = params['stride']
+        self.skip_conv = nn.Conv2d(dim_in, dim_out, 1)
+        self.norm = _make_norm(params.get('norm'), dim_out)
+        self.slope = _slope(params['activation'])
+
+    def forward(self, x, inter_idx, inter_w):
+        skip = x.feats
+        inter_idx, inter_w, sample_idx, y = self.inter_conv(x, inter_idx, inter_w)
+        # skip branch first, so that its result rides along as the residual of the last fused pass
+        b, ci, n, a = skip.shape
+        srows = skip.permute(0, 2, 3, 1)
+        if self.stride > 1:
+            srows = _ops.RowGatherFn.apply(srows.reshape(b, n, a * ci), sample_idx.to(torch.int32).contiguous())
+        p = srows.shape[1]
+        srows = srows.reshape(b * p * a, ci)
+        w = self.skip_conv.weight.view(self.skip_conv.out_channels, ci)
+        srows = _ops.LinearFn.apply(srows, w, self.skip_conv.bias)
+        srows = _apply_norm(self.norm, srows, b, self.slope)
+        if self.use_intra:
+            y = self.intra_conv(y, residual_rows=srows)
+            out = y.feats
+        else:
+            out = y.feats + _unrows(srows, b, p, a)
+        return inter_idx, inter_w, sample_idx, zptk.SphericalPointCloud(y.xyz, out, y.anchors)
+
+    def get_anchor(self):
+        return torch.from_numpy(sptk.get_anchors())
+
+
+class BasicSO3ConvBlock(nn.Module):
+    """A list of inter / intra / separable layers threading (inter_idx, inter_w)  (base_so3conv.py:135-172)."""
+
+    def __init__(self, params):
+        super().__init__()
+        self.blocks = nn.ModuleList()
+        self.layer_types = []
+        for param in params:
+            if param['type'] == 'intra_block':
+                conv = IntraSO3ConvBlock(**param['args'])
+            elif param['type'] == 'inter_block':
+                conv = InterSO3ConvBlock(**param['args'])
+            elif param['type'] == 'separable_block':
+                conv = SeparableSO3ConvBlock(param['args'])
+            else:
+                raise ValueError(f'No such type of SO3Conv {param["type"]}')
+            self.layer_types.append(param['type'])
+            self.blocks.append(conv)
+        self.params = params
+
+    def forward(self, x):
+        inter_idx, inter_w = None, None
+        for conv, param in zip(self.blocks, self.params):
+            if param['type'] in ['inter', 'inter_block', 'separable_block']:
+                inter_idx, inter_w, _, x = conv(x, inter_idx, inter_w)
+                if param['args']['stride'] > 1:
+                    inter_idx, inter_w = None, None
+            elif param['type'] in ['intra_block']:
+                x = conv(x)
+            else:
+                raise ValueError(f'No such type of SO3Conv {param["type"]}')
+        return x
+
+    def get_anchor(self):
+        return torch.from_numpy(sptk.get_anchors())
+
+
+def backbone_params(input_num=1024, kanchor=60, mlps=((64, 64), (128, 128), (256, 256), (256,)),
+                    strides=(2, 2, 2, 2), initial_radius_ratio=0.2, sampling_ratio=0.4, sampling_density=0.5,
+                    kernel_multiplier=2, input_radius=1.0, sigma_ratio=0.5, xyz_pooling=None, dropout_rate=0.0):
+    """Per-layer argument dictionaries of the classic equivariant backbone
+    (SPConvNets/models/cls_so3net_pn.py:43-150 with its default arguments)."""
+    strides = list(strides)
+    if input_num > 1024:
+        sampling_ratio /= (input_num / 1024)
+        strides[0] = int(2 * (input_num / 1024))
+    n_layer = len(mlps)
+    multipliers = [2 ** i for i in range(n_layer + 1)]
+    num_centers = [int(input_num / m) for m in multipliers]
+    radius_ratio = [initial_radius_ratio * m ** sampling_density for m in multipliers]
+    radii = [r * input_radius for r in radius_ratio]
+    weighted_sigma = [sigma_ratio * radii[0] ** 2]
+    for i in range(len(strides)):
+        weighted_sigma.append(weighted_sigma[i] * 2)
+    out, dim_in = [], 1
+    for i, block in enumerate(mlps):
+        layers = []
+        for j, dim_out in enumerate(block):
+            lazy_sample = i != 0 or j != 0
+            stride_conv = i == 0 or xyz_pooling != 'stride'
+            neighbor = int(sampling_ratio * num_centers[i] * radius_ratio[i] ** (1 / sampling_density))
+            if j == 0:
+                inter_stride = strides[i]
+                nidx = i if i == 0 else i + 1
+                if stride_conv:
+                    neighbor *= 2
+            else:
+                inter_stride, nidx = 1, i + 1
+            layers.append({'type': 'inter_block' if kanchor < 60 else 'separable_block', 'args': {
+                'dim_in': dim_in, 'dim_out': dim_out, 'kernel_size': 1, 'stride': inter_stride,
+                'radius': radii[nidx], 'sigma': weighted_sigma[nidx], 'n_neighbor': neighbor,
+                'lazy_sample': lazy_sample, 'dropout_rate': dropout_rate, 'multiplier': kernel_multiplier,
+                'activation': 'leaky_relu', 'pooling': xyz_pooling, 'kanchor': kanchor, 'norm': 'BatchNorm2d'}})
+            dim_in = dim_out
+        out.append(layers)
+    return out
+
+
+class SO3Backbone(nn.Module):
+    """`ClsSO3ConvModel.backbone` + its forward loop (cls_so3net_pn.py:15-33), without the head."""
+
+    def __init__(self, params, na=60):
+        super().__init__()
+        self.backbone = nn.ModuleList([BasicSO3ConvBlock(p) for p in params])
+        self.na_in = na
+
+    def forward(self, points):
+        """points [B,N,3] -> SphericalPointCloud (xyz [B,3,P], feats logical [B,C,P,A])."""
+        x = preprocess_input(points, self.na_in, False)
+        for block in self.backbone:
+            x = block(x)
+        return x

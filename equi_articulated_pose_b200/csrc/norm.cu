@@ -1,0 +1,261 @@
+// norm.cu -- BatchNorm2d / InstanceNorm2d statistics, normalise + leaky_relu (+ residual) and
+// their backward, on channels-last rows X[groups][rows][c] for sm_100a.
+//
+// Stands for torch's BatchNorm2d(train) / InstanceNorm2d(affine=False) + F.leaky_relu around the
+// reference blocks (SPConvNets/utils/base_so3conv.py:47-64,113-131,198-217).  HBM-bound
+// streaming kernels: float4 accesses, fp64 in-thread accumulation of the per-channel sums (the
+// skip branch of the first layer normalises a constant tensor, so cancellation matters), one
+// fp64 atomic per (CTA, channel).
+#include "common.cuh"
+
+namespace vgtkb {
+
+constexpr int NT = 256;  // threads per CTA
+
+struct OpStats {  // sum x, sum x^2
+    __device__ __forceinline__ void operator()(float x, int, int, double& s1, double& s2) const {
+        const double d = (double)x;
+        s1 += d;
+        s2 = fma(d, d, s2);
+    }
+};
+
+struct OpBwd {  // sum dyp, sum dyp*xhat with dyp = grad_y * lrelu'(xhat*gamma+beta)
+    const float* gy;
+    const float* stats;
+    const float* gamma;
+    const float* beta;
+    float slope;
+    int c;
+    __device__ __forceinline__ float dyp(float x, float g, int grp, int ch, float& xh) const {
+        const float mean = stats[(size_t)grp * 2 * c + ch], inv = stats[(size_t)grp * 2 * c + c + ch];
+        xh = (x - mean) * inv;
+        const float pre = xh * (gamma ? gamma[ch] : 1.f) + (beta ? beta[ch] : 0.f);
+        return pre > 0.f ? g : g * slope;
+    }
+};
+
+// column reduction: for every (group, channel) accumulate two fp64 sums over rows.
+// MODE 0: stats (x, x^2)   MODE 1: backward sums (needs gy)   MODE 2: plain column sum
+template <int MODE>
+__global__ void __launch_bounds__(NT)
+col_reduce_kernel(int64_t rows, int c, int rows_per_cta, const float* __restrict__ x, OpBwd bw,
+                  double* __restrict__ scratch) {
+    const int g = blockIdx.y;
+    const int tx = min(c, NT), ty = NT / tx;
+    const int lx = threadIdx.x % tx, ly = threadIdx.x / tx;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = min(rows, r0 + rows_per_cta);
+    const float* xg = x + (size_t)g * rows * c;
+    const float* gyg = MODE == 1 ? bw.gy + (size_t)g * rows * c : nullptr;
+    __shared__ double sh1[NT], sh2[NT];
+    for (int ch = lx; ch < c; ch += tx) {
+        double s1 = 0.0, s2 = 0.0;
+        if (ly < ty) {
+            for (int64_t r = r0 + ly; r < r1; r += ty) {
+                const float v = xg[r * c + ch];
+                if (MODE == 0) {
+                    const double d = (double)v;
+                    s1 += d;
+                    s2 = fma(d, d, s2);
+                } else if (MODE == 1) {
+                    float xh;
+                    const float d = bw.dyp(v, gyg[r * c + ch], g, ch, xh);
+                    s1 += (double)d;
+                    s2 += (double)d * (double)xh;
+                } else {
+                    s1 += (double)v;
+                }
+            }
+        }
+        sh1[threadIdx.x] = s1;
+        sh2[threadIdx.x] = s2;
+        __syncthreads();
+        if (ly == 0) {
+            for (int j = 1; j < ty; ++j) {
+                s1 += sh1[j * tx + lx];
+                s2 += sh2[j * tx + lx];
+            }
+            atomicAdd(scratch + ((size_t)g * 2 + 0) * c + ch, s1);
+            if (MODE != 2) atomicAdd(scratch + ((size_t)g * 2 + 1) * c + ch, s2);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void stats_finalize_kernel(int groups, int64_t rows, int c, float eps, const double* __restrict__ scratch,
+                                      float* __restrict__ stats, float* running_mean, float* running_var,
+                                      float momentum) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= groups * c) return;
+    const int g = t / c, ch = t % c;
+    const double n = (double)rows;
+    const double mean = scratch[((size_t)g * 2 + 0) * c + ch] / n;
+    double var = scratch[((size_t)g * 2 + 1) * c + ch] / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[(size_t)g * 2 * c + ch] = (float)mean;
+    stats[(size_t)g * 2 * c + c + ch] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean != nullptr && g == 0) {  // BatchNorm (groups == 1): torch uses the unbiased variance here
+        const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+        running_mean[ch] = (float)((1.0 - momentum) * running_mean[ch] + momentum * mean);
+        running_var[ch] = (float)((1.0 - momentum) * running_var[ch] + momentum * unbiased);
+    }
+}
+
+__global__ void norm_act_fwd_kernel(int64_t total4, int64_t rows, int c4, const float4* __restrict__ x,
+                                    const float* __restrict__ stats, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float slope, const float4* __restrict__ res,
+                                    float4* __restrict__ y) {
+    const int c = c4 * 4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(t % c4) * 4;
+        const int g = (int)(t / (rows * c4));
+        const float4 v = x[t];
+        const float4 mean = *reinterpret_cast<const float4*>(stats + (size_t)g * 2 * c + ch);
+        const float4 inv = *reinterpret_cast<const float4*>(stats + (size_t)g * 2 * c + c + ch);
+        float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gamma) ga = *reinterpret_cast<const float4*>(gamma + ch);
+        if (beta) be = *reinterpret_cast<const float4*>(beta + ch);
+        float o[4] = {(v.x - mean.x) * inv.x * ga.x + be.x, (v.y - mean.y) * inv.y * ga.y + be.y,
+                      (v.z - mean.z) * inv.z * ga.z + be.z, (v.w - mean.w) * inv.w * ga.w + be.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = o[i] > 0.f ? o[i] : o[i] * slope;
+        if (res) {
+            const float4 r = res[t];
+            o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+        }
+        y[t] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+__global__ void norm_act_fwd_scalar_kernel(int64_t total, int64_t rows, int c, const float* __restrict__ x,
+                                           const float* __restrict__ stats, const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, float slope, const float* __restrict__ res,
+                                           float* __restrict__ y) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(t % c);
+        const int g = (int)(t / (rows * c));
+        float o = (x[t] - stats[(size_t)g * 2 * c + ch]) * stats[(size_t)g * 2 * c + c + ch];
+        o = o * (gamma ? gamma[ch] : 1.f) + (beta ? beta[ch] : 0.f);
+        o = o > 0.f ? o : o * slope;
+        if (res) o += res[t];
+        y[t] = o;
+    }
+}
+
+// dx = gamma*invstd*(dyp - S1/n - xhat*S2/n)
+__global__ void norm_act_bwd_apply_kernel(int64_t total, int64_t rows, int c, const float* __restrict__ x,
+                                          OpBwd bw, const double* __restrict__ scratch, float* __restrict__ gx) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(t % c);
+        const int g = (int)(t / (rows * c));
+        float xh;
+        const float d = bw.dyp(x[t], bw.gy[t], g, ch, xh);
+        const float m1 = (float)(scratch[((size_t)g * 2 + 0) * c + ch] / (double)rows);
+        const float m2 = (float)(scratch[((size_t)g * 2 + 1) * c + ch] / (double)rows);
+        const float inv = bw.stats[(size_t)g * 2 * c + c + ch];
+        const float ga = bw.gamma ? bw.gamma[ch] : 1.f;
+        gx[t] = ga * inv * (d - m1 - xh * m2);
+    }
+}
+
+__global__ void affine_grad_kernel(int groups, int c, const double* __restrict__ scratch, float* ggamma, float* gbeta) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int g = 0; g < groups; ++g) {
+        s1 += scratch[((size_t)g * 2 + 0) * c + ch];
+        s2 += scratch[((size_t)g * 2 + 1) * c + ch];
+    }
+    if (gbeta) gbeta[ch] = (float)s1;
+    if (ggamma) ggamma[ch] = (float)s2;
+}
+
+__global__ void col_sum_finalize_kernel(int c, const double* __restrict__ scratch, float* out) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < c) out[ch] = (float)scratch[ch];
+}
+
+static int reduce_geometry(int64_t rows, int c, int groups, int& rows_per_cta, unsigned& gx) {
+    // aim at ~4 CTAs per SM overall, at least 64 rows per CTA
+    int64_t want = (int64_t)kNumSMs * 4 / (groups > 0 ? groups : 1);
+    if (want < 1) want = 1;
+    int64_t rpc = ceil_div64(rows, want);
+    if (rpc < 64) rpc = 64;
+    rows_per_cta = (int)rpc;
+    gx = (unsigned)ceil_div64(rows, rpc);
+    return 0;
+}
+
+}  // namespace vgtkb
+
+using namespace vgtkb;
+
+extern "C" int vgtkb_norm_stats(int groups, int64_t rows, int c, const float* x, float eps, double* scratch,
+                                float* stats, float* running_mean, float* running_var, float momentum, void* stream) {
+    VGTKB_REQUIRE(groups > 0 && rows > 0 && c > 0, "norm_stats: bad size");
+    VGTKB_REQUIRE(groups <= 65535, "norm_stats: too many groups");
+    cudaStream_t st = (cudaStream_t)stream;
+    VGTKB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (size_t)groups * 2 * c, st));
+    int rpc;
+    unsigned gx;
+    reduce_geometry(rows, c, groups, rpc, gx);
+    OpBwd dummy{};
+    col_reduce_kernel<0><<<dim3(gx, groups), NT, 0, st>>>(rows, c, rpc, x, dummy, scratch);
+    stats_finalize_kernel<<<ceil_div(groups * c, 128), 128, 0, st>>>(groups, rows, c, eps, scratch, stats, running_mean,
+                                                                    running_var, momentum);
+    return check_launch("norm_stats");
+}
+
+extern "C" int vgtkb_norm_act_forward(int groups, int64_t rows, int c, const float* x, const float* stats,
+                                      const float* gamma, const float* beta, float slope, const float* residual,
+                                      float* y, void* stream) {
+    VGTKB_REQUIRE(groups > 0 && rows > 0 && c > 0, "norm_act: bad size");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = (int64_t)groups * rows * c;
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool v4 = c % 4 == 0 && al(x) && al(y) && al(stats) && (!gamma || al(gamma)) && (!beta || al(beta)) &&
+                    (!residual || al(residual));
+    const int64_t work = v4 ? total / 4 : total;
+    const unsigned grid = (unsigned)(ceil_div64(work, NT) < (int64_t)kNumSMs * 16 ? ceil_div64(work, NT) : kNumSMs * 16);
+    if (v4)
+        norm_act_fwd_kernel<<<grid, NT, 0, st>>>(work, rows, c / 4, (const float4*)x, stats, gamma, beta, slope,
+                                                 (const float4*)residual, (float4*)y);
+    else
+        norm_act_fwd_scalar_kernel<<<grid, NT, 0, st>>>(total, rows, c, x, stats, gamma, beta, slope, residual, y);
+    return check_launch("norm_act_forward");
+}
+
+extern "C" int vgtkb_norm_act_backward(int groups, int64_t rows, int c, const float* x, const float* stats,
+                                       const float* gamma, const float* beta, float slope, const float* grad_y,
+                                       double* scratch, float* grad_x, float* grad_gamma, float* grad_beta,
+                                       void* stream) {
+    VGTKB_REQUIRE(groups > 0 && rows > 0 && c > 0, "norm_act_backward: bad size");
+    VGTKB_REQUIRE(groups <= 65535, "norm_act_backward: too many groups");
+    cudaStream_t st = (cudaStream_t)stream;
+    VGTKB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (size_t)groups * 2 * c, st));
+    OpBwd bw{grad_y, stats, gamma, beta, slope, c};
+    int rpc;
+    unsigned gx;
+    reduce_geometry(rows, c, groups, rpc, gx);
+    col_reduce_kernel<1><<<dim3(gx, groups), NT, 0, st>>>(rows, c, rpc, x, bw, scratch);
+    const int64_t total = (int64_t)groups * rows * c;
+    const unsigned grid = (unsigned)(ceil_div64(total, NT) < (int64_t)kNumSMs * 16 ? ceil_div64(total, NT) : kNumSMs * 16);
+    norm_act_bwd_apply_kernel<<<grid, NT, 0, st>>>(total, rows, c, x, bw, scratch, grad_x);
+    if (grad_gamma || grad_beta)
+        affine_grad_kernel<<<ceil_div(c, 128), 128, 0, st>>>(groups, c, scratch, grad_gamma, grad_beta);
+    return check_launch("norm_act_backward");
+}
+
+extern "C" int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream) {
+    VGTKB_REQUIRE(rows > 0 && c > 0, "col_sum: bad size");
+    cudaStream_t st = (cudaStream_t)stream;
+    VGTKB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (size_t)2 * c, st));
+    int rpc;
+    unsigned gx;
+    reduce_geometry(rows, c, 1, rpc, gx);
+    OpBwd dummy{};
+    col_reduce_kernel<2><<<dim3(gx, 1), NT, 0, st>>>(rows, c, rpc, x, dummy, scratch);
+    col_sum_finalize_kernel<<<ceil_div(c, 128), 128, 0, st>>>(c, scratch, out);
+    return check_launch("col_sum");
+}

@@ -1,0 +1,104 @@
+"""ctypes binding of libvgtkb200.so (the C ABI declared in include/vgtkb.h).
+
+There is NO CPU fallback: if the library is missing, or a tensor is not a contiguous CUDA
+tensor, the call raises.  PyTorch is used for device memory and streams only.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvgtkb200.so")
+ABI_VERSION = 1
+
+_lib = None
+_device_ok = set()
+
+c_int, c_i64, c_f32, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+# name -> argtypes; every entry point returns int (0 = ok).  Must list every symbol of vgtkb.h.
+SIGNATURES = {
+    "vgtkb_ball_query": [c_int, c_int, c_int, c_f32, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_furthest_point_sampling": [c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    "vgtkb_gather_points_forward": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_gather_points_backward": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_chamfer_forward": [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_chamfer_backward": [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_inter_weights": [c_int] * 6 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp],
+    "vgtkb_inter_group_forward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
+    "vgtkb_inter_group_backward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
+    "vgtkb_intra_group_forward": [c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_intra_group_backward": [c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_row_gather_forward": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_row_gather_backward": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_gemm_nt": [c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
+    "vgtkb_gemm_tn": [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_vp],
+    "vgtkb_norm_stats": [c_int, c_i64, c_int, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp],
+    "vgtkb_norm_act_forward": [c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
+    "vgtkb_norm_act_backward": [c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_col_sum": [c_i64, c_int, c_vp, c_vp, c_vp, c_vp],
+}
+NO_STATUS = {"vgtkb_last_error": (ctypes.c_char_p, []), "vgtkb_version": (c_int, []),
+             "vgtkb_device_check": (c_int, [])}
+
+
+class VgtkbError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VgtkbError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in NO_STATUS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = c_int, args
+    if lib.vgtkb_version() != ABI_VERSION:
+        raise VgtkbError(f"ABI mismatch: library {lib.vgtkb_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def _ensure_device(dev_index):
+    if dev_index in _device_ok:
+        return
+    lib = load()
+    with torch.cuda.device(dev_index):
+        if lib.vgtkb_device_check() != 0:
+            raise VgtkbError(lib.vgtkb_last_error().decode())
+    _device_ok.add(dev_index)
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise VgtkbError("expected a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise VgtkbError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def call(name, device, *args):
+    """Invoke an entry point on `device`'s current stream; raise on a non-zero status."""
+    lib = load()
+    _ensure_device(device.index if device.index is not None else torch.cuda.current_device())
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = getattr(lib, name)(*args, stream)
+    if rc != 0:
+        raise VgtkbError(f"{name} failed ({rc}): {lib.vgtkb_last_error().decode()}")
+    COUNTERS["launch_calls"] += 1
+
+
+COUNTERS = {"launch_calls": 0}

@@ -1,0 +1,315 @@
+"""Tensor-level operators over the C ABI (include/vgtkb.h) + their autograd wrappers.
+
+Layouts: the literal 1:1 ops keep the reference layouts (xyz [B,3,N], points [B,C,N]); the
+fused SO(3) path works on CHANNELS-LAST feature rows X[B,N,A,C].
+Every function allocates its outputs with torch and launches on the current stream.
+"""
+import torch
+
+from . import lib as _lib
+
+call, ptr = _lib.call, _lib.ptr
+
+# GEMM arithmetic: 0 = fp32 FFMA, 1 = tcgen05 3xTF32 (fp32-equivalent, default), 2 = tcgen05 1xTF32
+_GEMM_MODE = 1
+LEAKY_SLOPE = 0.01  # F.leaky_relu default used by the reference blocks
+
+
+def set_gemm_mode(mode):
+    global _GEMM_MODE
+    assert mode in (0, 1, 2)
+    _GEMM_MODE = mode
+
+
+def get_gemm_mode():
+    return _GEMM_MODE
+
+
+def _f32(t):
+    if t.dtype != torch.float32:
+        raise _lib.VgtkbError(f"expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _i32(t):
+    return t.to(torch.int32).contiguous()
+
+
+# ----------------------------------------------------------------------------- literal ops
+def ball_query(new_xyz, xyz, radius, nsample):
+    """vgtk.cuda.grouping.ball_query: new_xyz [B,3,M], xyz [B,3,N] -> int32 [B,M,nsample]."""
+    new_xyz, xyz = _f32(new_xyz), _f32(xyz)
+    b, _, m = new_xyz.shape
+    n = xyz.shape[2]
+    idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz.device)
+    call("vgtkb_ball_query", xyz.device, b, n, m, float(radius), int(nsample), ptr(new_xyz), ptr(xyz), ptr(idx))
+    return idx
+
+
+def furthest_point_sampling(xyz, m):
+    """vgtk.cuda.grouping.furthest_point_sampling: xyz [B,3,N] -> int32 [B,m]."""
+    xyz = _f32(xyz)
+    b, _, n = xyz.shape
+    idx = torch.zeros((b, m), dtype=torch.int32, device=xyz.device)
+    call("vgtkb_furthest_point_sampling", xyz.device, b, n, int(m), ptr(xyz), ptr(idx))
+    return idx
+
+
+def gather_points_forward(points, idx):
+    """vgtk.cuda.gathering.gather_points_forward: points [B,C,N], idx [B,M] -> [B,C,M]."""
+    points, idx = _f32(points), _i32(idx)
+    b, c, n = points.shape
+    m = idx.shape[1]
+    out = torch.empty((b, c, m), dtype=torch.float32, device=points.device)
+    call("vgtkb_gather_points_forward", points.device, b, c, n, m, ptr(points), ptr(idx), ptr(out))
+    return out
+
+
+def gather_points_backward(grad_out, idx, npoint):
+    grad_out, idx = _f32(grad_out), _i32(idx)
+    b, c, m = grad_out.shape
+    out = torch.empty((b, c, npoint), dtype=torch.float32, device=grad_out.device)
+    call("vgtkb_gather_points_backward", grad_out.device, b, c, int(npoint), m, ptr(grad_out), ptr(idx), ptr(out))
+    return out
+
+
+def chamfer_forward(xyz1, xyz2):
+    """chamfer.forward: xyz1 [B,n,3], xyz2 [B,m,3] -> dist1 [B,n], dist2 [B,m], idx1, idx2 (int32)."""
+    xyz1, xyz2 = _f32(xyz1), _f32(xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dev = xyz1.device
+    d1 = torch.empty((b, n), dtype=torch.float32, device=dev)
+    d2 = torch.empty((b, m), dtype=torch.float32, device=dev)
+    i1 = torch.empty((b, n), dtype=torch.int32, device=dev)
+    i2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+    call("vgtkb_chamfer_forward", dev, b, n, ptr(xyz1), m, ptr(xyz2), ptr(d1), ptr(d2), ptr(i1), ptr(i2))
+    return d1, d2, i1, i2
+
+
+def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
+    xyz1, xyz2, g1, g2 = _f32(xyz1), _f32(xyz2), _f32(grad_dist1), _f32(grad_dist2)
+    idx1, idx2 = _i32(idx1), _i32(idx2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    gx1, gx2 = torch.empty_like(xyz1), torch.empty_like(xyz2)
+    call("vgtkb_chamfer_backward", xyz1.device, b, n, ptr(xyz1), m, ptr(xyz2), ptr(idx1), ptr(idx2), ptr(g1), ptr(g2),
+         ptr(gx1), ptr(gx2))
+    return gx1, gx2
+
+
+def inter_weights(xyz, sample_xyz, idx, rot_kernels, sigma):
+    """Materialised kernel-point correlation w [B,P,A,K,nn] (API parity; fused path never stores it)."""
+    xyz, sample_xyz, idx, rk = _f32(xyz), _f32(sample_xyz), _i32(idx), _f32(rot_kernels)
+    b, _, n = xyz.shape
+    p, nn = idx.shape[1], idx.shape[2]
+    a, k = rk.shape[0], rk.shape[1]
+    w = torch.empty((b, p, a, k, nn), dtype=torch.float32, device=xyz.device)
+    call("vgtkb_inter_weights", xyz.device, b, n, p, nn, a, k, ptr(xyz), ptr(sample_xyz), ptr(idx), ptr(rk),
+         float(sigma), ptr(w))
+    return w
+
+
+# ----------------------------------------------------------------------------- raw fused ops
+def gemm_nt(a, b, bias=None, mode=None):
+    """C[M,N] = A[M,K] @ B[N,K]^T (+ bias)."""
+    a, b = _f32(a), _f32(b)
+    m, k = a.shape
+    n = b.shape[0]
+    assert b.shape[1] == k
+    c = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    call("vgtkb_gemm_nt", a.device, m, n, k, ptr(a), ptr(b), ptr(bias.contiguous()) if bias is not None else None,
+         ptr(c), _GEMM_MODE if mode is None else mode)
+    return c
+
+
+def gemm_tn(a, b, mode=None):
+    """C[M,N] = A[R,M]^T @ B[R,N]."""
+    a, b = _f32(a), _f32(b)
+    r, m = a.shape
+    n = b.shape[1]
+    assert b.shape[0] == r
+    c = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    call("vgtkb_gemm_tn", a.device, m, n, r, ptr(a), ptr(b), ptr(c), 0, _GEMM_MODE if mode is None else mode)
+    return c
+
+
+def col_sum(x):
+    x = _f32(x)
+    rows, c = x.shape
+    scratch = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+    out = torch.empty(c, dtype=torch.float32, device=x.device)
+    call("vgtkb_col_sum", x.device, rows, c, ptr(x), ptr(scratch), ptr(out))
+    return out
+
+
+# ----------------------------------------------------------------------------- autograd wrappers
+class InterGroupFn(torch.autograd.Function):
+    """feats X [B,N,A,Ci] -> G [B,P,A,K*Ci]; weights recomputed in shared memory, never stored."""
+
+    @staticmethod
+    def forward(ctx, feats, xyz, sample_xyz, idx, rot_kernels, sigma):
+        feats = _f32(feats)
+        b, n, a, ci = feats.shape
+        p, nn = idx.shape[1], idx.shape[2]
+        k = rot_kernels.shape[1]
+        g = torch.empty((b, p, a, k * ci), dtype=torch.float32, device=feats.device)
+        call("vgtkb_inter_group_forward", feats.device, b, n, p, nn, a, k, ci, ptr(xyz), ptr(sample_xyz), ptr(idx),
+             ptr(rot_kernels), float(sigma), ptr(feats), ptr(g))
+        ctx.save_for_backward(xyz, sample_xyz, idx, rot_kernels)
+        ctx.meta = (b, n, p, nn, a, k, ci, float(sigma))
+        return g
+
+    @staticmethod
+    def backward(ctx, grad_g):
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 6
+        xyz, sample_xyz, idx, rot_kernels = ctx.saved_tensors
+        b, n, p, nn, a, k, ci, sigma = ctx.meta
+        grad_g = _f32(grad_g)
+        gx = torch.zeros((b, n, a, ci), dtype=torch.float32, device=grad_g.device)
+        call("vgtkb_inter_group_backward", grad_g.device, b, n, p, nn, a, k, ci, ptr(xyz), ptr(sample_xyz), ptr(idx),
+             ptr(rot_kernels), sigma, ptr(grad_g), ptr(gx))
+        return gx, None, None, None, None, None
+
+
+class IntraGroupFn(torch.autograd.Function):
+    """Y [R,A,C] -> G [R,A,KK*C] with G[r,a,k,:] = Y[r, intra_idx[a,k], :]."""
+
+    @staticmethod
+    def forward(ctx, y, intra_idx):
+        y = _f32(y)
+        r, a, c = y.shape
+        kk = intra_idx.shape[1]
+        g = torch.empty((r, a, kk * c), dtype=torch.float32, device=y.device)
+        call("vgtkb_intra_group_forward", y.device, r, a, kk, c, ptr(intra_idx), ptr(y), ptr(g))
+        ctx.save_for_backward(intra_idx)
+        ctx.meta = (r, a, kk, c)
+        return g
+
+    @staticmethod
+    def backward(ctx, grad_g):
+        (intra_idx,) = ctx.saved_tensors
+        r, a, kk, c = ctx.meta
+        grad_g = _f32(grad_g)
+        gy = torch.empty((r, a, c), dtype=torch.float32, device=grad_g.device)
+        call("vgtkb_intra_group_backward", grad_g.device, r, a, kk, c, ptr(intra_idx), ptr(grad_g), ptr(gy))
+        return gy, None
+
+
+class LinearFn(torch.autograd.Function):
+    """y[M,N] = x[M,K] @ w[N,K]^T + bias  (the BasicSO3Conv contraction / 1x1 skip conv)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        x, w = _f32(x), _f32(w)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return gemm_nt(x, w, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = _f32(gy)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm_nt(gy, w.t().contiguous())
+        if ctx.needs_input_grad[1]:
+            gw = gemm_tn(gy, x)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = col_sum(gy)
+        return gx, gw, gb
+
+
+class RowGatherFn(torch.autograd.Function):
+    """x [B,N,W] , idx [B,M] -> [B,M,W] (skip-connection sub-sampling by sample_idx)."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        x = _f32(x)
+        b, n, w = x.shape
+        m = idx.shape[1]
+        out = torch.empty((b, m, w), dtype=torch.float32, device=x.device)
+        call("vgtkb_row_gather_forward", x.device, b, n, m, w, ptr(x), ptr(idx), ptr(out))
+        ctx.save_for_backward(idx)
+        ctx.meta = (b, n, m, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (idx,) = ctx.saved_tensors
+        b, n, m, w = ctx.meta
+        gout = _f32(gout)
+        gx = torch.zeros((b, n, w), dtype=torch.float32, device=gout.device)
+        call("vgtkb_row_gather_backward", gout.device, b, n, m, w, ptr(gout), ptr(idx), ptr(gx))
+        return gx, None
+
+
+class NormActFn(torch.autograd.Function):
+    """leaky_relu(norm(x)) [+ residual] on rows x [groups, rows, C].
+
+    groups == 1: BatchNorm2d in training mode (batch statistics; running stats updated in place)
+    groups == B: InstanceNorm2d(affine=False).  With `use_running` the running statistics are
+    used instead (eval-mode BatchNorm)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, momentum, eps, slope, use_running):
+        x = _f32(x)
+        g, rows, c = x.shape
+        dev = x.device
+        stats = torch.empty((g, 2, c), dtype=torch.float32, device=dev)
+        if use_running:
+            stats[:, 0] = running_mean
+            stats[:, 1] = torch.rsqrt(running_var + eps)
+        else:
+            scratch = torch.empty((g, 2, c), dtype=torch.float64, device=dev)
+            call("vgtkb_norm_stats", dev, g, rows, c, ptr(x), float(eps), ptr(scratch), ptr(stats),
+                 ptr(running_mean) if running_mean is not None else None,
+                 ptr(running_var) if running_var is not None else None, float(momentum))
+        y = torch.empty_like(x)
+        gam = gamma.contiguous() if gamma is not None else None
+        bet = beta.contiguous() if beta is not None else None
+        res = _f32(residual) if residual is not None else None
+        call("vgtkb_norm_act_forward", dev, g, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), float(slope), ptr(res),
+             ptr(y))
+        ctx.save_for_backward(x, stats, gam, bet)
+        ctx.meta = (g, rows, c, float(slope), use_running, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, stats, gam, bet = ctx.saved_tensors
+        g, rows, c, slope, use_running, has_res = ctx.meta
+        if use_running:
+            raise NotImplementedError("backward through eval-mode BatchNorm is not part of the hot path")
+        gy = _f32(gy)
+        dev = gy.device
+        scratch = torch.empty((g, 2, c), dtype=torch.float64, device=dev)
+        gx = torch.empty_like(x)
+        ggam = torch.empty(c, dtype=torch.float32, device=dev) if gam is not None else None
+        gbet = torch.empty(c, dtype=torch.float32, device=dev) if bet is not None else None
+        call("vgtkb_norm_act_backward", dev, g, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), slope, ptr(gy),
+             ptr(scratch), ptr(gx), ptr(ggam), ptr(gbet))
+        return gx, ggam, gbet, (gy if has_res else None), None, None, None, None, None, None
+
+
+def norm_act(x, gamma=None, beta=None, residual=None, running_mean=None, running_var=None, momentum=0.1, eps=1e-5,
+             slope=LEAKY_SLOPE, use_running=False):
+    return NormActFn.apply(x, gamma, beta, residual, running_mean, running_var, momentum, eps, slope, use_running)
+
+
+class ChamferFn(torch.autograd.Function):
+    """extensions/chamfer_dist/__init__.py:13-26 (ChamferFunction)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2):
+        d1, d2, i1, i2 = chamfer_forward(xyz1, xyz2)
+        ctx.save_for_backward(xyz1, xyz2, i1, i2)
+        ctx.mark_non_differentiable(i1, i2)
+        return d1, d2, i1, i2
+
+    @staticmethod
+    def backward(ctx, g1, g2, _gi1, _gi2):
+        xyz1, xyz2, i1, i2 = ctx.saved_tensors
+        gx1, gx2 = chamfer_backward(xyz1, xyz2, i1, i2, g1.contiguous(), g2.contiguous())
+        return gx1, gx2

@@ -1,0 +1,160 @@
+"""vgtk.so3conv.modules -- the SO(3) convolution modules (reference: vgtk/vgtk/so3conv/modules.py).
+
+Same constructor signatures, parameter / buffer names (`basic_conv.W`, `anchors`, `kernels`,
+`intra_idx`) and forward return tuples as the reference, so reference checkpoints load and
+SPConvNets' block builders run unchanged."""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from vgtk.spconv import SphericalPointCloud, SphericalPointCloudPose
+import vgtk.pc as pctk
+from . import functional as L
+from equi_articulated_pose_b200 import ops as _ops
+
+KERNEL_CONDENSE_RATIO = 0.7
+
+
+class BasicSO3Conv(nn.Module):
+    """[b,c1,k,p,a] -> [b,c2,p,a]: out[b,o,p,a] = sum_{c,k} W[o, c*K+k] x[b,c,k,p,a]
+    (reference :21-55).  W keeps the reference layout [dim_out, dim_in*kernel_size] (c major)."""
+
+    def __init__(self, dim_in, dim_out, kernel_size, debug=False):
+        super().__init__()
+        self.dim_in, self.dim_out, self.kernel_size = dim_in, dim_out, kernel_size
+        if debug:
+            self.register_buffer('W', torch.ones(dim_out, dim_in * kernel_size))
+        else:
+            W = torch.empty(dim_out, dim_in, kernel_size)
+            nn.init.xavier_normal_(W, gain=nn.init.calculate_gain('relu'))
+            self.register_parameter('W', nn.Parameter(W.view(dim_out, dim_in * kernel_size)))
+
+    def weight_kc(self):
+        """W re-indexed to the kernels' column order k*Ci + c (autograd-tracked view+copy, tiny)."""
+        return self.W.view(self.dim_out, self.dim_in, self.kernel_size).transpose(1, 2).reshape(self.dim_out, -1)
+
+    def forward_rows(self, rows):
+        """rows [M, K*Ci] (column k*Ci + c) -> [M, dim_out] on the tensor-core GEMM."""
+        return _ops.LinearFn.apply(rows, self.weight_kc(), None)
+
+    def forward(self, x):
+        bs, c, k, npt, na = x.shape
+        rows = x.permute(0, 3, 4, 2, 1).reshape(bs * npt * na, k * c)   # no copy for channels-last views
+        out = self.forward_rows(rows)
+        return out.view(bs, npt, na, self.dim_out).permute(0, 3, 1, 2)
+
+
+class KernelPropagation(nn.Module):
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        raise NotImplementedError("KernelPropagation is built by no shipped model (SURVEY.md 2.2 #7); out of scope")
+
+
+class InterSO3Conv(nn.Module):
+    """[b,c1,p1,a] -> [b,c2,p2,a]: ball-query neighbourhood, kernel-point correlation under the
+    rotation anchors, contraction with W (reference :125-174)."""
+
+    def __init__(self, dim_in, dim_out, kernel_size, stride, radius, sigma, n_neighbor, lazy_sample=True,
+                 pooling=None, kanchor=60):
+        super().__init__()
+        kernels = L.get_sphereical_kernel_points_from_ply(KERNEL_CONDENSE_RATIO * radius, kernel_size)
+        anchors = L.get_anchors(kanchor)
+        self.dim_in, self.dim_out = dim_in, dim_out
+        self.kernel_size = kernels.shape[0]
+        self.stride, self.radius, self.sigma, self.n_neighbor = stride, radius, sigma, n_neighbor
+        self.lazy_sample, self.pooling = lazy_sample, pooling
+        self.basic_conv = BasicSO3Conv(dim_in, dim_out, self.kernel_size)
+        self.register_buffer('anchors', torch.from_numpy(np.ascontiguousarray(anchors)))
+        self.register_buffer('kernels', torch.from_numpy(np.ascontiguousarray(kernels)))
+        self._rk = None
+
+    def rot_kernels(self):
+        if self._rk is None or self._rk.device != self.anchors.device:
+            self._rk = L.rotated_kernels(self.anchors, self.kernels)
+        return self._rk
+
+    def forward(self, x, inter_idx=None, inter_w=None):
+        inter_idx, inter_w, xyz, feats, sample_idx = L.inter_so3conv_grouping(
+            x.xyz, x.feats, self.stride, self.n_neighbor, self.anchors, self.kernels, self.radius, self.sigma,
+            inter_idx, inter_w, self.lazy_sample, pooling=self.pooling, rot_kernels=self.rot_kernels())
+        feats = self.basic_conv(feats)
+        return inter_idx, inter_w, sample_idx, SphericalPointCloud(xyz, feats, self.anchors)
+
+
+class InterSO3PoseConv(InterSO3Conv):
+    """Pose-aware variant (reference :177-322).  With an identity per-point pose -- the only case the
+    shipped configurations produce -- it is bit-identical to InterSO3Conv;
+    a non-identity pose needs the anchor-permuted gather, which is not built yet."""
+
+    def __init__(self, dim_in, dim_out, kernel_size, stride, radius, sigma, n_neighbor, lazy_sample=True,
+                 pooling=None, kanchor=60, permute_modes=0, use_2d=False, use_art_mode=False):
+        super().__init__(dim_in, dim_out, kernel_size, stride, radius, sigma, n_neighbor, lazy_sample, pooling, kanchor)
+        self.permute_modes, self.use_2d, self.use_art_mode = permute_modes, use_2d, use_art_mode
+
+    def forward(self, x, inter_idx=None, inter_w=None):
+        pose = x.pose
+        eye = torch.eye(4, dtype=pose.dtype, device=pose.device)
+        if not torch.equal(pose, eye.expand_as(pose)):
+            raise NotImplementedError("InterSO3PoseConv: only the identity-pose case is implemented")
+        # the reference recomputes the ball query every call and ignores a cached inter_idx (:931,1025)
+        idx, w, sample_idx, out = super().forward(x, None, None)
+        if sample_idx is not None and self.stride > 1:
+            sampled_pose = torch.gather(pose, 1, sample_idx.long().view(*sample_idx.shape, 1, 1).expand(-1, -1, 4, 4))
+        else:
+            sampled_pose = pose
+        return idx, w, sample_idx, SphericalPointCloudPose(out.xyz, out.feats, self.anchors, sampled_pose)
+
+
+class IntraSO3Conv(nn.Module):
+    """Group convolution over the 12 nearest rotation anchors (reference :325-347)."""
+
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        anchors = L.get_anchors()
+        intra_idx = L.get_intra_idx()
+        self.dim_in, self.dim_out = dim_in, dim_out
+        self.kernel_size = intra_idx.shape[1]
+        self.basic_conv = BasicSO3Conv(dim_in, dim_out, self.kernel_size)
+        self.register_buffer('anchors', torch.from_numpy(np.ascontiguousarray(anchors)))
+        self.register_buffer('intra_idx', torch.from_numpy(np.ascontiguousarray(intra_idx)).long())
+
+    def forward(self, x):
+        feats = L.intra_so3conv_grouping(self.intra_idx, x.feats)
+        feats = self.basic_conv(feats)
+        return SphericalPointCloud(x.xyz, feats, self.anchors)
+
+
+class IntraSO3Conv2D(nn.Module):
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        raise NotImplementedError("IntraSO3Conv2D: `use_2d` is never forwarded by the shipped models; out of scope")
+
+
+class PointnetSO3Conv(nn.Module):
+    """Equivariant PointNet pooling head (reference :376-413): anchor-rotated xyz concatenated to
+    the features, 1x1 conv, max over points."""
+
+    def __init__(self, dim_in, dim_out, kanchor=60, return_raw=False):
+        super().__init__()
+        anchors = L.get_anchors(kanchor)
+        self.dim_in, self.dim_out, self.return_raw = dim_in + 3, dim_out, return_raw
+        self.embed = nn.Conv2d(self.dim_in, self.dim_out, 1)
+        self.register_buffer('anchors', torch.from_numpy(np.ascontiguousarray(anchors)))
+
+    def forward(self, x):
+        xyz, feats = x.xyz, x.feats
+        nb, nc, npt, na = feats.shape
+        xyz = xyz - xyz.mean(2, keepdim=True)
+        if na == 1:
+            feats = torch.cat([x.feats, xyz[..., None]], 1)
+        else:
+            xyzr = torch.einsum('aji,bjn->bina', self.anchors, xyz)
+            feats = torch.cat([x.feats, xyzr], 1)
+        feats = self.embed(feats)
+        return feats if self.return_raw else torch.max(feats, 2)[0]
+
+
+class PointnetSO3PoseConv(PointnetSO3Conv):
+    """reference :416-...: identical pooling on a pose-carrying cloud."""
+    pass

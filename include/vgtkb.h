@@ -1,0 +1,152 @@
+/*
+ * vgtkb.h -- C ABI of libvgtkb200.so: the B200 (sm_100a) implementation of the vgtk
+ * SE(3)-equivariant point-convolution hot path of Meowuu7/equi-articulated-pose.
+ *
+ * Drop-in boundary.  Every entry point replaces one function of the reference's pybind
+ * extension modules (or one torch expression of vgtk.{spconv,so3conv}.functional that the
+ * reference evaluates in eager PyTorch); the reference interface each one stands for is cited
+ * as file:line relative to the reference tree.  The binding a reference maintainer would add
+ * is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes; all pointers are DEVICE pointers unless the name ends in
+ *     `_host`; no torch types.  The caller owns and allocates every buffer (the reference's
+ *     pybind wrappers allocated outputs with torch::zeros -- the Python shim does that now).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is what
+ *     the reference used: grouping_cuda_kernel.cu:478 etc.).
+ *   - return value: 0 on success, negative VGTKB_E* on failure; vgtkb_last_error() returns a
+ *     thread-local message.  The reference only printf'd launch errors
+ *     (grouping_cuda_kernel.cu:485-487); here they are reported.
+ *   - index tensors are int32 like the reference's (grouping_cuda.cpp:80-82).
+ *   - feature tensors on the fused path are CHANNELS-LAST: X[B][N][A][C] (row = (b,n,a),
+ *     C contiguous).  The literal 1:1 ops keep the reference layouts ([B,3,N], [B,C,N]).
+ */
+#ifndef VGTKB_H_
+#define VGTKB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VGTKB_OK 0
+#define VGTKB_EINVAL (-1)   /* bad argument (size, alignment, unsupported shape) */
+#define VGTKB_ECUDA (-2)    /* CUDA runtime / launch error */
+#define VGTKB_EUNSUP (-3)   /* feature not available on this device (needs sm_100) */
+
+const char* vgtkb_last_error(void);
+int vgtkb_version(void);                 /* ABI version, bumped on signature changes */
+int vgtkb_device_check(void);            /* VGTKB_OK iff current device is compute capability 10.x */
+
+/* ---------------------------------------------------------------- literal 1:1 ops ---------- */
+
+/* vgtk.cuda.grouping.ball_query  (vgtk/vgtk/cuda/grouping_cuda.cpp:71-86, kernel
+ * grouping_cuda_kernel.cu:67-113).  new_xyz [b,3,m], xyz [b,3,n] fp32 -> idx [b,m,nsample].
+ * First `nsample` support points with d2 < radius^2 in ascending index order; fewer than
+ * nsample-1 hits are repeated cyclically; exactly nsample-1 hits leave the last slot 0;
+ * zero hits give an all-zero row.  idx need not be zeroed by the caller. */
+int vgtkb_ball_query(int b, int n, int m, float radius, int nsample,
+                     const float* new_xyz, const float* xyz, int32_t* idx, void* stream);
+
+/* vgtk.cuda.grouping.furthest_point_sampling  (grouping_cuda.cpp:160-174, kernel
+ * grouping_cuda_kernel.cu:351-466).  xyz [b,3,n] fp32 -> idx [b,m].  Bit-exact including the
+ * block-size dependent tie-break of the reference's shared-memory tree and the |p|^2 <= 1e-3
+ * skip rule. */
+int vgtkb_furthest_point_sampling(int b, int n, int m, const float* xyz, int32_t* idx, void* stream);
+
+/* vgtk.cuda.gathering.gather_points_forward / backward (gathering_cuda.cpp:29-58, kernels
+ * gathering_cuda_kernel.cu:43-98).  points [b,c,n], idx [b,m] -> out [b,c,m];
+ * backward: grad_out [b,c,m] scatter-added into grad_points [b,c,n] (zeroed here). */
+int vgtkb_gather_points_forward(int b, int c, int n, int m, const float* points, const int32_t* idx,
+                                float* out, void* stream);
+int vgtkb_gather_points_backward(int b, int c, int n, int m, const float* grad_out, const int32_t* idx,
+                                 float* grad_points, void* stream);
+
+/* chamfer.forward / chamfer.backward (extensions/chamfer_dist/chamfer_cuda.cpp:22-39, kernels
+ * chamfer.cu:15-145,173-229).  xyz1 [b,n,3], xyz2 [b,m,3] fp32. */
+int vgtkb_chamfer_forward(int b, int n, const float* xyz1, int m, const float* xyz2,
+                          float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, void* stream);
+int vgtkb_chamfer_backward(int b, int n, const float* xyz1, int m, const float* xyz2,
+                           const int32_t* idx1, const int32_t* idx2,
+                           const float* grad_dist1, const float* grad_dist2,
+                           float* grad_xyz1, float* grad_xyz2, void* stream);
+
+/* ---------------------------------------------------------------- fused SO(3) conv path ---- */
+
+/* Kernel-point correlation, materialised (API parity only; the fused path never stores it):
+ * vgtk/vgtk/so3conv/functional.py:2508-2549.  xyz [b,3,n], sample_xyz [b,3,p], idx [b,p,nn],
+ * rot_kernels [a,k,3] (= R_a kappa_k) -> w [b,p,a,k,nn]. */
+int vgtkb_inter_weights(int b, int n, int p, int nn, int a, int k, const float* xyz, const float* sample_xyz,
+                        const int32_t* idx, const float* rot_kernels, float sigma, float* w, void* stream);
+
+/* Inter-anchor grouping = vgtk.cuda.zpconv.inter_zpconv_forward slot (zpconv_cuda.cpp:113-118)
+ * with the semantics of the live torch path: inter_so3conv_grouping_anchor + add_shadow_feature +
+ * inter_zpconv_grouping_naive (so3conv/functional.py:2508-2549, spconv/functional.py:375-406).
+ *   feats X [b,n,a,ci] (channels-last) -> G [b,p,a,k,ci]   (row (b,p,a), column k*ci + c)
+ *   G[b,p,a,k,c] = sum_j relu(1 - |xyz[b,:,idx[b,p,j]] - sample_xyz[b,:,p] - R_a kappa_k|^2 / sigma)
+ *                        * X[b, idx[b,p,j], a, c]
+ * The weights are recomputed on the fly, never stored. */
+int vgtkb_inter_group_forward(int b, int n, int p, int nn, int a, int k, int ci,
+                              const float* xyz, const float* sample_xyz, const int32_t* idx,
+                              const float* rot_kernels, float sigma,
+                              const float* feats, float* grouped, void* stream);
+/* inter_zpconv_backward slot: grad_feats [b,n,a,ci] += scatter of grad_grouped (grad_feats is
+ * accumulated into; the caller zeroes it when needed). */
+int vgtkb_inter_group_backward(int b, int n, int p, int nn, int a, int k, int ci,
+                               const float* xyz, const float* sample_xyz, const int32_t* idx,
+                               const float* rot_kernels, float sigma,
+                               const float* grad_grouped, float* grad_feats, void* stream);
+
+/* Intra-anchor grouping = intra_zpconv_forward slot with the semantics of
+ * intra_so3conv_grouping (so3conv/functional.py:2553-2567):
+ *   Y [rows, a, c] -> G [rows, a, kk, c],  G[r,a,k,c] = Y[r, intra_idx[a,k], c];  rows = b*p.
+ * backward: grad_y[r,a',c] = sum_{(a,k): intra_idx[a,k]=a'} grad_g[r,a,k,c] (deterministic). */
+int vgtkb_intra_group_forward(int64_t rows, int a, int kk, int c, const int32_t* intra_idx,
+                              const float* y, float* grouped, void* stream);
+int vgtkb_intra_group_backward(int64_t rows, int a, int kk, int c, const int32_t* intra_idx,
+                               const float* grad_grouped, float* grad_y, void* stream);
+
+/* Point-row gather used by the skip connection (zptk.functional.batched_index_select(feats, 2,
+ * sample_idx), SPConvNets/utils/base_so3conv.py:212-213) on channels-last rows of `width`
+ * floats: out[b,j,:] = x[b, idx[b,j], :]; backward accumulates (atomics) into grad_x. */
+int vgtkb_row_gather_forward(int b, int n, int m, int width, const float* x, const int32_t* idx,
+                             float* out, void* stream);
+int vgtkb_row_gather_backward(int b, int n, int m, int width, const float* grad_out, const int32_t* idx,
+                              float* grad_x, void* stream);
+
+/* Anchor/kernel contraction = BasicSO3Conv.forward (so3conv/modules.py:48-55) and the 1x1 skip
+ * conv, as row-major GEMMs.
+ *   vgtkb_gemm_nt: C[M,N] = A[M,K] * B[N,K]^T (+ bias[N])
+ *   vgtkb_gemm_tn: C[M,N] (+)= A[R,M]^T * B[R,N]   (weight gradients; reduction over rows R)
+ * `mode`: 0 = fp32 FFMA (CUDA cores), 1 = tcgen05 3xTF32 (fp32-equivalent, sm_100a tensor cores),
+ *         2 = tcgen05 single-pass TF32 (fast, ~1e-3 relative). */
+int vgtkb_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const float* bias,
+                  float* C, int mode, void* stream);
+int vgtkb_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C,
+                  int accumulate, int mode, void* stream);
+
+/* Normalisation + leaky_relu on channels-last rows X[groups][rows_per_group][c].
+ * groups == 1 : BatchNorm2d training statistics (base_so3conv.py:113,125-131)
+ * groups == b : InstanceNorm2d(affine=False)            (base_so3conv.py:47-64)
+ * stats [groups][2][c] = (mean, invstd); sums are accumulated in fp64 scratch [groups][2][c]. */
+int vgtkb_norm_stats(int groups, int64_t rows_per_group, int c, const float* x, float eps,
+                     double* scratch, float* stats, float* running_mean, float* running_var,
+                     float momentum, void* stream);
+/* y = leaky_relu((x-mean)*invstd*gamma+beta, slope) [+ residual]; gamma/beta may be NULL. */
+int vgtkb_norm_act_forward(int groups, int64_t rows_per_group, int c, const float* x, const float* stats,
+                           const float* gamma, const float* beta, float slope, const float* residual,
+                           float* y, void* stream);
+/* backward of the above w.r.t. x, gamma, beta.  grad_gamma/grad_beta [c] may be NULL (no affine).
+ * scratch: fp64 [groups][2][c]. */
+int vgtkb_norm_act_backward(int groups, int64_t rows_per_group, int c, const float* x, const float* stats,
+                            const float* gamma, const float* beta, float slope, const float* grad_y,
+                            double* scratch, float* grad_x, float* grad_gamma, float* grad_beta, void* stream);
+
+/* column sums of a row-major [rows, c] matrix (bias gradient of the skip conv) */
+int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGTKB_H_ */

@@ -1,0 +1,117 @@
+"""Generate the committed golden fixtures by RUNNING THE REFERENCE'S OWN PYTHON in place.
+
+    python tests/golden/make_golden.py          (needs /root/reference; CPU only)
+
+The reference ships no golden vectors for this path, so parity is
+pinned on outputs of the reference itself, imported through oracle/ref_harness.py.
+Writes (all small):
+  equi_articulated_pose_b200/data/so3_constants.npz  anchors Rs [60,3,3] f32, intra_idx [60,12] i64,
+                                                     kpsphere24 [24,3] f32 (+ icosahedron verts/faces)
+  tests/golden/ref_blocks_small.npz   2 stacked separable blocks, fwd + bwd, train mode
+  tests/golden/ref_intra_small.npz    one IntraSO3Conv (BASELINE config 1a, reduced size)
+  tests/golden/ref_weights_small.npz  inter_so3conv_grouping_anchor + grouping einsum
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness as H  # noqa: E402
+from oracle import so3 as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+DATA = os.path.join(ROOT, "equi_articulated_pose_b200", "data")
+
+
+def small_params():
+    """Two separable layers in one BasicSO3ConvBlock + one strided block; N=64."""
+    def layer(ci, co, stride, radius, sigma, nn, lazy):
+        return {'type': 'separable_block', 'args': {
+            'dim_in': ci, 'dim_out': co, 'kernel_size': 1, 'stride': stride, 'radius': radius, 'sigma': sigma,
+            'n_neighbor': nn, 'lazy_sample': lazy, 'dropout_rate': 0.0, 'multiplier': 2,
+            'activation': 'leaky_relu', 'pooling': None, 'kanchor': 60, 'norm': 'BatchNorm2d'}}
+    return [[layer(1, 8, 2, 0.6, 0.18, 16, False), layer(8, 8, 1, 0.8, 0.32, 8, True)],
+            [layer(8, 16, 2, 1.0, 0.5, 12, True)]]
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    M = H.import_blocks()
+    import vgtk.so3conv as sptk
+    import vgtk.so3conv.functional as L
+    import vgtk.spconv as zptk
+    import vgtk.pc as pctk
+
+    os.makedirs(DATA, exist_ok=True)
+    # ---- constants ------------------------------------------------------------------
+    Rs = L.get_anchors(60)
+    Ri = L.get_intra_idx()
+    anchors_dir = os.path.join(H.REF, "vgtk", "vgtk", "data", "anchors")
+    kp24 = pctk.load_ply(os.path.join(anchors_dir, "kpsphere24.ply")).astype("float32")
+    v12, f12 = H.read_ply(os.path.join(anchors_dir, "sphere12.ply"))
+    np.savez(os.path.join(DATA, "so3_constants.npz"), anchors=Rs.astype(np.float32), intra_idx=Ri.astype(np.int64),
+             kpsphere24=kp24, ico_vertices=v12, ico_faces=f12)
+    print("constants", Rs.shape, Ri.shape, kp24.shape)
+
+    # ---- weights + grouping ---------------------------------------------------------
+    g = torch.Generator().manual_seed(11)
+    gxyz = (torch.rand(2, 3, 5, 7, generator=g) - 0.5) * 0.5
+    kern = torch.from_numpy(L.get_sphereical_kernel_points_from_ply(0.7 * 0.4, 1))
+    anc = torch.from_numpy(Rs)
+    w = L.inter_so3conv_grouping_anchor(gxyz, anc, kern, 0.08)
+    feats = torch.randn(2, 3, 9, 60, generator=g)
+    idx = torch.randint(0, 9, (2, 5, 7), generator=g, dtype=torch.int32)
+    G = zptk.inter_zpconv_grouping_naive(idx, w, zptk.functional.add_shadow_feature(feats))
+    np.savez(os.path.join(GOLD, "ref_weights_small.npz"), grouped_xyz=gxyz.numpy(), kernels=kern.numpy(),
+             sigma=np.float32(0.08), inter_w=w.numpy(), feats=feats.numpy(), idx=idx.numpy(), grouped=G.numpy())
+
+    # ---- single intra conv (config 1a, reduced) -------------------------------------
+    torch.manual_seed(0)
+    conv = sptk.IntraSO3Conv(16, 24)
+    f = torch.randn(1, 16, 32, 60, generator=g)
+    x = zptk.SphericalPointCloud(torch.rand(1, 3, 32, generator=g) - 0.5, f, None)
+    out = conv(x).feats
+    np.savez(os.path.join(GOLD, "ref_intra_small.npz"), W=conv.basic_conv.W.detach().numpy(), feats=f.numpy(),
+             out=out.detach().numpy())
+
+    # ---- stacked separable blocks, fwd + bwd ----------------------------------------
+    params = small_params()
+    torch.manual_seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        backbone = torch.nn.ModuleList([M.BasicSO3ConvBlock(p) for p in params])
+    with torch.no_grad():
+        for n, p in backbone.named_parameters():
+            if n.endswith('norm.weight'):
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+            if n.endswith('norm.bias'):
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    backbone.train()
+    pts = O.synthetic_cloud(2, 64, seed=2001)
+    xyz = pts.permute(0, 2, 1).contiguous()
+    x = zptk.SphericalPointCloud(xyz, sptk.get_occupancy_features(pts, 60, False), None)
+    state = {('backbone.' + k): v.detach().clone().numpy() for k, v in backbone.state_dict().items()
+             if not k.endswith(('anchors', 'kernels', 'intra_idx', 'num_batches_tracked'))}
+    for blk in backbone:
+        x = blk(x)
+    loss = x.feats.square().mean()
+    loss.backward()
+    out = {'in_points': pts.numpy(), 'out_feats': x.feats.detach().numpy(), 'out_xyz': x.xyz.detach().numpy(),
+           'loss': loss.detach().numpy()}
+    for k, v in state.items():
+        out['state/' + k] = v
+    for n, p in backbone.named_parameters():
+        out['grad/backbone.' + n] = p.grad.numpy()
+    for k, v in backbone.state_dict().items():
+        if k.endswith(('running_mean', 'running_var')):
+            out['after/backbone.' + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLD, "ref_blocks_small.npz"), **out)
+    print("blocks", x.feats.shape, float(loss))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,204 @@
+"""CPU suite: pin the oracle (oracle/) against the committed outputs of the reference's own
+Python (tests/golden/, produced by tests/golden/make_golden.py) and against the derived
+known-answer tests of SURVEY.md appendix C."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cops, so3 as O
+from equi_articulated_pose_b200 import so3_constants as C
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+# ---------------------------------------------------------------- constants (appendix C.1, C.2)
+def test_anchor_fingerprints():
+    Rs, Ri = C.anchors_all(), C.intra_idx()
+    assert Rs.dtype == np.float32 and Rs.shape == (60, 3, 3)
+    assert hashlib.sha256(Rs.tobytes()).hexdigest()[:16] == "a2c584147246900d"
+    assert hashlib.sha256(Ri.astype(np.int64).tobytes()).hexdigest()[:16] == "d1c64694466d57e7"
+    assert (Rs[29] == np.eye(3, dtype=np.float32)).all()
+    assert Ri[0].tolist() == [10, 33, 13, 15, 56, 30, 59, 8, 44, 0, 45, 26]
+    assert Ri[29].tolist() == [44, 31, 32, 13, 42, 43, 30, 14, 12, 29, 28, 27]
+    assert int(Ri.sum()) == 21240
+
+
+def test_anchor_group_structure():
+    Rs, Ri = C.anchors_all().astype(np.float64), C.intra_idx()
+    prod = np.einsum('aij,bjk->abik', Rs, Rs).reshape(3600, 9)
+    d = ((prod[:, None, :] - Rs.reshape(1, 60, 9)) ** 2).sum(-1).min(1)
+    assert d.max() < 1e-10                                     # closed under multiplication
+    for k in range(12):
+        assert sorted(Ri[:, k].tolist()) == list(range(60))    # every column is a permutation
+    assert (Ri[:, 9] == np.arange(60)).all()                   # column 9 = identity
+    assert all(len(set(r.tolist())) == 12 for r in Ri)
+
+
+def test_anchor_derivation_matches_table():
+    assert np.abs(C.derive_anchor_group() - C.anchors_all()).max() < 1e-6
+    Ri = C.intra_idx()
+    assert (C.derive_intra_idx(C.anchors_all().astype(np.float64), Ri[0]) == Ri).all()
+
+
+def test_select_anchor():
+    assert C.get_anchors(1).shape == (1, 3, 3) and (C.get_anchors(1)[0] == np.eye(3)).all()
+    assert C.get_anchors(20).shape == (20, 3, 3) and C.get_anchors(40).shape == (40, 3, 3)
+
+
+def test_kernel_points(golden_dir):
+    g = _load(golden_dir, "ref_weights_small.npz")
+    assert np.array_equal(O.scaled_kernel_points(C.kernel_points_base(), 0.4), g["kernels"])
+    assert np.array_equal(C.scaled_kernel_points(0.7 * 0.4), g["kernels"])
+
+
+# ---------------------------------------------------------------- opt_n_threads (appendix C.6)
+def test_opt_n_threads_matches_integer_rule():
+    for n, want in ((380, 256), (512, 512), (1000, 512), (1024, 1024), (4096, 1024), (1, 1), (3, 2)):
+        assert cops.opt_n_threads(n) == want
+    for n in range(1, 20000):
+        p = 1
+        while p * 2 <= n and p < 1024:
+            p *= 2
+        assert cops.opt_n_threads(n) == p, n
+
+
+# ---------------------------------------------------------------- index ops: semantics by hand
+def test_ball_query_padding_rules():
+    xyz = np.zeros((1, 3, 6), np.float32)
+    xyz[0, 0] = [0.0, 0.05, 0.5, 0.06, 0.07, 0.9]
+    q = np.zeros((1, 3, 1), np.float32)
+    # 4 hits (0,1,3,4) with nsample=8 -> cyclic repetition
+    assert cops.ball_query(q, xyz, 0.1, 8)[0, 0].tolist() == [0, 1, 3, 4, 0, 1, 3, 4]
+    # nsample=5: cnt == nsample-1 -> last slot stays 0
+    assert cops.ball_query(q, xyz, 0.1, 5)[0, 0].tolist() == [0, 1, 3, 4, 0]
+    # nsample=3: first three in index order
+    assert cops.ball_query(q, xyz, 0.1, 3)[0, 0].tolist() == [0, 1, 3]
+    # no hit at all -> zeros; strict '<'
+    far = np.full((1, 3, 1), 5.0, np.float32)
+    assert cops.ball_query(far, xyz, 0.1, 4)[0, 0].tolist() == [0, 0, 0, 0]
+    q2 = np.zeros((1, 3, 1), np.float32); q2[0, 0, 0] = 0.25
+    x2 = np.zeros((1, 3, 2), np.float32); x2[0, 0] = [0.0, 0.5]
+    assert cops.ball_query(q2, x2, 0.25, 2)[0, 0].tolist() == [0, 0]      # d2 == r2 is not a hit
+
+
+def test_fps_rules():
+    g = np.random.default_rng(0)
+    xyz = g.normal(size=(2, 3, 100)).astype(np.float32)
+    idx = cops.furthest_point_sampling(xyz, 20)
+    assert (idx[:, 0] == 0).all()
+    # brute-force restatement without the block structure (valid when there are no exact ties)
+    for b in range(2):
+        P = xyz[b].T
+        temp = np.full(100, 1e10, np.float32)
+        old, out = 0, [0]
+        for _ in range(19):
+            d = ((P - P[old]) ** 2).sum(1).astype(np.float32)
+            temp = np.minimum(temp, d)
+            old = int(temp.argmax()); out.append(old)
+        assert out == idx[b].tolist()
+    # points with |p|^2 <= 1e-3 are never selected (except the forced start index 0)
+    xyz[0, :, 5:50] *= 1e-3
+    idx = cops.furthest_point_sampling(xyz, 40)
+    assert not set(idx[0, 1:].tolist()) & set(range(5, 50))
+    # all points skipped -> the tree returns index 0 forever
+    z = np.zeros((1, 3, 16), np.float32)
+    assert cops.furthest_point_sampling(z, 5)[0].tolist() == [0, 0, 0, 0, 0]
+
+
+def test_fps_tie_break_is_bit_reversed_thread_order():
+    # 8 points, block size 8: points 1 and 4 are equidistant from point 0 and everything else is closer.
+    xyz = np.zeros((1, 3, 8), np.float32)
+    xyz[0, 0] = [1.0, 3.0, 1.2, 1.3, -1.0, 1.1, 1.4, 1.5]     # |x - 1| = 2 for k=1 and k=4
+    xyz[0, 1] = 0.5
+    idx = cops.furthest_point_sampling(xyz, 2)
+    # tree: stride 4 pairs (0,4)(1,5).. -> slot0 holds k=4, slot1 holds k=1; final stride 1: tie -> left -> k=4
+    assert idx[0].tolist() == [0, 4]
+
+
+def test_gather_and_chamfer_small():
+    g = np.random.default_rng(1)
+    pts = g.normal(size=(2, 3, 7)).astype(np.float32)
+    idx = g.integers(0, 7, size=(2, 5)).astype(np.int32)
+    out = cops.gather_points_forward(pts, idx)
+    assert np.array_equal(out, np.take_along_axis(pts, idx[:, None, :].repeat(3, 1), 2))
+    back = cops.gather_points_backward(out, idx, 7)
+    ref = np.zeros_like(pts)
+    for b in range(2):
+        for j in range(5):
+            ref[b, :, idx[b, j]] += out[b, :, j]
+    assert np.allclose(back, ref)
+    a = g.normal(size=(2, 9, 3)).astype(np.float32)
+    c = g.normal(size=(2, 11, 3)).astype(np.float32)
+    d1, d2, i1, i2 = cops.chamfer_forward(a, c)
+    D = ((a[:, :, None, :] - c[:, None, :, :]) ** 2).sum(-1)
+    assert np.array_equal(i1, D.argmin(2)) and np.array_equal(i2, D.argmin(1))
+    assert np.allclose(d1, D.min(2), rtol=1e-6) and np.allclose(d2, D.min(1), rtol=1e-6)
+    # duplicate targets: the lowest index wins
+    c[:, 5] = c[:, 2]
+    _, _, i1, _ = cops.chamfer_forward(a, c)
+    assert not (i1 == 5).any()
+
+
+def test_chamfer_backward_matches_autograd():
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(2, 6, 3, generator=g, requires_grad=True)
+    c = torch.randn(2, 8, 3, generator=g, requires_grad=True)
+    D = ((a[:, :, None] - c[:, None]) ** 2).sum(-1)
+    w1, w2 = torch.randn(2, 6, generator=g), torch.randn(2, 8, generator=g)
+    ((D.min(2)[0] * w1).sum() + (D.min(1)[0] * w2).sum()).backward()
+    _, _, i1, i2 = cops.chamfer_forward(a.detach().numpy(), c.detach().numpy())
+    g1, g2 = cops.chamfer_backward(a.detach().numpy(), c.detach().numpy(), i1, i2, w1.numpy(), w2.numpy())
+    assert np.allclose(g1, a.grad.numpy(), atol=1e-5) and np.allclose(g2, c.grad.numpy(), atol=1e-5)
+
+
+# ---------------------------------------------------------------- float path vs the reference's outputs
+def test_anchor_weights_and_grouping_match_reference(golden_dir):
+    g = _load(golden_dir, "ref_weights_small.npz")
+    anchors = torch.from_numpy(C.anchors_all())
+    w = O.anchor_weights(torch.from_numpy(g["grouped_xyz"]), anchors, torch.from_numpy(g["kernels"]), float(g["sigma"]))
+    assert torch.allclose(w, torch.from_numpy(g["inter_w"]), atol=1e-6)
+    G = O.inter_group_feats(torch.from_numpy(g["idx"]), w, torch.from_numpy(g["feats"]))
+    assert torch.allclose(G, torch.from_numpy(g["grouped"]), atol=1e-5)
+
+
+def test_intra_conv_matches_reference(golden_dir):
+    g = _load(golden_dir, "ref_intra_small.npz")
+    out = O.basic_conv(torch.from_numpy(g["W"]),
+                       O.intra_group_feats(torch.from_numpy(C.intra_idx()), torch.from_numpy(g["feats"])))
+    assert torch.allclose(out, torch.from_numpy(g["out"]), atol=1e-5)
+
+
+def test_blocks_forward_backward_match_reference(golden_dir):
+    import sys
+    sys.path.insert(0, golden_dir)
+    from make_golden import small_params
+    g = _load(golden_dir, "ref_blocks_small.npz")
+    sd = {k[len("state/"):]: torch.from_numpy(g[k]).clone() for k in g.files if k.startswith("state/")}
+    for k in sd:
+        if k.endswith(("W", "weight", "bias")) and "running" not in k:
+            sd[k].requires_grad_(True)
+    pts = torch.from_numpy(g["in_points"])
+    xyz = pts.permute(0, 2, 1).contiguous()
+    feats = torch.ones(pts.shape[0], 1, pts.shape[1], 60)
+    oxyz, of = O.backbone_forward(sd, small_params(), xyz, feats, torch.from_numpy(C.anchors_all()),
+                                  torch.from_numpy(C.intra_idx()), C.kernel_points_base(), training=True)
+    ref = torch.from_numpy(g["out_feats"])
+    assert torch.equal(oxyz, torch.from_numpy(g["out_xyz"]))
+    assert (of - ref).abs().max() / ref.abs().max() < 1e-5
+    loss = of.square().mean()
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    for k in g.files:
+        if k.startswith("grad/"):
+            name = k[len("grad/"):]
+            gr, rr = sd[name].grad, torch.from_numpy(g[k])
+            # the first skip branch normalises a constant tensor: its true gradient is 0 and both sides hold rounding noise ~1e-6
+            assert (gr - rr).abs().max() <= 2e-4 * rr.abs().max() + 5e-6, name
+        if k.startswith("after/"):
+            name = k[len("after/"):]
+            assert torch.allclose(sd[name], torch.from_numpy(g[k]), atol=1e-5), name
