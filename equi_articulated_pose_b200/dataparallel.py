@@ -1,0 +1,81 @@
+"""Data-parallel plumbing: one process per GPU, clouds sharded over ranks, gradient all-reduce.
+
+The reference trains with DistributedDataParallel over NCCL, one cloud per rank
+(SPConvNets/trainer_unsup_arti_align.py:52-56,203-208,430-440): the convolution is per-sample,
+so the only exchange step of the path is the gradient all-reduce (7.67 M fp32 = 30.7 MB for the
+classic backbone).  Here the gradients live in ONE flat fp32 bucket that the parameters' .grad
+tensors are views of, so a step needs exactly one NCCL all-reduce (NVLink 5 / NVSwitch, NVLS
+in-switch reduction when available) and no flatten/unflatten copies.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment (torchrun).  -> (rank, local_rank, world)"""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, local_rank, world
+
+
+def shard_range(total, rank, world):
+    """Contiguous [lo, hi) slice of `total` clouds owned by `rank` (DistributedSampler-like, no padding)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class FlatGradBucket:
+    """All gradients of `params` as views of one contiguous fp32 buffer."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(total, dtype=torch.float32, device=ref.device)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero_(self):
+        self.flat.zero_()
+        for p in self.params:           # autograd may have replaced a view (first accumulation): re-attach
+            if p.grad is None or p.grad.untyped_storage().data_ptr() != self.flat.untyped_storage().data_ptr():
+                self._reattach()
+                break
+
+    def _reattach(self):
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            view = self.flat[off:off + n].view_as(p)
+            if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+            p.grad = view
+            off += n
+
+    def all_reduce_mean(self, group=None):
+        """One collective for the whole model; averages over ranks like DDP does."""
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return
+        self._reattach()
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        self.flat.div_(dist.get_world_size(group))
+
+    def nbytes(self):
+        return self.flat.numel() * 4

@@ -94,11 +94,24 @@ def call(name, device, *args):
     lib = load()
     _ensure_device(device.index if device.index is not None else torch.cuda.current_device())
     with torch.cuda.device(device):
-        stream = torch.cuda.current_stream().cuda_stream
-        rc = getattr(lib, name)(*args, stream)
+        cur = torch.cuda.current_stream()
+        if PROFILE is not None:
+            # CUDA events on the launching stream around this entry point (bench.py roofline leg)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
+            rc = getattr(lib, name)(*args, cur.cuda_stream)
+            e1.record(cur)
+            PROFILE.append((name, args, e0, e1))
+        else:
+            rc = getattr(lib, name)(*args, cur.cuda_stream)
     if rc != 0:
         raise VgtkbError(f"{name} failed ({rc}): {lib.vgtkb_last_error().decode()}")
     COUNTERS["launch_calls"] += 1
+    COUNTERS["kernels"] += KERNELS_PER_CALL.get(name, 1)
 
 
-COUNTERS = {"launch_calls": 0}
+COUNTERS = {"launch_calls": 0, "kernels": 0}
+PROFILE = None  # set to a list to record (entry point, args, start event, end event) per call
+# device kernels launched per entry point (memsets not counted); used for bench.py's gpu_launches
+KERNELS_PER_CALL = {"vgtkb_chamfer_forward": 2, "vgtkb_chamfer_backward": 4, "vgtkb_norm_stats": 2,
+                    "vgtkb_norm_act_backward": 3, "vgtkb_col_sum": 2}

@@ -17,6 +17,7 @@ baseline.  The product never imports them.
 """
 import os
 import re
+import shutil
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -65,6 +66,7 @@ def build(names=None, verbose=False):
         load(name=name, sources=srcs, build_directory=scratch, verbose=verbose,
              extra_cuda_cflags=["-O3", "-lineinfo"], is_python_module=False)
         os.replace(os.path.join(scratch, name + ".so"), so)
+        shutil.rmtree(scratch, ignore_errors=True)      # patched source copies and objects do not stay around
         built[name] = so
     return built
 

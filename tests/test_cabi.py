@@ -1,0 +1,65 @@
+"""CPU suite: the C-ABI library builds, loads and exports every symbol include/vgtkb.h declares,
+and the Python binding declares a prototype for each of them.  No compute call is made here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vgtkb.h")
+CSRC = os.path.join(ROOT, "equi_articulated_pose_b200", "csrc")
+
+
+def declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(vgtkb_[a-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    subprocess.check_call(["make", "-C", CSRC, "-j", "8"], stdout=subprocess.DEVNULL)
+    from equi_articulated_pose_b200 import lib
+    assert os.path.exists(lib.LIB_PATH)
+    return lib.LIB_PATH
+
+
+def test_header_declares_the_boundary():
+    syms = declared_symbols()
+    for must in ("vgtkb_ball_query", "vgtkb_furthest_point_sampling", "vgtkb_gather_points_forward",
+                 "vgtkb_gather_points_backward", "vgtkb_chamfer_forward", "vgtkb_chamfer_backward",
+                 "vgtkb_inter_group_forward", "vgtkb_intra_group_forward", "vgtkb_gemm_nt"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    so = ctypes.CDLL(libpath)
+    for s in declared_symbols():
+        assert hasattr(so, s), f"{s} declared in vgtkb.h but not exported"
+
+
+def test_binding_covers_every_declared_symbol(libpath):
+    from equi_articulated_pose_b200 import lib
+    bound = set(lib.SIGNATURES) | set(lib.NO_STATUS)
+    assert set(declared_symbols()) == bound
+    so = lib.load()
+    assert so.vgtkb_version() == lib.ABI_VERSION
+    assert isinstance(so.vgtkb_last_error(), bytes)
+
+
+def test_ops_refuse_cpu_tensors(libpath):
+    """No CPU fallback: a CPU tensor (or a missing device) raises instead of computing."""
+    import torch
+    from equi_articulated_pose_b200 import ops, lib
+    xyz = torch.zeros(1, 3, 8)
+    with pytest.raises((lib.VgtkbError, RuntimeError, AssertionError)):
+        ops.ball_query(xyz, xyz, 0.1, 4)
+
+
+def test_sass_has_blackwell_paths(libpath):
+    """The shipped binary is sm_100a code with TMA bulk copies (UBLKCP) in it."""
+    out = subprocess.run(["cuobjdump", "-sass", libpath], capture_output=True, text=True).stdout
+    assert "sm_100a" in out or "SM100" in out.upper()
+    assert "UBLKCP" in out
