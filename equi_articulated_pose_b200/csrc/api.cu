@@ -18,7 +18,7 @@ int sgemm_nt(int64_t M, int N, int K, const float* A, const float* B, const floa
 int sgemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C, int accumulate, cudaStream_t st);
 // gemm_tc.cu: return VGTKB_EUNSUP (without setting an error) when the shape is not covered
 int tc_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const float* bias, float* C, int passes,
-               cudaStream_t st);
+               float* workspace, cudaStream_t st);
 int tc_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C, int accumulate, int passes,
                cudaStream_t st);
 
@@ -42,13 +42,13 @@ extern "C" int vgtkb_device_check(void) {
 }
 
 extern "C" int vgtkb_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const float* bias, float* C,
-                             int mode, void* stream) {
+                             int mode, float* workspace, void* stream) {
     VGTKB_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_nt: bad size");
     VGTKB_REQUIRE(mode >= 0 && mode <= 2, "gemm_nt: bad mode %d", mode);
     if (M == 0) return VGTKB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode != 0) {
-        const int rc = tc_gemm_nt(M, N, K, A, B, bias, C, mode == 1 ? 3 : 1, st);
+        const int rc = tc_gemm_nt(M, N, K, A, B, bias, C, mode == 1 ? 3 : 1, workspace, st);
         if (rc != VGTKB_EUNSUP) return rc;
     }
     return sgemm_nt(M, N, K, A, B, bias, C, st);

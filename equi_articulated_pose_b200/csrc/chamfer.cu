@@ -61,7 +61,8 @@ chamfer_nn_kernel(int n, const float* __restrict__ xyz1, int m, const float* __r
             const float bx = buf[k * 3 + 0], by = buf[k * 3 + 1], bz = buf[k * 3 + 2];
 #pragma unroll
             for (int i = 0; i < CH_QPT; ++i) {
-                const float d = sq3(bx - x1[i], by - y1[i], bz - z1[i]);
+                // reference SASS (all 43 sites): FMUL on y, FFMA x, FFMA z -> fma(z,z,fma(x,x,y*y))
+                const float d = sq3(by - y1[i], bx - x1[i], bz - z1[i]);
                 const bool take = (k2 + k == 0) || d < best[i];
                 best[i] = take ? d : best[i];
                 besti[i] = take ? k2 + k : besti[i];

@@ -118,8 +118,10 @@ def gemm_nt(a, b, bias=None, mode=None):
     n = b.shape[0]
     assert b.shape[1] == k
     c = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    mode = _GEMM_MODE if mode is None else mode
+    ws = torch.empty(2 * n * k, dtype=torch.float32, device=a.device) if mode == 1 else None   # hi/lo split of b
     call("vgtkb_gemm_nt", a.device, m, n, k, ptr(a), ptr(b), ptr(bias.contiguous()) if bias is not None else None,
-         ptr(c), _GEMM_MODE if mode is None else mode)
+         ptr(c), mode, ptr(ws))
     return c
 
 

@@ -120,9 +120,11 @@ int vgtkb_row_gather_backward(int b, int n, int m, int width, const float* grad_
  *   vgtkb_gemm_nt: C[M,N] = A[M,K] * B[N,K]^T (+ bias[N])
  *   vgtkb_gemm_tn: C[M,N] (+)= A[R,M]^T * B[R,N]   (weight gradients; reduction over rows R)
  * `mode`: 0 = fp32 FFMA (CUDA cores), 1 = tcgen05 3xTF32 (fp32-equivalent, sm_100a tensor cores),
- *         2 = tcgen05 single-pass TF32 (fast, ~1e-3 relative). */
+ *         2 = tcgen05 single-pass TF32 (fast, ~1e-3 relative).
+ * `workspace` (gemm_nt, mode 1): device scratch of 2*N*K floats for the hi/lo split of B; when NULL
+ * the library allocates it stream-ordered (cudaMallocAsync), which is slower. */
 int vgtkb_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const float* bias,
-                  float* C, int mode, void* stream);
+                  float* C, int mode, float* workspace, void* stream);
 int vgtkb_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C,
                   int accumulate, int mode, void* stream);
 

@@ -141,7 +141,9 @@ static void chamfer_dir(int b, int n, const float* xyz1, int m, const float* xyz
             int besti = 0;
             for (int k = 0; k < m; ++k) {
                 const float* p = xyz2 + ((size_t)i * m + k) * 3;
-                const float dd = sq3(p[0] - x1, p[1] - y1, p[2] - z1);
+                /* recompiled reference (nvcc 12.9, sm_100a), every site of chamfer_dist_kernel:
+                 * FMUL y*y, FFMA x, FFMA z  ->  fma(z,z,fma(x,x,y*y)) */
+                const float dd = sq3(p[1] - y1, p[0] - x1, p[2] - z1);
                 if (k == 0 || dd < best) { best = dd; besti = k; }
             }
             dist[(size_t)i * n + j] = m > 0 ? best : 0.f;

@@ -33,7 +33,8 @@ def scaled_kernel_points(base_points, radius):
 def ball_query(query_xyz, support_xyz, radius, n_sample):
     """vgtk/vgtk/spconv/functional.py:341-350 + pc/sample.py:54-59 -> idx [B,P,nn] (int32)
     and grouped support coordinates [B,3,P,nn] (the appended shadow point is never indexed)."""
-    idx = torch.from_numpy(cops.ball_query(query_xyz.detach().numpy(), support_xyz.detach().numpy(), radius, n_sample))
+    idx = torch.from_numpy(cops.ball_query(query_xyz.detach().float().numpy(), support_xyz.detach().float().numpy(),
+                                           radius, n_sample))
     b, p, nn = idx.shape
     g = torch.gather(support_xyz, 2, idx.view(b, 1, -1).expand(-1, 3, -1).long()).view(b, 3, p, nn)
     return idx, g
@@ -43,7 +44,7 @@ def furthest_sample_index(xyz, n_sample, lazy_sample):
     """vgtk/vgtk/pc/sample.py:63-72."""
     if xyz.shape[2] == n_sample or lazy_sample:
         return torch.arange(n_sample, dtype=torch.int32).view(1, -1).expand(xyz.shape[0], -1).contiguous()
-    return torch.from_numpy(cops.furthest_point_sampling(xyz.detach().numpy(), n_sample))
+    return torch.from_numpy(cops.furthest_point_sampling(xyz.detach().float().numpy(), n_sample))
 
 
 def ball_grouping(xyz, stride, radius, n_neighbor, lazy_sample=True):
@@ -102,7 +103,7 @@ def _bn(x, sd, prefix, training, momentum=0.1, eps=1e-5):
 def inter_block(sd, prefix, args, xyz, feats, anchors, base_kp, training=True):
     """SPConvNets/utils/base_so3conv.py:93-132 (InterSO3ConvBlock with norm=BatchNorm2d,
     activation=leaky_relu) around vgtk/vgtk/so3conv/modules.py:125-174."""
-    kernels = torch.from_numpy(scaled_kernel_points(base_kp, args['radius']))
+    kernels = torch.from_numpy(scaled_kernel_points(base_kp, args['radius'])).to(feats.dtype)
     gxyz, idx, sidx, new_xyz = ball_grouping(xyz, args['stride'], args['radius'], args['n_neighbor'],
                                              args.get('lazy_sample', True))
     w = anchor_weights(gxyz, anchors, kernels, args['sigma'])
