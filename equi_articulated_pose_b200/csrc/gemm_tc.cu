@@ -5,17 +5,24 @@
 //   tc_gemm_tn : C[Mo,No] (+)= A[R,Mo]^T * B[R,No]             (weight gradient, split over R)
 //
 // fp32 in, fp32 out.  `passes` = 3 is the fp32-parity mode (3xTF32: operands split into a 19-bit
-// head and an exact fp32 remainder, three kind::tf32 MMAs per k-step accumulate hi*hi + lo*hi +
-// hi*lo in fp32 TMEM); `passes` = 1 is single-pass TF32.
+// head and an exact fp32 remainder, three kind::tf32 MMAs per k-step give hi*hi + lo*hi + hi*lo);
+// `passes` = 1 is single-pass TF32.
 //
-// Kernel shape (both): persistent CTAs (one per SM), warp-specialised:
-//   warps 0-3   epilogue: tcgen05.ld accumulator rows -> registers -> global
-//   warp  4     one elected thread issues tcgen05.mma; owns the TMEM allocation
-//   warps 5-12  operand producers: coalesced float4 loads of the activation operand, hi/lo split in
-//               registers, st.shared into the 128B-swizzled K-major (nt) / MN-major (tn) canonical
-//               layout; the weight operand of the nt kernel arrives pre-split through TMA
-// mbarrier rings: full/empty per smem stage, full/empty per TMEM accumulator (double buffered so the
-// epilogue of tile i overlaps the MMAs of tile i+1).
+// The TMEM accumulator rounds toward zero on every accumulate (measured: a shrink proportional to
+// the number of MMAs).  So the tensor core only ever accumulates a short CHUNK of the reduction
+// (chunk_kb k-blocks of 32) in TMEM; the epilogue warps drain every chunk with tcgen05.ld and keep
+// the running sum in fp32 registers with round-to-nearest adds.  Two TMEM buffers let chunk c+1
+// accumulate while chunk c is drained.
+//
+// Kernel shape (both kernels): persistent CTAs, one per SM, 14 warps, warp-specialised, register
+// file re-partitioned with setmaxnreg:
+//   warps 0-7   epilogue (lane quadrant = warp % 4, column half = warp / 4): tcgen05.ld + FADD into
+//               BN/2 register accumulators per thread; stores / red.global.add at the end of a tile
+//   warps 8-11  converters: hi/lo split of the raw fp32 tile the TMA delivered, in place in shared memory
+//   warp  12    one elected thread issues tcgen05.mma; owns the TMEM allocation
+//   warp  13    one elected thread issues the TMA loads (cp.async.bulk.tensor.2d)
+// mbarrier rings: raw_full (TMA landed) / full (converted) / empty per smem stage, full / empty per
+// TMEM buffer.
 #include "tc_common.cuh"
 
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
@@ -24,41 +31,94 @@ namespace vgtkb {
 
 using namespace tc;
 
-constexpr int TC_BM = 128;         // rows of A per tile = UMMA M = TMEM lanes
-constexpr int TC_BK = 32;          // fp32 per k-block = one 128-byte swizzle row
-constexpr int TC_EPI_WARPS = 4;
-constexpr int TC_PROD_WARPS = 8;
-constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;  // 416
+constexpr int TC_BM = 128;  // rows of A per tile = UMMA M = TMEM lanes
+constexpr int TC_BK = 32;   // fp32 per k-block = one 128-byte swizzle row
+// 16 warps = 4 complete warpgroups (setmaxnreg is a warpgroup-wide .sync.aligned instruction: a partial
+// warpgroup never completes it).  warps 0-7 epilogue, 8-11 and 14-15 converters, 12 MMA, 13 TMA.
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_CONV_WARPS = 6;
+constexpr int TC_MMA_WARP = 12;
+constexpr int TC_TMA_WARP = 13;
+constexpr int TC_THREADS = 16 * 32;                        // 512
+constexpr int TC_CONV_THREADS = TC_CONV_WARPS * 32;
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
+// register budget after setmaxnreg: 256 x 184 + 256 x 64 = 63488 <= 512 x 128 (the pool a CTA can re-partition
+// is what it was launched with: threads x the ptxas register count, 128 here)
+// (the pool a CTA can re-partition is what it was launched with: threads x ptxas register count)
+#define VGTKB_REG_EPI 184
+#define VGTKB_REG_OTHER 64
+#define VGTKB_STR2(x) #x
+#define VGTKB_STR(x) VGTKB_STR2(x)
+
+__device__ __forceinline__ void reg_inc_epi() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 " VGTKB_STR(VGTKB_REG_EPI) ";" ::: "memory");
+}
+__device__ __forceinline__ void reg_dec_other() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 " VGTKB_STR(VGTKB_REG_OTHER) ";" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+
 template <int BN>
-struct NtCfg {
+struct TcCfg {
     static constexpr int A_BYTES = TC_BM * TC_BK * 4;  // 16 KB (one of hi / lo)
     static constexpr int B_BYTES = BN * TC_BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = (TC_SMEM_BUDGET / STAGE_BYTES) > 6 ? 6 : (TC_SMEM_BUDGET / STAGE_BYTES);
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two chunk buffers
+    static constexpr int HALF = BN / 2;                          // accumulator columns per epilogue thread
     static_assert(STAGES >= 2, "need at least two smem stages");
+    static_assert(BN % 64 == 0, "BN must be a multiple of 64");
 };
+
+struct TcBarriers {
+    uint64_t raw_full[6], full[6], empty[6], tfull[2], tempty[2];
+    uint32_t tmem_base;
+};
+
+template <int STAGES>
+__device__ __forceinline__ void tc_init_barriers(TcBarriers& b) {
+    for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&b.raw_full[s], 1);            // the TMA issuer's expect_tx arrive
+        mbar_init(&b.full[s], TC_CONV_WARPS);    // one elected arrive per converter warp
+        mbar_init(&b.empty[s], 1);               // tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+        mbar_init(&b.tfull[a], 1);                     // tcgen05.commit
+        mbar_init(&b.tempty[a], TC_EPI_WARPS * 32);    // every epilogue thread
+    }
+    fence_barrier_init();
+}
+
+// converters: split `n16` 16-byte slots starting at `raw` in place (hi) and into raw + lo_off (lo)
+__device__ __forceinline__ void convert_region(uint32_t raw, uint32_t lo_off, int n16, int ct) {
+#pragma unroll 4
+    for (int i = ct; i < n16; i += TC_CONV_THREADS) {
+        const uint32_t a = raw + (uint32_t)i * 16u;
+        const float4 v = ld_shared_v4(a);
+        float4 hi, lo;
+        split_tf32(v, hi, lo);
+        st_shared_v4(a, hi);
+        st_shared_v4(a + lo_off, lo);
+    }
+}
 
 // ---------------------------------------------------------------------------------- NT kernel
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
-                  const float* __restrict__ A, const float* __restrict__ bias, float* __restrict__ C, int64_t M, int N,
-                  int K, int passes) {
-    using Cfg = NtCfg<BN>;
+tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                  const __grid_constant__ CUtensorMap map_blo, const float* __restrict__ bias, float* __restrict__ C,
+                  int64_t M, int N, int K, int passes, int chunk_kb) {
+    using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // the dynamic window is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-
-    __shared__ __align__(8) uint64_t full_bar[STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[STAGES];
-    __shared__ __align__(8) uint64_t tfull_bar[2];
-    __shared__ __align__(8) uint64_t tempty_bar[2];
-    __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(8) TcBarriers bars;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (int)((M + TC_BM - 1) / TC_BM);
@@ -66,180 +126,153 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
     const int total_tiles = m_tiles * n_tiles;
     const int nkb = (K + TC_BK - 1) / TC_BK;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], TC_PROD_WARPS + 1);  // 8 producer warps + the TMA issuer's expect_tx arrive
-            mbar_init(&empty_bar[s], 1);                 // tcgen05.commit
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&tfull_bar[a], 1);                     // tcgen05.commit
-            mbar_init(&tempty_bar[a], TC_EPI_WARPS * 32);    // every epilogue thread
-        }
-        fence_barrier_init();
-    }
-    if (warp == TC_EPI_WARPS) {
-        tmem_alloc(&tmem_base_slot, Cfg::TMEM_COLS);
-    }
+    if (threadIdx.x == 0) tc_init_barriers<STAGES>(bars);
+    if (warp == TC_MMA_WARP) tmem_alloc(&bars.tmem_base, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t tmem_base = bars.tmem_base;
 
     if (warp < TC_EPI_WARPS) {
-        // ============================ epilogue ============================
-        int t = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-            const int mt = tile / n_tiles, nt = tile % n_tiles;
-            const int acc = t & 1;
-            mbar_wait_guard(&tfull_bar[acc], (t >> 1) & 1);
-            tc_fence_after();
-            const int64_t row = (int64_t)mt * TC_BM + warp * 32 + lane;
-            const int n0 = nt * BN;
-            const bool vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                if (n0 + c0 >= N) break;  // warp-uniform
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                if (row < M) {
-                    float* dst = C + row * N + n0 + c0;
-                    if (vec_ok && n0 + c0 + 32 <= N) {
+        // ============================ epilogue: drain chunks, RN accumulate in registers ============
+        reg_inc_epi();
+        const int q = warp & 3, h = warp >> 2;
+        float acc[Cfg::HALF];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            if (bias != nullptr) {
-                                const float4 bb = *reinterpret_cast<const float4*>(bias + n0 + c0 + j);
-                                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                            }
-                            *reinterpret_cast<float4*>(dst + j) = o;
+        for (int i = 0; i < Cfg::HALF; ++i) acc[i] = 0.f;
+        int ci = 0;
+        const bool vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = tile / n_tiles, nt = tile % n_tiles;
+            for (int kb0 = 0; kb0 < nkb; kb0 += chunk_kb, ++ci) {
+                const int buf = ci & 1;
+                mbar_wait_guard(&bars.tfull[buf], (ci >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < Cfg::HALF / 32; ++j) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * Cfg::HALF + j * 32), v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+                }
+                tc_fence_before();
+                mbar_arrive(&bars.tempty[buf]);
+            }
+            const int64_t row = (int64_t)mt * TC_BM + q * 32 + lane;
+            const int c_base = nt * BN + h * Cfg::HALF;
+            if (row < M) {
+                float* dst = C + row * N + c_base;
+#pragma unroll
+                for (int j = 0; j < Cfg::HALF; j += 4) {
+                    if (vec_ok && c_base + j + 4 <= N) {
+                        float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                        if (bias != nullptr) {
+                            const float4 bb = *reinterpret_cast<const float4*>(bias + c_base + j);
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
                         }
+                        *reinterpret_cast<float4*>(dst + j) = o;
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n0 + c0 + j < N) dst[j] = v[j] + (bias != nullptr ? bias[n0 + c0 + j] : 0.f);
+                        for (int e = 0; e < 4; ++e)
+                            if (c_base + j + e < N) dst[j + e] = acc[j + e] + (bias != nullptr ? bias[c_base + j + e] : 0.f);
                     }
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
+#pragma unroll
+            for (int i = 0; i < Cfg::HALF; ++i) acc[i] = 0.f;
         }
-    } else if (warp == TC_EPI_WARPS) {
+    } else if (warp != TC_MMA_WARP && warp != TC_TMA_WARP) {
+        // ============================ converters ============================
+        reg_dec_other();
+        const int ct = warp < TC_MMA_WARP ? threadIdx.x - TC_EPI_WARPS * 32 : threadIdx.x - (TC_TMA_WARP + 1) * 32 + 128;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
+                if (passes == 3) {
+                    convert_region(smem_base + s * Cfg::STAGE_BYTES, Cfg::A_BYTES, Cfg::A_BYTES / 16, ct);
+                    fence_proxy_async();   // generic-proxy stores -> visible to the tensor-core (async) proxy
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.full[s]);
+            }
+        }
+    } else if (warp == TC_MMA_WARP) {
         // ============================ MMA issuer ============================
+        reg_dec_other();
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TC_BM, BN, 0, 0);
-            int it = 0, t = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-                const int acc = t & 1;
-                mbar_wait_guard(&tempty_bar[acc], ((t >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait_guard(&full_bar[s], (it / STAGES) & 1);
+            int it = 0, ci = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int kb0 = 0; kb0 < nkb; kb0 += chunk_kb, ++ci) {
+                    const int buf = ci & 1;
+                    mbar_wait_guard(&bars.tempty[buf], ((ci >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
-                    const uint32_t a_lo = a_hi + Cfg::A_BYTES;
-                    const uint32_t b_hi = a_lo + Cfg::A_BYTES;
-                    const uint32_t b_lo = b_hi + Cfg::B_BYTES;
-                    const int krem = K - kb * TC_BK;
-                    const int ksteps = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t koff = ks * 32;  // 8 tf32 = 32 bytes inside the 128 B swizzle row
-                        const uint64_t da_hi = make_smem_desc(a_hi + koff, 16, 1024);
-                        const uint64_t db_hi = make_smem_desc(b_hi + koff, 16, 1024);
-                        const uint32_t first = (kb | ks) != 0;
-                        if (passes == 3) {
-                            const uint64_t da_lo = make_smem_desc(a_lo + koff, 16, 1024);
-                            const uint64_t db_lo = make_smem_desc(b_lo + koff, 16, 1024);
-                            umma_tf32(d_tmem, da_lo, db_hi, idesc, first);   // small terms first
-                            umma_tf32(d_tmem, da_hi, db_lo, idesc, 1);
-                            umma_tf32(d_tmem, da_hi, db_hi, idesc, 1);
-                        } else {
-                            umma_tf32(d_tmem, da_hi, db_hi, idesc, first);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                    const int kb1 = kb0 + chunk_kb < nkb ? kb0 + chunk_kb : nkb;
+                    for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
+                        mbar_wait_guard(&bars.full[s], (it / STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
+                        const uint32_t a_lo = a_hi + Cfg::A_BYTES;
+                        const uint32_t b_hi = a_lo + Cfg::A_BYTES;
+                        const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+                        const int krem = K - kb * TC_BK;
+                        const int ksteps = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint32_t koff = ks * 32;  // 8 tf32 = 32 bytes inside the 128 B swizzle row
+                            const uint64_t da_hi = make_smem_desc(a_hi + koff, 16, 1024);
+                            const uint64_t db_hi = make_smem_desc(b_hi + koff, 16, 1024);
+                            const uint32_t first = ((kb - kb0) | ks) != 0;
+                            if (passes == 3) {
+                                const uint64_t da_lo = make_smem_desc(a_lo + koff, 16, 1024);
+                                const uint64_t db_lo = make_smem_desc(b_lo + koff, 16, 1024);
+                                umma_tf32(d_tmem, da_lo, db_hi, idesc, first);   // small terms first
+                                umma_tf32(d_tmem, da_hi, db_lo, idesc, 1);
+                                umma_tf32(d_tmem, da_hi, db_hi, idesc, 1);
+                            } else {
+                                umma_tf32(d_tmem, da_hi, db_hi, idesc, first);
+                            }
                         }
+                        umma_commit(&bars.empty[s]);   // smem stage reusable once these MMAs have read it
                     }
-                    umma_commit(&empty_bar[s]);   // smem stage reusable once these MMAs have read it
+                    umma_commit(&bars.tfull[buf]);     // chunk complete
                 }
-                umma_commit(&tfull_bar[acc]);     // accumulator complete
             }
         }
         __syncwarp();
     } else {
-        // ============================ producers ============================
-        const int pw = warp - TC_EPI_WARPS - 1;             // 0..7
-        const int pt = pw * 32 + lane;                      // 0..255
-        const int prow = pt >> 3;                           // 0..31 (+32*i)
-        const int chunk = pt & 7;                           // 16-byte chunk inside the 128 B row
-        const bool tma_thread = (pw == 0 && lane == 0);
-        if (tma_thread) {
+        // ============================ TMA producer ============================
+        reg_dec_other();
+        if (lane == 0) {
+            tma_prefetch_desc(&map_a);
             tma_prefetch_desc(&map_bhi);
             tma_prefetch_desc(&map_blo);
-        }
-        const uint32_t b_tx_bytes = (uint32_t)Cfg::B_BYTES * (passes == 3 ? 2u : 1u);
-        // swizzled offsets of this thread's four 16-byte slots inside an A tile
-        uint32_t a_off[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = prow + 32 * i;
-            a_off[i] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
-        }
-        const int kcol = chunk * 4;
-        int it = 0;
-        float4 cur[4];
-        auto load_a = [&](int tile, int kb, float4 (&dst)[4]) {
-            const int mt = tile / n_tiles;
-            const int k = kb * TC_BK + kcol;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t row = (int64_t)mt * TC_BM + prow + 32 * i;
-                dst[i] = (row < M && k < K) ? __ldg(reinterpret_cast<const float4*>(A + row * K + k))
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        int tile = blockIdx.x;
-        if (tile < total_tiles) load_a(tile, 0, cur);
-        while (tile < total_tiles) {
-            const int nt = tile % n_tiles;
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                // prefetch the next k-block (or the first of the next tile) into registers
-                float4 nxt[4];
-                int ntile = tile, nkb_i = kb + 1;
-                if (nkb_i == nkb) { ntile = tile + gridDim.x; nkb_i = 0; }
-                const bool have_next = ntile < total_tiles;
-                if (have_next) load_a(ntile, nkb_i, nxt);
-
-                const int s = it % STAGES;
-                mbar_wait_guard(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-                const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
-                const uint32_t a_lo = a_hi + Cfg::A_BYTES;
-                if (tma_thread) {
+            const uint32_t tx = (uint32_t)Cfg::A_BYTES + (uint32_t)Cfg::B_BYTES * (passes == 3 ? 2u : 1u);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / n_tiles, nt = tile % n_tiles;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
                     unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[s], b_tx_bytes);
-                    tma_load_2d(st + 2 * Cfg::A_BYTES, &map_bhi, kb * TC_BK, nt * BN, &full_bar[s]);
-                    if (passes == 3) tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &map_blo, kb * TC_BK, nt * BN, &full_bar[s]);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 hi, lo;
-                    split_tf32(cur[i], hi, lo);
-                    st_shared_v4(a_hi + a_off[i], hi);
-                    if (passes == 3) st_shared_v4(a_lo + a_off[i], lo);
-                }
-                fence_proxy_async();   // generic-proxy stores -> visible to the tensor-core (async) proxy
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[s]);
-                if (have_next) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+                    mbar_arrive_expect_tx(&bars.raw_full[s], tx);
+                    tma_load_2d(st, &map_a, kb * TC_BK, mt * TC_BM, &bars.raw_full[s]);
+                    tma_load_2d(st + 2 * Cfg::A_BYTES, &map_bhi, kb * TC_BK, nt * BN, &bars.raw_full[s]);
+                    if (passes == 3)
+                        tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &map_blo, kb * TC_BK, nt * BN, &bars.raw_full[s]);
                 }
             }
-            tile += gridDim.x;
         }
+        __syncwarp();
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == TC_EPI_WARPS) {
+    if (warp == TC_MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
@@ -252,6 +285,193 @@ __global__ void split_tf32_kernel(int64_t n, const float* __restrict__ x, float*
         const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
         hi[i] = h;
         lo[i] = v - h;
+    }
+}
+
+// ---------------------------------------------------------------------------------- TN kernel
+// T[i, j] = sum_r P[r, p0+i] * Q[r, q0+j]   (i < 128, j < BN), both operands MN-major in shared
+// memory in the SWIZZLE_128B_BASE32B canonical layout (the layout MN-major tf32 operands require):
+// atoms of 32 (MN) x 4 (K) fp32 = 512 B, 32-byte chunks XOR-permuted by the k-row.  One TMA box
+// (32 rows of R x 32 columns, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) fills one MN atom column for a
+// whole k-block, so a stage is [mn-atom][32 k-rows x 128 B]: LBO (next MN atom) = 4096 B, SBO (next
+// k-atom of 4 rows) = 512 B, and one MMA (K = 8) starts 1024 B after the previous one.
+// Work item = (R slice, P tile, Q tile); finished tiles are added into C with red.global.add:
+//   C[(q0+j) * ldc + (p0+i)] += T[i, j]      (lanes run along i: coalesced)
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q, int Pw, int Qw,
+                  float* __restrict__ C, int ldc, int64_t R, int64_t rows_per_split, int splits, int passes, int chunk_kb) {
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr uint32_t MN_LBO = 4096, K_SBO = 512, L32 = 1;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    __shared__ __align__(8) TcBarriers bars;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p_tiles = (Pw + TC_BM - 1) / TC_BM;
+    const int q_tiles = (Qw + BN - 1) / BN;
+    const int tiles = p_tiles * q_tiles;
+    const int items = tiles * splits;
+
+    if (threadIdx.x == 0) tc_init_barriers<STAGES>(bars);
+    if (warp == TC_MMA_WARP) tmem_alloc(&bars.tmem_base, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars.tmem_base;
+
+    auto item_nkb = [&](int item, int64_t& r0) {
+        const int sp = item / tiles;
+        r0 = (int64_t)sp * rows_per_split;
+        const int64_t r1 = r0 + rows_per_split < R ? r0 + rows_per_split : R;
+        return (int)((r1 - r0 + TC_BK - 1) / TC_BK);
+    };
+
+    if (warp < TC_EPI_WARPS) {
+        // ============================ epilogue ============================
+        reg_inc_epi();
+        const int q = warp & 3, h = warp >> 2;
+        float acc[Cfg::HALF];
+#pragma unroll
+        for (int i = 0; i < Cfg::HALF; ++i) acc[i] = 0.f;
+        int ci = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int tile = item % tiles;
+            const int p0 = (tile / q_tiles) * TC_BM, q0 = (tile % q_tiles) * BN;
+            int64_t r0;
+            const int nkb = item_nkb(item, r0);
+            for (int kb0 = 0; kb0 < nkb; kb0 += chunk_kb, ++ci) {
+                const int buf = ci & 1;
+                mbar_wait_guard(&bars.tfull[buf], (ci >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < Cfg::HALF / 32; ++j) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * Cfg::HALF + j * 32), v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+                }
+                tc_fence_before();
+                mbar_arrive(&bars.tempty[buf]);
+            }
+            const int i = p0 + q * 32 + lane;
+            const int c_base = q0 + h * Cfg::HALF;
+            if (i < Pw) {
+#pragma unroll
+                for (int j = 0; j < Cfg::HALF; ++j)
+                    if (c_base + j < Qw) atomicAdd(C + (size_t)(c_base + j) * ldc + i, acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < Cfg::HALF; ++j) acc[j] = 0.f;
+        }
+    } else if (warp != TC_MMA_WARP && warp != TC_TMA_WARP) {
+        // ============================ converters (both operands) ============================
+        reg_dec_other();
+        const int ct = warp < TC_MMA_WARP ? threadIdx.x - TC_EPI_WARPS * 32 : threadIdx.x - (TC_TMA_WARP + 1) * 32 + 128;
+        int it = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            int64_t r0;
+            const int nkb = item_nkb(item, r0);
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
+                if (passes == 3) {
+                    const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+                    convert_region(st, Cfg::A_BYTES, Cfg::A_BYTES / 16, ct);
+                    convert_region(st + 2 * Cfg::A_BYTES, Cfg::B_BYTES, Cfg::B_BYTES / 16, ct);
+                    fence_proxy_async();
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.full[s]);
+            }
+        }
+    } else if (warp == TC_MMA_WARP) {
+        // ============================ MMA issuer ============================
+        reg_dec_other();
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BM, BN, 1, 1);   // both operands MN-major
+            int it = 0, ci = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                int64_t r0;
+                const int nkb = item_nkb(item, r0);
+                const int64_t rows = (r0 + rows_per_split < R ? r0 + rows_per_split : R) - r0;
+                for (int kb0 = 0; kb0 < nkb; kb0 += chunk_kb, ++ci) {
+                    const int buf = ci & 1;
+                    mbar_wait_guard(&bars.tempty[buf], ((ci >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                    const int kb1 = kb0 + chunk_kb < nkb ? kb0 + chunk_kb : nkb;
+                    for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
+                        mbar_wait_guard(&bars.full[s], (it / STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t p_hi = smem_base + s * Cfg::STAGE_BYTES;
+                        const uint32_t p_lo = p_hi + Cfg::A_BYTES;
+                        const uint32_t q_hi = p_lo + Cfg::A_BYTES;
+                        const uint32_t q_lo = q_hi + Cfg::B_BYTES;
+                        const int64_t rrem = rows - (int64_t)kb * TC_BK;
+                        const int ksteps = rrem >= TC_BK ? TC_BK / 8 : (int)((rrem + 7) / 8);
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint32_t koff = ks * 1024;   // 8 k-rows = two k-atoms
+                            const uint64_t dp_hi = make_smem_desc(p_hi + koff, MN_LBO, K_SBO, L32);
+                            const uint64_t dq_hi = make_smem_desc(q_hi + koff, MN_LBO, K_SBO, L32);
+                            const uint32_t first = ((kb - kb0) | ks) != 0;
+                            if (passes == 3) {
+                                const uint64_t dp_lo = make_smem_desc(p_lo + koff, MN_LBO, K_SBO, L32);
+                                const uint64_t dq_lo = make_smem_desc(q_lo + koff, MN_LBO, K_SBO, L32);
+                                umma_tf32(d_tmem, dp_lo, dq_hi, idesc, first);
+                                umma_tf32(d_tmem, dp_hi, dq_lo, idesc, 1);
+                                umma_tf32(d_tmem, dp_hi, dq_hi, idesc, 1);
+                            } else {
+                                umma_tf32(d_tmem, dp_hi, dq_hi, idesc, first);
+                            }
+                        }
+                        umma_commit(&bars.empty[s]);
+                    }
+                    umma_commit(&bars.tfull[buf]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============================ TMA producer ============================
+        reg_dec_other();
+        if (lane == 0) {
+            tma_prefetch_desc(&map_p);
+            tma_prefetch_desc(&map_q);
+            const uint32_t tx = (uint32_t)Cfg::A_BYTES + (uint32_t)Cfg::B_BYTES;
+            int it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int tile = item % tiles;
+                const int p0 = (tile / q_tiles) * TC_BM, q0 = (tile % q_tiles) * BN;
+                int64_t r0;
+                const int nkb = item_nkb(item, r0);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
+                    unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
+                    const int row = (int)(r0 + (int64_t)kb * TC_BK);
+                    mbar_arrive_expect_tx(&bars.raw_full[s], tx);
+#pragma unroll
+                    for (int a = 0; a < TC_BM / 32; ++a)
+                        tma_load_2d(st + a * 4096, &map_p, p0 + a * 32, row, &bars.raw_full[s]);
+#pragma unroll
+                    for (int a = 0; a < BN / 32; ++a)
+                        tma_load_2d(st + 2 * Cfg::A_BYTES + a * 4096, &map_q, q0 + a * 32, row, &bars.raw_full[s]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -272,8 +492,8 @@ static EncodeTiledFn get_encoder() {
     return fn;
 }
 
-// row-major fp32 matrix [rows, cols]; box = [box_rows, 32 floats], 128-byte swizzle, zero fill out of bounds
-static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows) {
+// row-major fp32 matrix [rows, cols]; box = [box_rows, 32 floats], 128-byte swizzle span, zero fill out of bounds
+static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows, CUtensorMapSwizzle swz) {
     EncodeTiledFn enc = get_encoder();
     if (enc == nullptr) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -284,7 +504,7 @@ static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_
     const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -304,21 +524,29 @@ static int num_sms() {
     return n;
 }
 
+static int default_chunk(int passes) {
+    // k-blocks (of 32) the tensor core accumulates before the epilogue folds the chunk into registers:
+    // 2 k-blocks = 8 k-steps x passes MMAs.
+    return passes == 3 ? 2 : 4;
+}
+
 template <int BN>
 static int launch_nt(int64_t M, int N, int K, const float* A, const float* Bhi, const float* Blo, const float* bias,
                      float* C, int passes, cudaStream_t st) {
-    using Cfg = NtCfg<BN>;
-    CUtensorMap mhi, mlo;
-    int rc = make_map_2d(&mhi, Bhi, N, K, BN);
+    using Cfg = TcCfg<BN>;
+    CUtensorMap ma, mhi, mlo;
+    int rc = make_map_2d(&ma, A, M, K, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_map_2d(&mlo, Blo, N, K, BN);
+    rc = make_map_2d(&mhi, Bhi, N, K, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_2d(&mlo, Blo, N, K, BN, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024;
     auto kern = tc_gemm_nt_kernel<BN>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = ceil_div64(M, TC_BM) * ceil_div(N, BN);
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    kern<<<grid, TC_THREADS, smem, st>>>(mhi, mlo, A, bias, C, M, N, K, passes);
+    kern<<<grid, TC_THREADS, smem, st>>>(ma, mhi, mlo, bias, C, M, N, K, passes, default_chunk(passes));
     return check_launch("gemm_nt(tcgen05)");
 }
 
@@ -353,201 +581,15 @@ int tc_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const fl
     return rc;
 }
 
-// ---------------------------------------------------------------------------------- TN kernel
-// T[i, j] = sum_r P[r, p0+i] * Q[r, q0+j]   (i < 128, j < BN), both operands MN-major in shared
-// memory: canonical SWIZZLE_128B_BASE32B atoms (the layout MN-major tf32 operands require) of
-// 32 (MN) x 4 (K) fp32 = 512 B, 32-byte chunks XOR-permuted by the k-row; stage layout
-// [k-atom (8)][mn-atom][512 B], so LBO (next MN atom) = 512 B and SBO (next k-atom) = MN/32 * 512 B.
-// Work item = (R slice, P tile, Q tile); partial tiles are added into C with red.global.add.
-//   C[(q0+j) * ldc + (p0+i)] += T[i, j]      (lanes run along i: coalesced)
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_tn_kernel(const float* __restrict__ P, int Pw, const float* __restrict__ Q, int Qw, float* __restrict__ C, int ldc,
-                  int64_t R, int64_t rows_per_split, int splits, int passes) {
-    using Cfg = NtCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
-    constexpr uint32_t P_SBO = (TC_BM / 32) * 512;   // bytes between 4-row k-atoms of the P tile
-    constexpr uint32_t Q_SBO = (BN / 32) * 512;
-    constexpr uint32_t MN_LBO = 512;
-    constexpr uint32_t L32 = 1;                       // SWIZZLE_128B_BASE32B
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-
-    __shared__ __align__(8) uint64_t full_bar[STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[STAGES];
-    __shared__ __align__(8) uint64_t tfull_bar[2];
-    __shared__ __align__(8) uint64_t tempty_bar[2];
-    __shared__ uint32_t tmem_base_slot;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p_tiles = (Pw + TC_BM - 1) / TC_BM;
-    const int q_tiles = (Qw + BN - 1) / BN;
-    const int tiles = p_tiles * q_tiles;
-    const int items = tiles * splits;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], TC_PROD_WARPS);
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], TC_EPI_WARPS * 32);
-        }
-        fence_barrier_init();
-    }
-    if (warp == TC_EPI_WARPS) tmem_alloc(&tmem_base_slot, Cfg::TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_slot;
-
-    auto item_rows = [&](int item, int64_t& r0, int64_t& r1) {
-        const int sp = item / tiles;
-        r0 = (int64_t)sp * rows_per_split;
-        r1 = r0 + rows_per_split < R ? r0 + rows_per_split : R;
-    };
-
-    if (warp < TC_EPI_WARPS) {
-        // ============================ epilogue ============================
-        int t = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x, ++t) {
-            const int tile = item % tiles;
-            const int p0 = (tile / q_tiles) * TC_BM, q0 = (tile % q_tiles) * BN;
-            const int acc = t & 1;
-            mbar_wait_guard(&tfull_bar[acc], (t >> 1) & 1);
-            tc_fence_after();
-            const int i = p0 + warp * 32 + lane;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                if (q0 + c0 >= Qw) break;  // warp-uniform
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                if (i < Pw) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (q0 + c0 + j < Qw) atomicAdd(C + (size_t)(q0 + c0 + j) * ldc + i, v[j]);
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
-        }
-    } else if (warp == TC_EPI_WARPS) {
-        // ============================ MMA issuer ============================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_BM, BN, 1, 1);   // both operands MN-major
-            int it = 0, t = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++t) {
-                int64_t r0, r1;
-                item_rows(item, r0, r1);
-                const int nkb = (int)((r1 - r0 + TC_BK - 1) / TC_BK);
-                const int acc = t & 1;
-                mbar_wait_guard(&tempty_bar[acc], ((t >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait_guard(&full_bar[s], (it / STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t p_hi = smem_base + s * Cfg::STAGE_BYTES;
-                    const uint32_t p_lo = p_hi + Cfg::A_BYTES;
-                    const uint32_t q_hi = p_lo + Cfg::A_BYTES;
-                    const uint32_t q_lo = q_hi + Cfg::B_BYTES;
-                    const int64_t rrem = r1 - r0 - (int64_t)kb * TC_BK;
-                    const int ksteps = rrem >= TC_BK ? TC_BK / 8 : (int)((rrem + 7) / 8);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        // one MMA (K = 8) spans two k-atoms
-                        const uint64_t dp_hi = make_smem_desc(p_hi + ks * 2 * P_SBO, MN_LBO, P_SBO, L32);
-                        const uint64_t dq_hi = make_smem_desc(q_hi + ks * 2 * Q_SBO, MN_LBO, Q_SBO, L32);
-                        const uint32_t first = (kb | ks) != 0;
-                        if (passes == 3) {
-                            const uint64_t dp_lo = make_smem_desc(p_lo + ks * 2 * P_SBO, MN_LBO, P_SBO, L32);
-                            const uint64_t dq_lo = make_smem_desc(q_lo + ks * 2 * Q_SBO, MN_LBO, Q_SBO, L32);
-                            umma_tf32(d_tmem, dp_lo, dq_hi, idesc, first);
-                            umma_tf32(d_tmem, dp_hi, dq_lo, idesc, 1);
-                            umma_tf32(d_tmem, dp_hi, dq_hi, idesc, 1);
-                        } else {
-                            umma_tf32(d_tmem, dp_hi, dq_hi, idesc, first);
-                        }
-                    }
-                    umma_commit(&empty_bar[s]);
-                }
-                umma_commit(&tfull_bar[acc]);
-            }
-        }
-        __syncwarp();
-    } else {
-        // ============================ producers ============================
-        const int pw = warp - TC_EPI_WARPS - 1;
-        const int pt = pw * 32 + lane;         // 0..255
-        const int krow = pt >> 3;              // 0..31: row of R inside the k-block
-        const int sub = pt & 7;                // 16-byte chunk inside a 128 B atom row
-        // inside an atom: row (krow & 3) of 128 B; the 32-byte chunk index is XORed with the row
-        const uint32_t row_off = (uint32_t)((krow & 3) * 128 + ((((sub >> 1) ^ (krow & 3)) << 5) | ((sub & 1) << 4)));
-        const uint32_t p_koff = (uint32_t)(krow >> 2) * P_SBO + row_off;
-        const uint32_t q_koff = (uint32_t)(krow >> 2) * Q_SBO + row_off;
-        int it = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int tile = item % tiles;
-            const int p0 = (tile / q_tiles) * TC_BM, q0 = (tile % q_tiles) * BN;
-            int64_t r0, r1;
-            item_rows(item, r0, r1);
-            const int nkb = (int)((r1 - r0 + TC_BK - 1) / TC_BK);
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int64_t r = r0 + (int64_t)kb * TC_BK + krow;
-                const bool rok = r < r1;
-                float4 pv[TC_BM / 32], qv[BN / 32];
-#pragma unroll
-                for (int i = 0; i < TC_BM / 32; ++i) {
-                    const int col = p0 + i * 32 + sub * 4;
-                    pv[i] = (rok && col < Pw) ? __ldg(reinterpret_cast<const float4*>(P + r * Pw + col))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int i = 0; i < BN / 32; ++i) {
-                    const int col = q0 + i * 32 + sub * 4;
-                    qv[i] = (rok && col < Qw) ? __ldg(reinterpret_cast<const float4*>(Q + r * Qw + col))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                const int s = it % STAGES;
-                mbar_wait_guard(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-                const uint32_t p_hi = smem_base + s * Cfg::STAGE_BYTES;
-                const uint32_t p_lo = p_hi + Cfg::A_BYTES;
-                const uint32_t q_hi = p_lo + Cfg::A_BYTES;
-                const uint32_t q_lo = q_hi + Cfg::B_BYTES;
-#pragma unroll
-                for (int i = 0; i < TC_BM / 32; ++i) {
-                    float4 hi, lo;
-                    split_tf32(pv[i], hi, lo);
-                    st_shared_v4(p_hi + p_koff + i * MN_LBO, hi);
-                    if (passes == 3) st_shared_v4(p_lo + p_koff + i * MN_LBO, lo);
-                }
-#pragma unroll
-                for (int i = 0; i < BN / 32; ++i) {
-                    float4 hi, lo;
-                    split_tf32(qv[i], hi, lo);
-                    st_shared_v4(q_hi + q_koff + i * MN_LBO, hi);
-                    if (passes == 3) st_shared_v4(q_lo + q_koff + i * MN_LBO, lo);
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[s]);
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == TC_EPI_WARPS) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-    }
-}
-
 template <int BN>
 static int launch_tn(const float* P, int Pw, const float* Q, int Qw, float* C, int ldc, int64_t R, int passes,
                      cudaStream_t st) {
-    using Cfg = NtCfg<BN>;
+    using Cfg = TcCfg<BN>;
+    CUtensorMap mp, mq;
+    int rc = make_map_2d(&mp, P, R, Pw, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    rc = make_map_2d(&mq, Q, R, Qw, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
     const int tiles = ceil_div(Pw, TC_BM) * ceil_div(Qw, BN);
     int64_t splits = ceil_div64((int64_t)2 * num_sms(), tiles);
     const int64_t max_splits = ceil_div64(R, 512);
@@ -560,14 +602,15 @@ static int launch_tn(const float* P, int Pw, const float* Q, int Qw, float* C, i
     auto kern = tc_gemm_tn_kernel<BN>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)(items < num_sms() ? items : num_sms());
-    kern<<<grid, TC_THREADS, smem, st>>>(P, Pw, Q, Qw, C, ldc, R, rps, (int)splits, passes);
+    kern<<<grid, TC_THREADS, smem, st>>>(mp, mq, Pw, Qw, C, ldc, R, rps, (int)splits, passes, default_chunk(passes));
     return check_launch("gemm_tn(tcgen05)");
 }
 
 // C[M,N] (+)= A[R,M]^T B[R,N]:  P = B (tiles of 128 over N), Q = A (tiles of <= 256 over M)
 int tc_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C, int accumulate, int passes,
                cudaStream_t st) {
-    if (M % 4 != 0 || N % 4 != 0 || R < 64 || ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) != 0)
+    if (M % 4 != 0 || N % 4 != 0 || R < 64 || R >= ((int64_t)1 << 31) ||
+        ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) != 0)
         return VGTKB_EUNSUP;
     if ((int64_t)M * N < 64 * 64 / 4) return VGTKB_EUNSUP;   // tiny outputs: the FFMA split-R kernel is fine
     if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));

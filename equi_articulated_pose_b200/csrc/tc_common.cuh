@@ -97,10 +97,17 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
 }
 
 // ---- bounded mbarrier wait: a protocol bug traps instead of hanging the GPU -----------------------
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = global_timer_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();   // 4 s: protocol bug
     }
 }
 

@@ -227,6 +227,27 @@ def test_intra_conv_matches_reference_fixture(dev, ops):
     assert rel_err(out, torch.from_numpy(g["out"])) < FP32_TOL
 
 
+def test_config1_intra_so3conv_forward(dev, ops):
+    """BASELINE config 1: single IntraSO3Conv(64, 64) forward, N=128 points, the 12-wide
+    anchor neighbourhood of the 60 SO(3) anchors, batch 1, weights from torch.manual_seed(0); vs the oracle."""
+    import equi_articulated_pose_b200 as eap
+    eap.install()
+    import vgtk.so3conv as sptk
+    import vgtk.spconv as zptk
+    from oracle import so3 as O
+    from equi_articulated_pose_b200 import so3_constants as C
+    torch.manual_seed(0)
+    conv = sptk.IntraSO3Conv(64, 64)
+    g = torch.Generator().manual_seed(1000)
+    feats = torch.randn(1, 64, 128, 60, generator=g)
+    xyz = torch.rand(1, 3, 128, generator=g) - 0.5
+    want = O.basic_conv(conv.basic_conv.W.detach(), O.intra_group_feats(torch.from_numpy(C.intra_idx()), feats))
+    conv = conv.to(dev)
+    out = conv(zptk.SphericalPointCloud(xyz.to(dev), feats.to(dev), None))
+    assert tuple(out.feats.shape) == (1, 64, 128, 60) and torch.equal(out.xyz.cpu(), xyz)
+    assert rel_err(out.feats, want) < FP32_TOL
+
+
 def test_intra_group_backward(dev, ops):
     from oracle import so3 as O
     from equi_articulated_pose_b200 import so3_constants as C
@@ -252,9 +273,8 @@ def test_gemm_nt_tn(dev, ops, mode, M, N, K):
     A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
     bias = torch.randn(N, generator=g)
     want = (A.double() @ B.double().t() + bias.double()).float()
-    # mode 1 = 3xTF32 on tcgen05: products are fp32-exact, the TMEM accumulator truncates (RZ) on every
-    # add, which shows as a K-proportional shrink (4e-5 at K = 6144); mode 0 = FFMA
-    tol = 2e-5 if mode == 0 else 1e-4
+    # mode 1 = 3xTF32 on tcgen05 with chunked round-to-nearest accumulation (~1e-6); mode 0 = FFMA
+    tol = 2e-5 if mode == 0 else 5e-6
     got = ops.gemm_nt(A.to(dev), B.to(dev), bias.to(dev), mode=mode)
     assert rel_err(got, want) < tol
     D = torch.randn(M, N, generator=g)
@@ -363,12 +383,10 @@ def test_classic_backbone_fwd_bwd_vs_oracle(dev, ops, loss_kind, gemm_mode):
 
     Forward: 1e-4 against the fp32 oracle (= the reference's arithmetic) and the fp64 oracle.
     Backward: every gradient is measured against the fp64 evaluation of the same graph, normalised by
-    the largest entry of its tensor.  The fp32 CPU oracle itself is 3e-3..4e-2 away from fp64 (naive
-    fp32 summation in torch-CPU BatchNorm/InstanceNorm backward), so the bar is "as close to fp64 as
-    the fp32 reference": mode 0 (FFMA contraction) within 3x of it, mode 1 (3xTF32 on tcgen05, whose
-    TMEM accumulator rounds toward zero on every add -- it hurts the weight gradients, which are sums
-    with heavy cancellation) within 0.15 absolute for now; see DESIGN.md section 6 for the planned
-    chunked accumulation that removes this."""
+    the largest entry of its tensor.  fp32 gradients of this network have a noise floor of
+    3e-3..4e-2 whatever the implementation (the fp32 CPU oracle = the reference's arithmetic is that
+    far from fp64; so are the FFMA mode 0 and the 3xTF32 mode 1 with chunked RN accumulation), so the
+    bar is "as close to fp64 as the fp32 reference": within 5x of its error or 3e-2 of the tensor maximum."""
     prev = ops.get_gemm_mode()
     ops.set_gemm_mode(gemm_mode)
     try:
@@ -385,10 +403,8 @@ def test_classic_backbone_fwd_bwd_vs_oracle(dev, ops, loss_kind, gemm_mode):
     for name, scale, e_gpu, e_ref in rows:
         if scale < 1e-6 * gmax:   # structurally zero gradients (bias before BatchNorm, first skip branch)
             assert e_gpu < 1e-4 * gmax, (name, e_gpu)
-        elif gemm_mode == 0:
-            assert e_gpu <= 3 * e_ref + 2e-3 * scale, (name, e_gpu / scale, e_ref / scale)
         else:
-            assert e_gpu <= 0.15 * scale, (name, e_gpu / scale, e_ref / scale)
+            assert e_gpu <= max(5 * e_ref, 3e-2 * scale), (name, e_gpu / scale, e_ref / scale)
 
 
 def test_config2_shape_forward_vs_oracle(dev):
