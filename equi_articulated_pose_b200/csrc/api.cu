@@ -44,11 +44,11 @@ extern "C" int vgtkb_device_check(void) {
 extern "C" int vgtkb_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const float* bias, float* C,
                              int mode, float* workspace, void* stream) {
     VGTKB_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_nt: bad size");
-    VGTKB_REQUIRE(mode >= 0 && mode <= 2, "gemm_nt: bad mode %d", mode);
+    VGTKB_REQUIRE(mode >= 0 && mode <= 3, "gemm_nt: bad mode %d", mode);
     if (M == 0) return VGTKB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode != 0) {
-        const int rc = tc_gemm_nt(M, N, K, A, B, bias, C, mode == 1 ? 3 : 1, workspace, st);
+        const int rc = tc_gemm_nt(M, N, K, A, B, bias, C, mode == 1 ? 3 : (mode == 3 ? 6 : 1), workspace, st);
         if (rc != VGTKB_EUNSUP) return rc;
     }
     return sgemm_nt(M, N, K, A, B, bias, C, st);
@@ -57,14 +57,14 @@ extern "C" int vgtkb_gemm_nt(int64_t M, int N, int K, const float* A, const floa
 extern "C" int vgtkb_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C, int accumulate,
                              int mode, void* stream) {
     VGTKB_REQUIRE(M > 0 && N > 0 && R >= 0, "gemm_tn: bad size");
-    VGTKB_REQUIRE(mode >= 0 && mode <= 2, "gemm_tn: bad mode %d", mode);
+    VGTKB_REQUIRE(mode >= 0 && mode <= 3, "gemm_tn: bad mode %d", mode);
     cudaStream_t st = (cudaStream_t)stream;
     if (R == 0) {
         if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
         return VGTKB_OK;
     }
     if (mode != 0) {
-        const int rc = tc_gemm_tn(M, N, R, A, B, C, accumulate, mode == 1 ? 3 : 1, st);
+        const int rc = tc_gemm_tn(M, N, R, A, B, C, accumulate, mode == 2 ? 1 : 3, st);
         if (rc != VGTKB_EUNSUP) return rc;
     }
     return sgemm_tn(M, N, R, A, B, C, accumulate, st);

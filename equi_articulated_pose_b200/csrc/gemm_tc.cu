@@ -107,8 +107,31 @@ __device__ __forceinline__ void convert_region(uint32_t raw, uint32_t lo_off, in
     }
 }
 
+// bf16x3 converter for a K-major tile: the raw fp32 k-block (128 rows x 64 columns, two TMA boxes of
+// 16 KB) becomes, IN PLACE, the bf16 hi tile (first 16 KB) and lo tile (second 16 KB), both 128 rows x
+// 128 B in the 128B-swizzled K-major layout.  Row r of both output tiles only depends on row r of the
+// two boxes, and the eight lanes that own a row sit in one warp: load, convert, __syncwarp, store.
+__device__ __forceinline__ void convert_rows_bf16(uint32_t stage, int cw, int lane) {
+    const int j = lane & 7, sub = lane >> 3;
+    for (int g = cw; g < TC_BM / 4; g += TC_CONV_WARPS) {
+        const int r = g * 4 + sub;
+        const uint32_t rowbase = stage + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+        const uint32_t src = rowbase + (uint32_t)(j >> 2) * 16384u;
+        const int c0 = 2 * (j & 3);
+        const float4 v0 = ld_shared_v4(src + (uint32_t)(((c0) ^ (r & 7)) << 4));
+        const float4 v1 = ld_shared_v4(src + (uint32_t)(((c0 + 1) ^ (r & 7)) << 4));
+        uint4 hi, lo;
+        split_bf16x8(v0, v1, hi, lo);
+        __syncwarp();
+        const uint32_t dst = rowbase + (uint32_t)((j ^ (r & 7)) << 4);
+        st_shared_u4(dst, hi);
+        st_shared_u4(dst + 16384u, lo);
+    }
+}
+
 // ---------------------------------------------------------------------------------- NT kernel
-template <int BN>
+// BF = false: kind::tf32 (passes 1 or 3), k-block = 32 columns.  BF = true: bf16x3 (kind::f16), k-block = 64.
+template <int BN, bool BF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                   const __grid_constant__ CUtensorMap map_blo, const float* __restrict__ bias, float* __restrict__ C,
@@ -124,7 +147,9 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int m_tiles = (int)((M + TC_BM - 1) / TC_BM);
     const int n_tiles = (N + BN - 1) / BN;
     const int total_tiles = m_tiles * n_tiles;
-    const int nkb = (K + TC_BK - 1) / TC_BK;
+    constexpr int KBE = BF ? 64 : TC_BK;     // K elements per k-block (one 128-byte operand row)
+    constexpr int UK = BF ? 16 : 8;          // K elements per MMA
+    const int nkb = (K + KBE - 1) / KBE;
 
     if (threadIdx.x == 0) tc_init_barriers<STAGES>(bars);
     if (warp == TC_MMA_WARP) tmem_alloc(&bars.tmem_base, Cfg::TMEM_COLS);
@@ -158,25 +183,46 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tc_fence_before();
                 mbar_arrive(&bars.tempty[buf]);
             }
-            const int64_t row = (int64_t)mt * TC_BM + q * 32 + lane;
+            // transpose each 32x32 block through a private 4 KB staging tile so that a store instruction
+            // covers 4 rows x 128 contiguous bytes (the accumulator layout is one row per lane)
+            const uint32_t stg = smem_base + (uint32_t)(STAGES * Cfg::STAGE_BYTES) + (uint32_t)warp * 4096u;
+            const int64_t row0 = (int64_t)mt * TC_BM + q * 32;
             const int c_base = nt * BN + h * Cfg::HALF;
-            if (row < M) {
-                float* dst = C + row * N + c_base;
 #pragma unroll
-                for (int j = 0; j < Cfg::HALF; j += 4) {
-                    if (vec_ok && c_base + j + 4 <= N) {
-                        float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-                        if (bias != nullptr) {
-                            const float4 bb = *reinterpret_cast<const float4*>(bias + c_base + j);
-                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            for (int j = 0; j < Cfg::HALF / 32; ++j) {
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4)
+                    st_shared_v4(stg + (uint32_t)(lane * 128 + ((c4 ^ (lane & 7)) << 4)),
+                                 make_float4(acc[j * 32 + c4 * 4], acc[j * 32 + c4 * 4 + 1], acc[j * 32 + c4 * 4 + 2],
+                                             acc[j * 32 + c4 * 4 + 3]));
+                __syncwarp();
+                const int c4 = lane & 7;
+                const int col = c_base + j * 32 + c4 * 4;
+                float bb[4] = {0.f, 0.f, 0.f, 0.f};
+                if (bias != nullptr) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (col + e < N) bb[e] = bias[col + e];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + (lane >> 3);
+                    float4 o = ld_shared_v4(stg + (uint32_t)(rr * 128 + ((c4 ^ (rr & 7)) << 4)));
+                    o.x += bb[0]; o.y += bb[1]; o.z += bb[2]; o.w += bb[3];
+                    const int64_t grow = row0 + rr;
+                    if (grow < M) {
+                        float* dst = C + grow * N + col;
+                        if (vec_ok && col + 4 <= N) {
+                            *reinterpret_cast<float4*>(dst) = o;
+                        } else {
+                            if (col < N) dst[0] = o.x;
+                            if (col + 1 < N) dst[1] = o.y;
+                            if (col + 2 < N) dst[2] = o.z;
+                            if (col + 3 < N) dst[3] = o.w;
                         }
-                        *reinterpret_cast<float4*>(dst + j) = o;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (c_base + j + e < N) dst[j + e] = acc[j + e] + (bias != nullptr ? bias[c_base + j + e] : 0.f);
                     }
                 }
+                __syncwarp();
             }
 #pragma unroll
             for (int i = 0; i < Cfg::HALF; ++i) acc[i] = 0.f;
@@ -190,7 +236,10 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
-                if (passes == 3) {
+                if (BF) {
+                    convert_rows_bf16(smem_base + s * Cfg::STAGE_BYTES, ct >> 5, lane);
+                    fence_proxy_async();
+                } else if (passes == 3) {
                     convert_region(smem_base + s * Cfg::STAGE_BYTES, Cfg::A_BYTES, Cfg::A_BYTES / 16, ct);
                     fence_proxy_async();   // generic-proxy stores -> visible to the tensor-core (async) proxy
                 }
@@ -202,7 +251,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ============================ MMA issuer ============================
         reg_dec_other();
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_BM, BN, 0, 0);
+            const uint32_t idesc = BF ? make_idesc_bf16(TC_BM, BN, 0, 0) : make_idesc_tf32(TC_BM, BN, 0, 0);
             int it = 0, ci = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 for (int kb0 = 0; kb0 < nkb; kb0 += chunk_kb, ++ci) {
@@ -220,14 +269,20 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         const uint32_t a_lo = a_hi + Cfg::A_BYTES;
                         const uint32_t b_hi = a_lo + Cfg::A_BYTES;
                         const uint32_t b_lo = b_hi + Cfg::B_BYTES;
-                        const int krem = K - kb * TC_BK;
-                        const int ksteps = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
+                        const int krem = K - kb * KBE;
+                        const int ksteps = krem >= KBE ? KBE / UK : (krem + UK - 1) / UK;
                         for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint32_t koff = ks * 32;  // 8 tf32 = 32 bytes inside the 128 B swizzle row
+                            const uint32_t koff = ks * 32;  // 8 tf32 / 16 bf16 = 32 bytes inside the 128 B swizzle row
                             const uint64_t da_hi = make_smem_desc(a_hi + koff, 16, 1024);
                             const uint64_t db_hi = make_smem_desc(b_hi + koff, 16, 1024);
                             const uint32_t first = ((kb - kb0) | ks) != 0;
-                            if (passes == 3) {
+                            if (BF) {
+                                const uint64_t da_lo = make_smem_desc(a_lo + koff, 16, 1024);
+                                const uint64_t db_lo = make_smem_desc(b_lo + koff, 16, 1024);
+                                umma_bf16(d_tmem, da_lo, db_hi, idesc, first);
+                                umma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
+                                umma_bf16(d_tmem, da_hi, db_hi, idesc, 1);
+                            } else if (passes == 3) {
                                 const uint64_t da_lo = make_smem_desc(a_lo + koff, 16, 1024);
                                 const uint64_t db_lo = make_smem_desc(b_lo + koff, 16, 1024);
                                 umma_tf32(d_tmem, da_lo, db_hi, idesc, first);   // small terms first
@@ -251,7 +306,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tma_prefetch_desc(&map_a);
             tma_prefetch_desc(&map_bhi);
             tma_prefetch_desc(&map_blo);
-            const uint32_t tx = (uint32_t)Cfg::A_BYTES + (uint32_t)Cfg::B_BYTES * (passes == 3 ? 2u : 1u);
+            const uint32_t tx = BF ? 2u * (uint32_t)Cfg::A_BYTES + 2u * (uint32_t)Cfg::B_BYTES
+                                   : (uint32_t)Cfg::A_BYTES + (uint32_t)Cfg::B_BYTES * (passes == 3 ? 2u : 1u);
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / n_tiles, nt = tile % n_tiles;
@@ -260,10 +316,11 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
                     unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&bars.raw_full[s], tx);
-                    tma_load_2d(st, &map_a, kb * TC_BK, mt * TC_BM, &bars.raw_full[s]);
-                    tma_load_2d(st + 2 * Cfg::A_BYTES, &map_bhi, kb * TC_BK, nt * BN, &bars.raw_full[s]);
-                    if (passes == 3)
-                        tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &map_blo, kb * TC_BK, nt * BN, &bars.raw_full[s]);
+                    tma_load_2d(st, &map_a, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
+                    if (BF) tma_load_2d(st + Cfg::A_BYTES, &map_a, kb * KBE + 32, mt * TC_BM, &bars.raw_full[s]);
+                    tma_load_2d(st + 2 * Cfg::A_BYTES, &map_bhi, kb * KBE, nt * BN, &bars.raw_full[s]);
+                    if (BF || passes == 3)
+                        tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &map_blo, kb * KBE, nt * BN, &bars.raw_full[s]);
                 }
             }
         }
@@ -285,6 +342,17 @@ __global__ void split_tf32_kernel(int64_t n, const float* __restrict__ x, float*
         const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
         hi[i] = h;
         lo[i] = v - h;
+    }
+}
+
+// bf16 hi/lo split of the weight operand into a workspace [2][n] of bf16
+__global__ void split_bf16_kernel(int64_t n, const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        const uint32_t h = pack_bf16x2(v, 0.f) & 0xFFFFu;
+        const float hf = __uint_as_float(h << 16);
+        hi[i] = (uint16_t)h;
+        lo[i] = (uint16_t)(pack_bf16x2(v - hf, 0.f) & 0xFFFFu);
     }
 }
 
@@ -492,18 +560,22 @@ static EncodeTiledFn get_encoder() {
     return fn;
 }
 
-// row-major fp32 matrix [rows, cols]; box = [box_rows, 32 floats], 128-byte swizzle span, zero fill out of bounds
-static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows, CUtensorMapSwizzle swz) {
+// row-major matrix [rows, cols] of fp32 (or bf16); box = [box_rows, 128 bytes], 128-byte swizzle span, zero
+// fill out of bounds
+static int make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows, CUtensorMapSwizzle swz,
+                       bool bf16 = false) {
     EncodeTiledFn enc = get_encoder();
     if (enc == nullptr) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
         return VGTKB_EUNSUP;
     }
+    const int esz = bf16 ? 2 : 4;
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t gstr[1] = {(cuuint64_t)cols * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)cols * esz};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+    const CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                           const_cast<void*>(base), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -530,23 +602,23 @@ static int default_chunk(int passes) {
     return passes == 3 ? 2 : 4;
 }
 
-template <int BN>
-static int launch_nt(int64_t M, int N, int K, const float* A, const float* Bhi, const float* Blo, const float* bias,
+template <int BN, bool BF>
+static int launch_nt(int64_t M, int N, int K, const float* A, const void* Bhi, const void* Blo, const float* bias,
                      float* C, int passes, cudaStream_t st) {
     using Cfg = TcCfg<BN>;
     CUtensorMap ma, mhi, mlo;
     int rc = make_map_2d(&ma, A, M, K, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_map_2d(&mhi, Bhi, N, K, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_map_2d(&mhi, Bhi, N, K, BN, CU_TENSOR_MAP_SWIZZLE_128B, BF);
     if (rc) return rc;
-    rc = make_map_2d(&mlo, Blo, N, K, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_map_2d(&mlo, Blo, N, K, BN, CU_TENSOR_MAP_SWIZZLE_128B, BF);
     if (rc) return rc;
-    const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024;
-    auto kern = tc_gemm_nt_kernel<BN>;
+    const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024 + TC_EPI_WARPS * 4096;   // + epilogue staging
+    auto kern = tc_gemm_nt_kernel<BN, BF>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = ceil_div64(M, TC_BM) * ceil_div(N, BN);
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    kern<<<grid, TC_THREADS, smem, st>>>(ma, mhi, mlo, bias, C, M, N, K, passes, default_chunk(passes));
+    kern<<<grid, TC_THREADS, smem, st>>>(ma, mhi, mlo, bias, C, M, N, K, passes, BF ? 1 : default_chunk(passes));
     return check_launch("gemm_nt(tcgen05)");
 }
 
@@ -562,6 +634,8 @@ int tc_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const fl
     float* owned = nullptr;
     const float* Bhi = B;
     const float* Blo = B;
+    const bool bf = passes == 6 && K % 8 == 0;   // 6 = bf16x3 (needs 16-byte aligned bf16 rows)
+    if (passes == 6) passes = 3;                  // K % 8 != 0: 3xTF32 instead
     if (passes == 3) {
         ws = workspace;
         if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 15) != 0 || nb % 4 != 0) {
@@ -569,14 +643,19 @@ int tc_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const fl
             ws = owned;
         }
         const int blocks = (int)(ceil_div64(nb, 256) < 1184 ? ceil_div64(nb, 256) : 1184);
-        split_tf32_kernel<<<blocks, 256, 0, st>>>(nb, B, ws, ws + nb);
+        if (bf) split_bf16_kernel<<<blocks, 256, 0, st>>>(nb, B, reinterpret_cast<uint16_t*>(ws), reinterpret_cast<uint16_t*>(ws + nb));
+        else split_tf32_kernel<<<blocks, 256, 0, st>>>(nb, B, ws, ws + nb);
         Bhi = ws;
         Blo = ws + nb;
     }
     int rc;
-    if (N <= 64) rc = launch_nt<64>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
-    else if (N <= 128) rc = launch_nt<128>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
-    else rc = launch_nt<256>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
+    if (bf) {
+        if (N <= 64) rc = launch_nt<64, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
+        else if (N <= 128) rc = launch_nt<128, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
+        else rc = launch_nt<256, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
+    } else if (N <= 64) rc = launch_nt<64, false>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
+    else if (N <= 128) rc = launch_nt<128, false>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
+    else rc = launch_nt<256, false>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
     if (owned != nullptr) cudaFreeAsync(owned, st);
     return rc;
 }

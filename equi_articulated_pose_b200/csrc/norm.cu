@@ -83,6 +83,93 @@ col_reduce_kernel(int64_t rows, int c, int rows_per_cta, const float* __restrict
     }
 }
 
+// float4 variant (c % 4 == 0, 16-byte aligned): thread <-> 4 adjacent channels, rows strided over ty
+template <int MODE>
+__global__ void __launch_bounds__(NT)
+col_reduce4_kernel(int64_t rows, int c, int rows_per_cta, const float* __restrict__ x, OpBwd bw, double* __restrict__ scratch) {
+    const int g = blockIdx.y;
+    const int c4 = c >> 2;
+    const int tx = min(c4, NT), ty = NT / tx;
+    const int lx = threadIdx.x % tx, ly = threadIdx.x / tx;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = min(rows, r0 + rows_per_cta);
+    const float4* xg = reinterpret_cast<const float4*>(x + (size_t)g * rows * c);
+    const float4* gyg = MODE == 1 ? reinterpret_cast<const float4*>(bw.gy + (size_t)g * rows * c) : nullptr;
+    __shared__ double sh[NT][8];
+    for (int q = lx; q < c4; q += tx) {
+        const int ch = q * 4;
+        double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+        float mean[4] = {0.f, 0.f, 0.f, 0.f}, inv[4] = {1.f, 1.f, 1.f, 1.f}, ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+        if (MODE == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                mean[i] = bw.stats[(size_t)g * 2 * c + ch + i];
+                inv[i] = bw.stats[(size_t)g * 2 * c + c + ch + i];
+                if (bw.gamma) ga[i] = bw.gamma[ch + i];
+                if (bw.beta) be[i] = bw.beta[ch + i];
+            }
+        }
+        if (ly < ty) {
+#pragma unroll 4
+            for (int64_t r = r0 + ly; r < r1; r += ty) {
+                const float4 v4 = xg[r * c4 + q];
+                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+                if (MODE == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const double d = (double)v[i];
+                        s1[i] += d;
+                        s2[i] = fma(d, d, s2[i]);
+                    }
+                } else if (MODE == 1) {
+                    const float4 g4 = gyg[r * c4 + q];
+                    const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float xh = (v[i] - mean[i]) * inv[i];
+                        const float pre = xh * ga[i] + be[i];
+                        const float d = pre > 0.f ? gv[i] : gv[i] * bw.slope;
+                        s1[i] += (double)d;
+                        s2[i] += (double)d * (double)xh;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s1[i] += (double)v[i];
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            sh[threadIdx.x][i] = s1[i];
+            sh[threadIdx.x][4 + i] = s2[i];
+        }
+        __syncthreads();
+        if (ly == 0) {
+            for (int j = 1; j < ty; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    s1[i] += sh[j * tx + lx][i];
+                    s2[i] += sh[j * tx + lx][4 + i];
+                }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                atomicAdd(scratch + ((size_t)g * 2 + 0) * c + ch + i, s1[i]);
+                if (MODE != 2) atomicAdd(scratch + ((size_t)g * 2 + 1) * c + ch + i, s2[i]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int MODE>
+static void launch_col_reduce(int groups, int64_t rows, int c, int rpc, unsigned gx, const float* x, const OpBwd& bw,
+                              double* scratch, cudaStream_t st) {
+    const bool v4 = c % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                    (MODE != 1 || (reinterpret_cast<uintptr_t>(bw.gy) & 15) == 0);
+    if (v4) col_reduce4_kernel<MODE><<<dim3(gx, groups), NT, 0, st>>>(rows, c, rpc, x, bw, scratch);
+    else col_reduce_kernel<MODE><<<dim3(gx, groups), NT, 0, st>>>(rows, c, rpc, x, bw, scratch);
+}
+
 __global__ void stats_finalize_kernel(int groups, int64_t rows, int c, float eps, const double* __restrict__ scratch,
                                       float* __restrict__ stats, float* running_mean, float* running_var,
                                       float momentum) {
@@ -159,6 +246,31 @@ __global__ void norm_act_bwd_apply_kernel(int64_t total, int64_t rows, int c, co
     }
 }
 
+__global__ void norm_act_bwd_apply4_kernel(int64_t total4, int64_t rows, int c4, const float4* __restrict__ x, OpBwd bw,
+                                           const double* __restrict__ scratch, float4* __restrict__ gx) {
+    const int c = c4 * 4;
+    const float4* gy = reinterpret_cast<const float4*>(bw.gy);
+    const double inv_rows = 1.0 / (double)rows;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(t % c4) * 4;
+        const int g = (int)(t / (rows * c4));
+        const float4 xv = x[t], gv = gy[t];
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float mean = bw.stats[(size_t)g * 2 * c + ch + i], inv = bw.stats[(size_t)g * 2 * c + c + ch + i];
+            const float ga = bw.gamma ? bw.gamma[ch + i] : 1.f, be = bw.beta ? bw.beta[ch + i] : 0.f;
+            const float xh = (xs[i] - mean) * inv;
+            const float d = (xh * ga + be) > 0.f ? gs[i] : gs[i] * bw.slope;
+            const float m1 = (float)(scratch[((size_t)g * 2 + 0) * c + ch + i] * inv_rows);
+            const float m2 = (float)(scratch[((size_t)g * 2 + 1) * c + ch + i] * inv_rows);
+            o[i] = ga * inv * (d - m1 - xh * m2);
+        }
+        gx[t] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 __global__ void affine_grad_kernel(int groups, int c, const double* __restrict__ scratch, float* ggamma, float* gbeta) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= c) return;
@@ -201,7 +313,7 @@ extern "C" int vgtkb_norm_stats(int groups, int64_t rows, int c, const float* x,
     unsigned gx;
     reduce_geometry(rows, c, groups, rpc, gx);
     OpBwd dummy{};
-    col_reduce_kernel<0><<<dim3(gx, groups), NT, 0, st>>>(rows, c, rpc, x, dummy, scratch);
+    launch_col_reduce<0>(groups, rows, c, rpc, gx, x, dummy, scratch, st);
     stats_finalize_kernel<<<ceil_div(groups * c, 128), 128, 0, st>>>(groups, rows, c, eps, scratch, stats, running_mean,
                                                                     running_var, momentum);
     return check_launch("norm_stats");
@@ -238,10 +350,17 @@ extern "C" int vgtkb_norm_act_backward(int groups, int64_t rows, int c, const fl
     int rpc;
     unsigned gx;
     reduce_geometry(rows, c, groups, rpc, gx);
-    col_reduce_kernel<1><<<dim3(gx, groups), NT, 0, st>>>(rows, c, rpc, x, bw, scratch);
+    launch_col_reduce<1>(groups, rows, c, rpc, gx, x, bw, scratch, st);
     const int64_t total = (int64_t)groups * rows * c;
-    const unsigned grid = (unsigned)(ceil_div64(total, NT) < (int64_t)kNumSMs * 16 ? ceil_div64(total, NT) : kNumSMs * 16);
-    norm_act_bwd_apply_kernel<<<grid, NT, 0, st>>>(total, rows, c, x, bw, scratch, grad_x);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (c % 4 == 0 && al16(x) && al16(grad_y) && al16(grad_x)) {
+        const int64_t total4 = total / 4;
+        const unsigned grid4 = (unsigned)(ceil_div64(total4, NT) < (int64_t)kNumSMs * 16 ? ceil_div64(total4, NT) : kNumSMs * 16);
+        norm_act_bwd_apply4_kernel<<<grid4, NT, 0, st>>>(total4, rows, c / 4, (const float4*)x, bw, scratch, (float4*)grad_x);
+    } else {
+        const unsigned grid = (unsigned)(ceil_div64(total, NT) < (int64_t)kNumSMs * 16 ? ceil_div64(total, NT) : kNumSMs * 16);
+        norm_act_bwd_apply_kernel<<<grid, NT, 0, st>>>(total, rows, c, x, bw, scratch, grad_x);
+    }
     if (grad_gamma || grad_beta)
         affine_grad_kernel<<<ceil_div(c, 128), 128, 0, st>>>(groups, c, scratch, grad_gamma, grad_beta);
     return check_launch("norm_act_backward");
@@ -255,7 +374,7 @@ extern "C" int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratc
     unsigned gx;
     reduce_geometry(rows, c, 1, rpc, gx);
     OpBwd dummy{};
-    col_reduce_kernel<2><<<dim3(gx, 1), NT, 0, st>>>(rows, c, rpc, x, dummy, scratch);
+    launch_col_reduce<2>(1, rows, c, rpc, gx, x, dummy, scratch, st);
     col_sum_finalize_kernel<<<ceil_div(c, 128), 128, 0, st>>>(c, scratch, out);
     return check_launch("col_sum");
 }

@@ -10,14 +10,15 @@ from . import lib as _lib
 
 call, ptr = _lib.call, _lib.ptr
 
-# GEMM arithmetic: 0 = fp32 FFMA, 1 = tcgen05 3xTF32 (fp32-equivalent, default), 2 = tcgen05 1xTF32
+# GEMM arithmetic: 0 = fp32 FFMA, 1 = tcgen05 3xTF32 (fp32-equivalent, default), 2 = tcgen05 1xTF32,
+# 3 = tcgen05 bf16x3 (16 significand bits per operand, ~1e-5; 2x the TF32 tensor rate)
 _GEMM_MODE = 1
 LEAKY_SLOPE = 0.01  # F.leaky_relu default used by the reference blocks
 
 
 def set_gemm_mode(mode):
     global _GEMM_MODE
-    assert mode in (0, 1, 2)
+    assert mode in (0, 1, 2, 3)
     _GEMM_MODE = mode
 
 
@@ -119,7 +120,7 @@ def gemm_nt(a, b, bias=None, mode=None):
     assert b.shape[1] == k
     c = torch.empty((m, n), dtype=torch.float32, device=a.device)
     mode = _GEMM_MODE if mode is None else mode
-    ws = torch.empty(2 * n * k, dtype=torch.float32, device=a.device) if mode == 1 else None   # hi/lo split of b
+    ws = torch.empty(2 * n * k, dtype=torch.float32, device=a.device) if mode in (1, 3) else None   # hi/lo split of b
     call("vgtkb_gemm_nt", a.device, m, n, k, ptr(a), ptr(b), ptr(bias.contiguous()) if bias is not None else None,
          ptr(c), mode, ptr(ws))
     return c
