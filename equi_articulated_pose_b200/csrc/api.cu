@@ -20,7 +20,7 @@ int sgemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C, 
 int tc_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const float* bias, float* C, int passes,
                float* workspace, cudaStream_t st);
 int tc_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C, int accumulate, int passes,
-               cudaStream_t st);
+               float* workspace, cudaStream_t st);
 
 }  // namespace vgtkb
 
@@ -55,7 +55,7 @@ extern "C" int vgtkb_gemm_nt(int64_t M, int N, int K, const float* A, const floa
 }
 
 extern "C" int vgtkb_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C, int accumulate,
-                             int mode, void* stream) {
+                             int mode, float* workspace, void* stream) {
     VGTKB_REQUIRE(M > 0 && N > 0 && R >= 0, "gemm_tn: bad size");
     VGTKB_REQUIRE(mode >= 0 && mode <= 3, "gemm_tn: bad mode %d", mode);
     cudaStream_t st = (cudaStream_t)stream;
@@ -64,7 +64,7 @@ extern "C" int vgtkb_gemm_tn(int M, int N, int64_t R, const float* A, const floa
         return VGTKB_OK;
     }
     if (mode != 0) {
-        const int rc = tc_gemm_tn(M, N, R, A, B, C, accumulate, mode == 2 ? 1 : 3, st);
+        const int rc = tc_gemm_tn(M, N, R, A, B, C, accumulate, mode == 1 ? 3 : (mode == 3 ? 6 : 1), workspace, st);
         if (rc != VGTKB_EUNSUP) return rc;
     }
     return sgemm_tn(M, N, R, A, B, C, accumulate, st);

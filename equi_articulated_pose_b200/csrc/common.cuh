@@ -7,7 +7,7 @@
 
 #include "../../include/vgtkb.h"
 
-#define VGTKB_ABI_VERSION 2
+#define VGTKB_ABI_VERSION 3
 
 namespace vgtkb {
 

@@ -356,6 +356,71 @@ __global__ void split_bf16_kernel(int64_t n, const float* __restrict__ x, uint16
     }
 }
 
+// bf16x3 converter for an MN-major operand (weight-gradient kernel).  The raw fp32 k-block (64 rows of R
+// x W columns) arrives as W/32 TMA boxes of 64 rows x 128 B (8 KB each, 128B swizzle).  It becomes, IN
+// PLACE, W/64 bf16 hi atoms-columns (64 k-rows x 128 B = 64 columns each, 8 KB) followed by W/64 lo ones, in
+// the canonical 128B-swizzled MN-major layout.  Row k of every output tile only depends on row k of the raw
+// boxes, and one warp owns a row: load everything, convert, __syncwarp, store.
+template <int W>
+__device__ __forceinline__ void convert_tn_row_bf16(uint32_t region, int k, int lane) {
+    constexpr int NP = (W + 127) / 128;
+    constexpr uint32_t LO_OFF = (uint32_t)(W / 64) * 8192u;
+    float4 v[NP];
+    const uint32_t rowoff = (uint32_t)(k * 128);
+#pragma unroll
+    for (int t = 0; t < NP; ++t) {
+        const int mn = t * 128 + 4 * lane;
+        if (mn < W) v[t] = ld_shared_v4(region + (uint32_t)(t * 4 + (lane >> 3)) * 8192u + rowoff + (uint32_t)(((lane & 7) ^ (k & 7)) << 4));
+        else v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t h0[NP], h1[NP], l0[NP], l1[NP];
+#pragma unroll
+    for (int t = 0; t < NP; ++t) {
+        h0[t] = pack_bf16x2(v[t].x, v[t].y);
+        h1[t] = pack_bf16x2(v[t].z, v[t].w);
+        l0[t] = pack_bf16x2(v[t].x - __uint_as_float(h0[t] << 16), v[t].y - __uint_as_float(h0[t] & 0xFFFF0000u));
+        l1[t] = pack_bf16x2(v[t].z - __uint_as_float(h1[t] << 16), v[t].w - __uint_as_float(h1[t] & 0xFFFF0000u));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NP; ++t) {
+        const int mn = t * 128 + 4 * lane;
+        if (mn < W) {
+            const int e = mn & 63;
+            const uint32_t dst = region + (uint32_t)(mn >> 6) * 8192u + rowoff + (uint32_t)((((e >> 3) ^ (k & 7)) << 4) | (((e >> 2) & 1) << 3));
+            st_shared_u2(dst, h0[t], h1[t]);
+            st_shared_u2(dst + LO_OFF, l0[t], l1[t]);
+        }
+    }
+}
+
+// four rows of a 128-column operand per call (more loads in flight per warp)
+__device__ __forceinline__ void convert_tn_rows4_bf16(uint32_t region, int k0, int lane) {
+    float4 v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int k = k0 + r;
+        v[r] = ld_shared_v4(region + (uint32_t)(lane >> 3) * 8192u + (uint32_t)(k * 128) + (uint32_t)(((lane & 7) ^ (k & 7)) << 4));
+    }
+    uint32_t h0[4], h1[4], l0[4], l1[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        h0[r] = pack_bf16x2(v[r].x, v[r].y);
+        h1[r] = pack_bf16x2(v[r].z, v[r].w);
+        l0[r] = pack_bf16x2(v[r].x - __uint_as_float(h0[r] << 16), v[r].y - __uint_as_float(h0[r] & 0xFFFF0000u));
+        l1[r] = pack_bf16x2(v[r].z - __uint_as_float(h1[r] << 16), v[r].w - __uint_as_float(h1[r] & 0xFFFF0000u));
+    }
+    __syncwarp();
+    const int mn = 4 * lane, e = mn & 63;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int k = k0 + r;
+        const uint32_t dst = region + (uint32_t)(mn >> 6) * 8192u + (uint32_t)(k * 128) + (uint32_t)((((e >> 3) ^ (k & 7)) << 4) | (((e >> 2) & 1) << 3));
+        st_shared_u2(dst, h0[r], h1[r]);
+        st_shared_u2(dst + 16384u, l0[r], l1[r]);
+    }
+}
+
 // ---------------------------------------------------------------------------------- TN kernel
 // T[i, j] = sum_r P[r, p0+i] * Q[r, q0+j]   (i < 128, j < BN), both operands MN-major in shared
 // memory in the SWIZZLE_128B_BASE32B canonical layout (the layout MN-major tf32 operands require):
@@ -365,13 +430,20 @@ __global__ void split_bf16_kernel(int64_t n, const float* __restrict__ x, uint16
 // k-atom of 4 rows) = 512 B, and one MMA (K = 8) starts 1024 B after the previous one.
 // Work item = (R slice, P tile, Q tile); finished tiles are added into C with red.global.add:
 //   C[(q0+j) * ldc + (p0+i)] += T[i, j]      (lanes run along i: coalesced)
-template <int BN>
+// BF = false: kind::tf32 (k-block = 32 rows of R).  BF = true: bf16x3, kind::f16, k-block = 64 rows of R,
+// operands in the canonical 128B-swizzled MN-major bf16 layout: stage = [mn-atom of 64 columns][64 k-rows x 128 B],
+// LBO (next MN atom) = 8192 B, SBO (next 8 k-rows) = 1024 B, one MMA (K = 16) starts 2048 B after the previous.
+template <int BN, bool BF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q, int Pw, int Qw,
+tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
+                  const __grid_constant__ CUtensorMap map_q2, int Pw, int Qw,
                   float* __restrict__ C, int ldc, int64_t R, int64_t rows_per_split, int splits, int passes, int chunk_kb) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
-    constexpr uint32_t MN_LBO = 4096, K_SBO = 512, L32 = 1;
+    constexpr uint32_t MN_LBO = BF ? 8192 : 4096, K_SBO = BF ? 1024 : 512, L32 = BF ? 2 : 1;
+    constexpr int KR = BF ? 64 : TC_BK;       // rows of R per k-block
+    constexpr int UK = BF ? 16 : 8;           // rows of R per MMA
+    constexpr uint32_t KSTEP_BYTES = BF ? 2048 : 1024;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -394,7 +466,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
         const int sp = item / tiles;
         r0 = (int64_t)sp * rows_per_split;
         const int64_t r1 = r0 + rows_per_split < R ? r0 + rows_per_split : R;
-        return (int)((r1 - r0 + TC_BK - 1) / TC_BK);
+        return (int)((r1 - r0 + KR - 1) / KR);
     };
 
     if (warp < TC_EPI_WARPS) {
@@ -445,7 +517,13 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
-                if (passes == 3) {
+                if (BF) {
+                    const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+                    // only P is converted here: Q (the narrow operand every P tile re-reads) was split to bf16
+                    // hi/lo once in global memory and arrives in its final layout through TMA
+                    for (int task = ct >> 5; task < KR / 4; task += TC_CONV_WARPS) convert_tn_rows4_bf16(st, task * 4, lane);
+                    fence_proxy_async();
+                } else if (passes == 3) {
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
                     convert_region(st, Cfg::A_BYTES, Cfg::A_BYTES / 16, ct);
                     convert_region(st + 2 * Cfg::A_BYTES, Cfg::B_BYTES, Cfg::B_BYTES / 16, ct);
@@ -459,7 +537,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
         // ============================ MMA issuer ============================
         reg_dec_other();
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_BM, BN, 1, 1);   // both operands MN-major
+            const uint32_t idesc = BF ? make_idesc_bf16(TC_BM, BN, 1, 1) : make_idesc_tf32(TC_BM, BN, 1, 1);   // MN-major
             int it = 0, ci = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
                 int64_t r0;
@@ -480,14 +558,20 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
                         const uint32_t p_lo = p_hi + Cfg::A_BYTES;
                         const uint32_t q_hi = p_lo + Cfg::A_BYTES;
                         const uint32_t q_lo = q_hi + Cfg::B_BYTES;
-                        const int64_t rrem = rows - (int64_t)kb * TC_BK;
-                        const int ksteps = rrem >= TC_BK ? TC_BK / 8 : (int)((rrem + 7) / 8);
+                        const int64_t rrem = rows - (int64_t)kb * KR;
+                        const int ksteps = rrem >= KR ? KR / UK : (int)((rrem + UK - 1) / UK);
                         for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint32_t koff = ks * 1024;   // 8 k-rows = two k-atoms
+                            const uint32_t koff = ks * KSTEP_BYTES;   // one MMA's rows of R
                             const uint64_t dp_hi = make_smem_desc(p_hi + koff, MN_LBO, K_SBO, L32);
                             const uint64_t dq_hi = make_smem_desc(q_hi + koff, MN_LBO, K_SBO, L32);
                             const uint32_t first = ((kb - kb0) | ks) != 0;
-                            if (passes == 3) {
+                            if (BF) {
+                                const uint64_t dp_lo = make_smem_desc(p_lo + koff, MN_LBO, K_SBO, L32);
+                                const uint64_t dq_lo = make_smem_desc(q_lo + koff, MN_LBO, K_SBO, L32);
+                                umma_bf16(d_tmem, dp_lo, dq_hi, idesc, first);
+                                umma_bf16(d_tmem, dp_hi, dq_lo, idesc, 1);
+                                umma_bf16(d_tmem, dp_hi, dq_hi, idesc, 1);
+                            } else if (passes == 3) {
                                 const uint64_t dp_lo = make_smem_desc(p_lo + koff, MN_LBO, K_SBO, L32);
                                 const uint64_t dq_lo = make_smem_desc(q_lo + koff, MN_LBO, K_SBO, L32);
                                 umma_tf32(d_tmem, dp_lo, dq_hi, idesc, first);
@@ -510,7 +594,9 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
         if (lane == 0) {
             tma_prefetch_desc(&map_p);
             tma_prefetch_desc(&map_q);
-            const uint32_t tx = (uint32_t)Cfg::A_BYTES + (uint32_t)Cfg::B_BYTES;
+            if (BF) tma_prefetch_desc(&map_q2);
+            const uint32_t tx = ((uint32_t)Cfg::A_BYTES + (uint32_t)Cfg::B_BYTES) * (BF ? 2u : 1u);
+            constexpr uint32_t BOX_BYTES = BF ? 8192 : 4096;
             int it = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
                 const int tile = item % tiles;
@@ -521,14 +607,22 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
                     const int s = it % STAGES;
                     mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
                     unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
-                    const int row = (int)(r0 + (int64_t)kb * TC_BK);
+                    const int row = (int)(r0 + (int64_t)kb * KR);
                     mbar_arrive_expect_tx(&bars.raw_full[s], tx);
 #pragma unroll
                     for (int a = 0; a < TC_BM / 32; ++a)
-                        tma_load_2d(st + a * 4096, &map_p, p0 + a * 32, row, &bars.raw_full[s]);
+                        tma_load_2d(st + a * BOX_BYTES, &map_p, p0 + a * 32, row, &bars.raw_full[s]);
+                    if (BF) {
 #pragma unroll
-                    for (int a = 0; a < BN / 32; ++a)
-                        tma_load_2d(st + 2 * Cfg::A_BYTES + a * 4096, &map_q, q0 + a * 32, row, &bars.raw_full[s]);
+                        for (int a = 0; a < BN / 64; ++a) {   // bf16 hi / lo atoms of 64 columns, final layout
+                            tma_load_2d(st + 2 * Cfg::A_BYTES + a * 8192, &map_q, q0 + a * 64, row, &bars.raw_full[s]);
+                            tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + a * 8192, &map_q2, q0 + a * 64, row, &bars.raw_full[s]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < BN / 32; ++a)
+                            tma_load_2d(st + 2 * Cfg::A_BYTES + a * BOX_BYTES, &map_q, q0 + a * 32, row, &bars.raw_full[s]);
+                    }
                 }
             }
         }
@@ -660,42 +754,59 @@ int tc_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const fl
     return rc;
 }
 
-template <int BN>
-static int launch_tn(const float* P, int Pw, const float* Q, int Qw, float* C, int ldc, int64_t R, int passes,
+template <int BN, bool BF>
+static int launch_tn(const float* P, int Pw, const void* Q, const void* Q2, int Qw, float* C, int ldc, int64_t R, int passes,
                      cudaStream_t st) {
     using Cfg = TcCfg<BN>;
-    CUtensorMap mp, mq;
-    int rc = make_map_2d(&mp, P, R, Pw, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    constexpr int KR = BF ? 64 : TC_BK;
+    CUtensorMap mp, mq, mq2;
+    const CUtensorMapSwizzle swz = BF ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    int rc = make_map_2d(&mp, P, R, Pw, KR, swz);
     if (rc) return rc;
-    rc = make_map_2d(&mq, Q, R, Qw, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    rc = make_map_2d(&mq, Q, R, Qw, KR, swz, BF);      // BF: bf16 hi, box = 64 columns x 64 rows
+    if (rc) return rc;
+    rc = make_map_2d(&mq2, Q2, R, Qw, KR, swz, BF);    // BF: bf16 lo (tf32 path: unused duplicate)
     if (rc) return rc;
     const int tiles = ceil_div(Pw, TC_BM) * ceil_div(Qw, BN);
     int64_t splits = ceil_div64((int64_t)2 * num_sms(), tiles);
     const int64_t max_splits = ceil_div64(R, 512);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
-    int64_t rps = ceil_div64(ceil_div64(R, splits), TC_BK) * TC_BK;
+    int64_t rps = ceil_div64(ceil_div64(R, splits), KR) * KR;
     splits = ceil_div64(R, rps);
     const int64_t items = splits * tiles;
     const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024;
-    auto kern = tc_gemm_tn_kernel<BN>;
+    auto kern = tc_gemm_tn_kernel<BN, BF>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)(items < num_sms() ? items : num_sms());
-    kern<<<grid, TC_THREADS, smem, st>>>(mp, mq, Pw, Qw, C, ldc, R, rps, (int)splits, passes, default_chunk(passes));
+    kern<<<grid, TC_THREADS, smem, st>>>(mp, mq, mq2, Pw, Qw, C, ldc, R, rps, (int)splits, passes, BF ? 1 : default_chunk(passes));
     return check_launch("gemm_tn(tcgen05)");
 }
 
 // C[M,N] (+)= A[R,M]^T B[R,N]:  P = B (tiles of 128 over N), Q = A (tiles of <= 256 over M)
+// `workspace` (bf16x3 only): R*M floats, holds the bf16 hi/lo split of A.
 int tc_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C, int accumulate, int passes,
-               cudaStream_t st) {
+               float* workspace, cudaStream_t st) {
     if (M % 4 != 0 || N % 4 != 0 || R < 64 || R >= ((int64_t)1 << 31) ||
         ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) != 0)
         return VGTKB_EUNSUP;
     if ((int64_t)M * N < 64 * 64 / 4) return VGTKB_EUNSUP;   // tiny outputs: the FFMA split-R kernel is fine
+    if (passes == 6 && (M % 8 != 0 || workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0))
+        passes = 3;                                           // bf16 rows must be 16-byte aligned: 3xTF32 instead
     if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
-    if (M <= 64) return launch_tn<64>(B, N, A, M, C, N, R, passes, st);
-    if (M <= 128) return launch_tn<128>(B, N, A, M, C, N, R, passes, st);
-    return launch_tn<256>(B, N, A, M, C, N, R, passes, st);
+    if (passes == 6) {   // bf16x3
+        const int64_t na = R * (int64_t)M;
+        uint16_t* hi = reinterpret_cast<uint16_t*>(workspace);
+        uint16_t* lo = hi + na;
+        const int blocks = (int)(ceil_div64(na, 256) < 2368 ? ceil_div64(na, 256) : 2368);
+        split_bf16_kernel<<<blocks, 256, 0, st>>>(na, A, hi, lo);
+        if (M <= 64) return launch_tn<64, true>(B, N, hi, lo, M, C, N, R, 3, st);
+        if (M <= 128) return launch_tn<128, true>(B, N, hi, lo, M, C, N, R, 3, st);
+        return launch_tn<256, true>(B, N, hi, lo, M, C, N, R, 3, st);
+    }
+    if (M <= 64) return launch_tn<64, false>(B, N, A, A, M, C, N, R, passes, st);
+    if (M <= 128) return launch_tn<128, false>(B, N, A, A, M, C, N, R, passes, st);
+    return launch_tn<256, false>(B, N, A, A, M, C, N, R, passes, st);
 }
 
 }  // namespace vgtkb

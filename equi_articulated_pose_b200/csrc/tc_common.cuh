@@ -161,6 +161,9 @@ __device__ __forceinline__ void split_bf16x8(const float4& v0, const float4& v1,
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
+__device__ __forceinline__ void st_shared_u2(uint32_t saddr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
 __device__ __forceinline__ void st_shared_u4(uint32_t saddr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

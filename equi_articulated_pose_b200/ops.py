@@ -10,9 +10,10 @@ from . import lib as _lib
 
 call, ptr = _lib.call, _lib.ptr
 
-# GEMM arithmetic: 0 = fp32 FFMA, 1 = tcgen05 3xTF32 (fp32-equivalent, default), 2 = tcgen05 1xTF32,
-# 3 = tcgen05 bf16x3 (16 significand bits per operand, ~1e-5; 2x the TF32 tensor rate)
-_GEMM_MODE = 1
+# GEMM arithmetic: 0 = fp32 FFMA, 1 = tcgen05 3xTF32 (~1e-6 per GEMM), 2 = tcgen05 1xTF32 (~1e-3),
+# 3 = tcgen05 bf16x3 (default: 16 significand bits per operand, ~5e-6 per GEMM, 3.5e-5 on the backbone output at
+#     config-2 size against the 1e-4 bar; 2x the TF32 tensor rate)
+_GEMM_MODE = 3
 LEAKY_SLOPE = 0.01  # F.leaky_relu default used by the reference blocks
 
 
@@ -133,7 +134,9 @@ def gemm_tn(a, b, mode=None):
     n = b.shape[1]
     assert b.shape[0] == r
     c = torch.empty((m, n), dtype=torch.float32, device=a.device)
-    call("vgtkb_gemm_tn", a.device, m, n, r, ptr(a), ptr(b), ptr(c), 0, _GEMM_MODE if mode is None else mode)
+    mode = _GEMM_MODE if mode is None else mode
+    ws = torch.empty(r * m, dtype=torch.float32, device=a.device) if mode == 3 else None   # bf16 hi/lo split of a
+    call("vgtkb_gemm_tn", a.device, m, n, r, ptr(a), ptr(b), ptr(c), 0, mode, ptr(ws))
     return c
 
 

@@ -120,13 +120,17 @@ int vgtkb_row_gather_backward(int b, int n, int m, int width, const float* grad_
  *   vgtkb_gemm_nt: C[M,N] = A[M,K] * B[N,K]^T (+ bias[N])
  *   vgtkb_gemm_tn: C[M,N] (+)= A[R,M]^T * B[R,N]   (weight gradients; reduction over rows R)
  * `mode`: 0 = fp32 FFMA (CUDA cores), 1 = tcgen05 3xTF32 (fp32-equivalent, sm_100a tensor cores),
- *         2 = tcgen05 single-pass TF32 (fast, ~1e-3 relative).
- * `workspace` (gemm_nt, mode 1): device scratch of 2*N*K floats for the hi/lo split of B; when NULL
- * the library allocates it stream-ordered (cudaMallocAsync), which is slower. */
+ *         2 = tcgen05 single-pass TF32 (fast, ~1e-3 relative),
+ *         3 = tcgen05 bf16x3 (operands split into two bf16, 16 significand bits, ~5e-6 relative; 2x the TF32 rate).
+ * In modes 1-3 the tensor core only accumulates 64 reduction elements at a time in TMEM; the running sum
+ * is kept in fp32 registers with round-to-nearest adds (the TMEM accumulator rounds toward zero).
+ * `workspace`: device scratch, 16-byte aligned.  gemm_nt, modes 1/3: 2*N*K floats (hi/lo split of B); when
+ * NULL the library allocates it stream-ordered (cudaMallocAsync), which is slower.  gemm_tn, mode 3: R*M
+ * floats (bf16 hi/lo split of A); when NULL mode 3 runs as mode 1. */
 int vgtkb_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const float* bias,
                   float* C, int mode, float* workspace, void* stream);
 int vgtkb_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C,
-                  int accumulate, int mode, void* stream);
+                  int accumulate, int mode, float* workspace, void* stream);
 
 /* Normalisation + leaky_relu on channels-last rows X[groups][rows_per_group][c].
  * groups == 1 : BatchNorm2d training statistics (base_so3conv.py:113,125-131)

@@ -266,7 +266,7 @@ def test_intra_group_backward(dev, ops):
 
 
 # ------------------------------------------------------------------------------ GEMM / norm
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 3])
 @pytest.mark.parametrize("M,N,K", [(128 * 60, 64, 24), (3000, 64, 1536), (7680, 256, 3072), (999, 24, 192), (257, 130, 33)])
 def test_gemm_nt_tn(dev, ops, mode, M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
@@ -274,7 +274,8 @@ def test_gemm_nt_tn(dev, ops, mode, M, N, K):
     bias = torch.randn(N, generator=g)
     want = (A.double() @ B.double().t() + bias.double()).float()
     # mode 1 = 3xTF32 on tcgen05 with chunked round-to-nearest accumulation (~1e-6); mode 0 = FFMA
-    tol = 2e-5 if mode == 0 else 5e-6
+    # mode 3 = bf16x3 (two bf16 per operand: ~5e-6)
+    tol = {0: 2e-5, 1: 5e-6, 3: 3e-5}[mode]
     got = ops.gemm_nt(A.to(dev), B.to(dev), bias.to(dev), mode=mode)
     assert rel_err(got, want) < tol
     D = torch.randn(M, N, generator=g)
@@ -376,7 +377,7 @@ def _grad_errors(net, sdo, sd64):
     return rows
 
 
-@pytest.mark.parametrize("gemm_mode", [0, 1])
+@pytest.mark.parametrize("gemm_mode", [0, 1, 3])
 @pytest.mark.parametrize("loss_kind", ["proj", "square"])
 def test_classic_backbone_fwd_bwd_vs_oracle(dev, ops, loss_kind, gemm_mode):
     """Full 7-layer classic backbone (cls_so3net_pn defaults), N=256, B=2, fwd+bwd vs the oracle.
@@ -404,8 +405,9 @@ def test_classic_backbone_fwd_bwd_vs_oracle(dev, ops, loss_kind, gemm_mode):
         if scale < 1e-6 * gmax:   # structurally zero gradients (bias before BatchNorm, first skip branch)
             assert e_gpu < 1e-4 * gmax, (name, e_gpu)
         else:
-            # mode 0 (FFMA fallback) sums the weight gradient with fp32 atomics over 256-row slices: a
-            # noisier realisation of the same floor (observed up to 8e-2 on single tensors)
+            # mode 0 (FFMA fallback) sums the weight gradient with fp32 atomics over 256-row slices and mode 3
+            # (bf16x3) carries 16 significand bits per operand: noisier realisations of the same floor
+            # (observed up to 8e-2 / 6e-2 of the tensor maximum on single tensors)
             floor = 3e-2 if gemm_mode == 1 else 1e-1
             assert e_gpu <= max(5 * e_ref, floor * scale), (name, e_gpu / scale, e_ref / scale)
 
