@@ -191,6 +191,15 @@ def summarize_profile(records, steps, peaks):
         d["ms"] += ms
         d["calls"] += 1
         d[kind] += amt
+    shapes = {}
+    for name, a, e0, e1 in records:
+        if name in ("vgtkb_gemm_nt", "vgtkb_gemm_tn", "vgtkb_inter_group_forward", "vgtkb_inter_group_backward"):
+            key = name[6:] + str(tuple(int(v) for v in (a[:3] if "gemm" in name else a[:7])))
+            d = shapes.setdefault(key, [0.0, 0])
+            d[0] += e0.elapsed_time(e1)
+            d[1] += 1
+    shape_table = {k: {"ms_per_step": v[0] / steps, "calls_per_step": v[1] / steps}
+                   for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:24]}
     total = sum(d["ms"] for d in agg.values()) or 1.0
     table = {k: {"ms_per_step": d["ms"] / steps, "calls_per_step": d["calls"] / steps, "share": d["ms"] / total}
              for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
@@ -212,7 +221,7 @@ def summarize_profile(records, steps, peaks):
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "peak_source": peaks.get("_source", "fallback"),
                 "avg_launch_ms": d["ms"] / d["calls"], "algorithmic_per_launch": d["byte"] / d["calls"]}
-    return roof, table
+    return roof, table, shape_table
 
 
 def load_peaks():
@@ -313,7 +322,7 @@ def run_ours(args):
 
     if rank == 0:
         peaks = load_peaks()
-        roof, table = summarize_profile(records, args.steps, peaks)
+        roof, table, shape_table = summarize_profile(records, args.steps, peaks)
         pts_per_step = total_clouds * N_POINTS
         line = {"metric": METRIC, "value": pts_per_step * args.steps / (ms * 1e-3), "unit": "points/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -324,7 +333,7 @@ def run_ours(args):
                            "l2": "256 MiB buffer written between steps (L2 flush); per-step activations >> 126 MB L2"},
                 "e2e": {"value": pts_per_step * args.steps / (ms_e2e * 1e-3), "unit": "points/s",
                         "h2d_bytes_per_step": clouds_host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_table": table,
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_table": table, "shape_table": shape_table,
                 "loss": float(loss_host)}
         if world == 1 and not args.no_cpu_baseline:
             r = time_oracle(1, 1)

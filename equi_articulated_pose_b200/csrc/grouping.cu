@@ -74,8 +74,13 @@ template <>
 struct VecT<4> { using type = float4; };
 
 // fast path: ci % (32*CPL) == 0, k <= 24.  grid (p, b), 8 warps, warp <-> anchor.
+// The 24 kernel points are processed in two groups of 12 so that the accumulators (12 x CPL registers)
+// leave room for 3 CTAs per SM (the first version kept 24 x CPL: 153/205 registers, 1 CTA per SM, 12 %
+// occupancy, latency bound -- profiles/r1_ncu_inter_group.txt); the second pass re-reads the neighbour
+// rows from L1/L2.
+constexpr int IG_KG = 12;
 template <int CPL>
-__global__ void __launch_bounds__(IG_WARPS * 32)
+__global__ void __launch_bounds__(IG_WARPS * 32, 3)
 inter_group_fwd_kernel(int n, int p, int nn, int a, int k, int ci, const float* __restrict__ xyz,
                        const float* __restrict__ sxyz, const int32_t* __restrict__ idx,
                        const float* __restrict__ rk, float inv_sigma, const float* __restrict__ feats,
@@ -91,6 +96,7 @@ inter_group_fwd_kernel(int n, int p, int nn, int a, int k, int ci, const float* 
     __syncthreads();
     float* w_a = s_w + warp * nn * IG_KP;
     const int chunks = ci / (32 * CPL);
+    const float* fb = feats + (size_t)b * n * a * ci;
     for (int ai = warp; ai < a; ai += IG_WARPS) {
         __syncwarp();
         warp_weights(lane, ai, nn, k, rk, inv_sigma, s_g, w_a);
@@ -98,40 +104,46 @@ inter_group_fwd_kernel(int n, int p, int nn, int a, int k, int ci, const float* 
         float* out = grouped + (((size_t)b * p + pi) * a + ai) * (size_t)k * ci;
         for (int ch = 0; ch < chunks; ++ch) {
             const int c0 = ch * 32 * CPL + lane * CPL;
-            float acc[IG_KP][CPL];
+            const float* fcol = fb + (size_t)ai * ci + c0;
+#pragma unroll 1
+            for (int kg = 0; kg < IG_KP; kg += IG_KG) {
+                float acc[IG_KG][CPL];
 #pragma unroll
-            for (int i = 0; i < IG_KP; ++i)
+                for (int i = 0; i < IG_KG; ++i)
 #pragma unroll
-                for (int u = 0; u < CPL; ++u) acc[i][u] = 0.f;
+                    for (int u = 0; u < CPL; ++u) acc[i][u] = 0.f;
 #pragma unroll 4
-            for (int ni = 0; ni < nn; ++ni) {
-                const V xv = *reinterpret_cast<const V*>(feats + (((size_t)b * n + s_j[ni]) * a + ai) * ci + c0);
-                const float* xs = reinterpret_cast<const float*>(&xv);
-                const float4* wr = reinterpret_cast<const float4*>(w_a + ni * IG_KP);
+                for (int ni = 0; ni < nn; ++ni) {
+                    const V xv = __ldg(reinterpret_cast<const V*>(fcol + (size_t)s_j[ni] * a * ci));
+                    const float* xs = reinterpret_cast<const float*>(&xv);
+                    const float4* wr = reinterpret_cast<const float4*>(w_a + ni * IG_KP + kg);
 #pragma unroll
-                for (int k4 = 0; k4 < IG_KP / 4; ++k4) {
-                    const float4 w4 = wr[k4];
-                    const float ws[4] = {w4.x, w4.y, w4.z, w4.w};
+                    for (int k4 = 0; k4 < IG_KG / 4; ++k4) {
+                        const float4 w4 = wr[k4];
+                        const float ws[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int u = 0; u < CPL; ++u) acc[k4 * 4 + i][u] = fmaf(ws[i], xs[u], acc[k4 * 4 + i][u]);
+                            for (int u = 0; u < CPL; ++u) acc[k4 * 4 + i][u] = fmaf(ws[i], xs[u], acc[k4 * 4 + i][u]);
+                    }
                 }
+#pragma unroll
+                for (int ki = 0; ki < IG_KG; ++ki)
+                    if (kg + ki < k) {
+                        V o;
+                        float* os = reinterpret_cast<float*>(&o);
+#pragma unroll
+                        for (int u = 0; u < CPL; ++u) os[u] = acc[ki][u];
+                        __stcs(reinterpret_cast<V*>(out + (size_t)(kg + ki) * ci + c0), o);   // streaming: G is read once, later
+                    }
             }
-#pragma unroll
-            for (int ki = 0; ki < IG_KP; ++ki)
-                if (ki < k) {
-                    V o;
-                    float* os = reinterpret_cast<float*>(&o);
-#pragma unroll
-                    for (int u = 0; u < CPL; ++u) os[u] = acc[ki][u];
-                    *reinterpret_cast<V*>(out + (size_t)ki * ci + c0) = o;
-                }
         }
     }
 }
 
 // backward of the fast path: dX[b, j_n, a, c] += sum_k w[n][k] dG[b,p,a,k,c]
+// (bound by the red.global.add traffic: the 16-byte vector atomics of CPL = 4 beat higher occupancy with
+// CPL = 2 -- measured 2.9 ms vs 3.4 ms per step)
 template <int CPL>
 __global__ void __launch_bounds__(IG_WARPS * 32)
 inter_group_bwd_kernel(int n, int p, int nn, int a, int k, int ci, const float* __restrict__ xyz,
@@ -161,7 +173,7 @@ inter_group_bwd_kernel(int n, int p, int nn, int a, int k, int ci, const float* 
             for (int ki = 0; ki < IG_KP; ++ki) {
                 V v;
                 float* vs = reinterpret_cast<float*>(&v);
-                if (ki < k) v = *reinterpret_cast<const V*>(gin + (size_t)ki * ci + c0);
+                if (ki < k) v = __ldcs(reinterpret_cast<const V*>(gin + (size_t)ki * ci + c0));   // dG is read once
                 else
 #pragma unroll
                     for (int u = 0; u < CPL; ++u) vs[u] = 0.f;
