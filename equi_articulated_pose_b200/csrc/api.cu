@@ -22,6 +22,11 @@ int tc_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const fl
 int tc_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C, int accumulate, int passes,
                float* workspace, cudaStream_t st);
 
+int tc_gemm_nt_gather(int64_t points, int anchors, int kk_n, int c_n, int N, const int32_t* table, const float* X,
+                      const float* B, const float* bias, float* C, int passes, float* workspace, cudaStream_t st);
+int tc_gemm_tn_gather(int64_t points, int anchors, int kk_n, int c_n, int M, const int32_t* table, const float* X,
+                      const float* Y, float* C, int accumulate, int passes, float* workspace, cudaStream_t st);
+
 }  // namespace vgtkb
 
 using namespace vgtkb;
@@ -68,4 +73,27 @@ extern "C" int vgtkb_gemm_tn(int M, int N, int64_t R, const float* A, const floa
         if (rc != VGTKB_EUNSUP) return rc;
     }
     return sgemm_tn(M, N, R, A, B, C, accumulate, st);
+}
+
+static int passes_of(int mode) { return mode == 1 ? 3 : (mode == 3 ? 6 : 1); }
+
+extern "C" int vgtkb_gather_gemm_nt(int64_t points, int anchors, int kk, int c, int n, const int32_t* table, const float* x,
+                                    const float* w, const float* bias, float* out, int mode, float* workspace, void* stream) {
+    VGTKB_REQUIRE(points >= 0 && anchors > 0 && kk > 0 && c > 0 && n > 0, "gather_gemm_nt: bad size");
+    VGTKB_REQUIRE(mode >= 1 && mode <= 3, "gather_gemm_nt: mode %d (the gather GEMM only exists on the tensor-core path)", mode);
+    if (points == 0) return VGTKB_OK;
+    const int rc = tc_gemm_nt_gather(points, anchors, kk, c, n, table, x, w, bias, out, passes_of(mode), workspace,
+                                     (cudaStream_t)stream);
+    if (rc == VGTKB_EUNSUP) set_error("gather_gemm_nt: unsupported shape (needs c %% 64 == 0, 16-byte aligned operands)");
+    return rc;
+}
+
+extern "C" int vgtkb_gather_gemm_tn(int64_t points, int anchors, int kk, int c, int m, const int32_t* table, const float* x,
+                                    const float* y, float* out, int accumulate, int mode, float* workspace, void* stream) {
+    VGTKB_REQUIRE(points >= 0 && anchors > 0 && kk > 0 && c > 0 && m > 0, "gather_gemm_tn: bad size");
+    VGTKB_REQUIRE(mode >= 1 && mode <= 3, "gather_gemm_tn: mode %d (the gather GEMM only exists on the tensor-core path)", mode);
+    const int rc = tc_gemm_tn_gather(points, anchors, kk, c, m, table, x, y, out, accumulate, passes_of(mode), workspace,
+                                     (cudaStream_t)stream);
+    if (rc == VGTKB_EUNSUP) set_error("gather_gemm_tn: unsupported shape (needs c %% 32 == 0, m %% 4 == 0, points >= 64)");
+    return rc;
 }

@@ -7,7 +7,7 @@
 
 #include "../../include/vgtkb.h"
 
-#define VGTKB_ABI_VERSION 3
+#define VGTKB_ABI_VERSION 4
 
 namespace vgtkb {
 

@@ -75,6 +75,17 @@ struct TcCfg {
     static_assert(BN % 64 == 0, "BN must be a multiple of 64");
 };
 
+// Gather-GEMM addressing (intra-anchor convolution, vgtk/vgtk/so3conv/functional.py:2553-2567 fused into the
+// contraction): the activation operand is never materialised.  X is [points, anchors, c]; a tile owns ONE
+// output anchor `an` and 128 (64) consecutive points, so the k-block (kk, c0..) of its operand is the regular
+// box X[points, table[an*kk_n + kk], c0..] -- one 3-D TMA load with the middle coordinate looked up.
+struct TcGather {
+    int anchors;            // 0: plain GEMM
+    int kk_n;               // neighbours per anchor (12)
+    int c;                  // channels of X
+    const int32_t* table;   // [anchors, kk_n]
+};
+
 struct TcBarriers {
     uint64_t raw_full[6], full[6], empty[6], tfull[2], tempty[2];
     uint32_t tmem_base;
@@ -135,7 +146,7 @@ template <int BN, bool BF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                   const __grid_constant__ CUtensorMap map_blo, const float* __restrict__ bias, float* __restrict__ C,
-                  int64_t M, int N, int K, int passes, int chunk_kb) {
+                  int64_t M, int N, int K, int passes, int chunk_kb, TcGather ga) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -146,7 +157,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (int)((M + TC_BM - 1) / TC_BM);
     const int n_tiles = (N + BN - 1) / BN;
-    const int total_tiles = m_tiles * n_tiles;
+    const int a_cnt = ga.anchors > 0 ? ga.anchors : 1;      // gather: M counts points, a tile owns one anchor
+    const int total_tiles = m_tiles * a_cnt * n_tiles;      // tile -> (mt, an, nt), nt fastest
     constexpr int KBE = BF ? 64 : TC_BK;     // K elements per k-block (one 128-byte operand row)
     constexpr int UK = BF ? 16 : 8;          // K elements per MMA
     const int nkb = (K + KBE - 1) / KBE;
@@ -168,7 +180,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         int ci = 0;
         const bool vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int mt = tile / n_tiles, nt = tile % n_tiles;
+            const int nt = tile % n_tiles, an = (tile / n_tiles) % a_cnt, mt = tile / (n_tiles * a_cnt);
             for (int kb0 = 0; kb0 < nkb; kb0 += chunk_kb, ++ci) {
                 const int buf = ci & 1;
                 mbar_wait_guard(&bars.tfull[buf], (ci >> 1) & 1);
@@ -211,7 +223,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     o.x += bb[0]; o.y += bb[1]; o.z += bb[2]; o.w += bb[3];
                     const int64_t grow = row0 + rr;
                     if (grow < M) {
-                        float* dst = C + grow * N + col;
+                        float* dst = C + (grow * a_cnt + an) * N + col;
                         if (vec_ok && col + 4 <= N) {
                             *reinterpret_cast<float4*>(dst) = o;
                         } else {
@@ -310,14 +322,21 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                                    : (uint32_t)Cfg::A_BYTES + (uint32_t)Cfg::B_BYTES * (passes == 3 ? 2u : 1u);
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / n_tiles, nt = tile % n_tiles;
+                const int nt = tile % n_tiles, an = (tile / n_tiles) % a_cnt, mt = tile / (n_tiles * a_cnt);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
                     unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&bars.raw_full[s], tx);
-                    tma_load_2d(st, &map_a, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
-                    if (BF) tma_load_2d(st + Cfg::A_BYTES, &map_a, kb * KBE + 32, mt * TC_BM, &bars.raw_full[s]);
+                    if (ga.anchors > 0) {
+                        const int kcol = kb * KBE, kk = kcol / ga.c, c0 = kcol - kk * ga.c;
+                        const int mid = __ldg(ga.table + an * ga.kk_n + kk);
+                        tma_load_3d(st, &map_a, c0, mid, mt * TC_BM, &bars.raw_full[s]);
+                        if (BF) tma_load_3d(st + Cfg::A_BYTES, &map_a, c0 + 32, mid, mt * TC_BM, &bars.raw_full[s]);
+                    } else {
+                        tma_load_2d(st, &map_a, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
+                        if (BF) tma_load_2d(st + Cfg::A_BYTES, &map_a, kb * KBE + 32, mt * TC_BM, &bars.raw_full[s]);
+                    }
                     tma_load_2d(st + 2 * Cfg::A_BYTES, &map_bhi, kb * KBE, nt * BN, &bars.raw_full[s]);
                     if (BF || passes == 3)
                         tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &map_blo, kb * KBE, nt * BN, &bars.raw_full[s]);
@@ -437,7 +456,8 @@ template <int BN, bool BF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
                   const __grid_constant__ CUtensorMap map_q2, int Pw, int Qw,
-                  float* __restrict__ C, int ldc, int64_t R, int64_t rows_per_split, int splits, int passes, int chunk_kb) {
+                  float* __restrict__ C, int ldc, int64_t R, int64_t rows_per_split, int splits, int passes, int chunk_kb,
+                  TcGather ga, int anchors_per_item) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr uint32_t MN_LBO = BF ? 8192 : 4096, K_SBO = BF ? 1024 : 512, L32 = BF ? 2 : 1;
@@ -453,7 +473,10 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
     const int p_tiles = (Pw + TC_BM - 1) / TC_BM;
     const int q_tiles = (Qw + BN - 1) / BN;
     const int tiles = p_tiles * q_tiles;
-    const int items = tiles * splits;
+    // gather mode (intra-conv weight gradient): R counts points, an item also owns a group of output anchors and
+    // runs through them one after the other with the SAME register accumulators (one red.global.add pass per item)
+    const int n_groups = ga.anchors > 0 ? (ga.anchors + anchors_per_item - 1) / anchors_per_item : 1;
+    const int items = tiles * n_groups * splits;        // item -> (sp, grp, tile), tile fastest
 
     if (threadIdx.x == 0) tc_init_barriers<STAGES>(bars);
     if (warp == TC_MMA_WARP) tmem_alloc(&bars.tmem_base, Cfg::TMEM_COLS);
@@ -463,10 +486,17 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
     const uint32_t tmem_base = bars.tmem_base;
 
     auto item_nkb = [&](int item, int64_t& r0) {
-        const int sp = item / tiles;
+        const int sp = item / (tiles * n_groups);
         r0 = (int64_t)sp * rows_per_split;
         const int64_t r1 = r0 + rows_per_split < R ? r0 + rows_per_split : R;
         return (int)((r1 - r0 + KR - 1) / KR);
+    };
+    // anchors [a0, a0 + nan) of an item (plain GEMM: one pseudo anchor)
+    auto item_anchors = [&](int item, int& a0) {
+        if (ga.anchors <= 0) { a0 = 0; return 1; }
+        const int grp = (item / tiles) % n_groups;
+        a0 = grp * anchors_per_item;
+        return min(anchors_per_item, ga.anchors - a0);
     };
 
     if (warp < TC_EPI_WARPS) {
@@ -481,8 +511,9 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
             const int tile = item % tiles;
             const int p0 = (tile / q_tiles) * TC_BM, q0 = (tile % q_tiles) * BN;
             int64_t r0;
-            const int nkb = item_nkb(item, r0);
-            for (int kb0 = 0; kb0 < nkb; kb0 += chunk_kb, ++ci) {
+            int a0;
+            const int nblk = item_nkb(item, r0) * item_anchors(item, a0);
+            for (int kb0 = 0; kb0 < nblk; kb0 += chunk_kb, ++ci) {
                 const int buf = ci & 1;
                 mbar_wait_guard(&bars.tfull[buf], (ci >> 1) & 1);
                 tc_fence_after();
@@ -513,8 +544,9 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
         int it = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             int64_t r0;
-            const int nkb = item_nkb(item, r0);
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
+            int a0;
+            const int nblk = item_nkb(item, r0) * item_anchors(item, a0);
+            for (int kb = 0; kb < nblk; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
                 if (BF) {
@@ -541,14 +573,16 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
             int it = 0, ci = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
                 int64_t r0;
+                int a0;
                 const int nkb = item_nkb(item, r0);
+                const int nblk = nkb * item_anchors(item, a0);
                 const int64_t rows = (r0 + rows_per_split < R ? r0 + rows_per_split : R) - r0;
-                for (int kb0 = 0; kb0 < nkb; kb0 += chunk_kb, ++ci) {
+                for (int kb0 = 0; kb0 < nblk; kb0 += chunk_kb, ++ci) {
                     const int buf = ci & 1;
                     mbar_wait_guard(&bars.tempty[buf], ((ci >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-                    const int kb1 = kb0 + chunk_kb < nkb ? kb0 + chunk_kb : nkb;
+                    const int kb1 = kb0 + chunk_kb < nblk ? kb0 + chunk_kb : nblk;
                     for (int kb = kb0; kb < kb1; ++kb, ++it) {
                         const int s = it % STAGES;
                         mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
@@ -558,7 +592,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
                         const uint32_t p_lo = p_hi + Cfg::A_BYTES;
                         const uint32_t q_hi = p_lo + Cfg::A_BYTES;
                         const uint32_t q_lo = q_hi + Cfg::B_BYTES;
-                        const int64_t rrem = rows - (int64_t)kb * KR;
+                        const int64_t rrem = rows - (int64_t)(kb % nkb) * KR;
                         const int ksteps = rrem >= KR ? KR / UK : (int)((rrem + UK - 1) / UK);
                         for (int ks = 0; ks < ksteps; ++ks) {
                             const uint32_t koff = ks * KSTEP_BYTES;   // one MMA's rows of R
@@ -602,13 +636,41 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
                 const int tile = item % tiles;
                 const int p0 = (tile / q_tiles) * TC_BM, q0 = (tile % q_tiles) * BN;
                 int64_t r0;
+                int a0;
                 const int nkb = item_nkb(item, r0);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int nblk = nkb * item_anchors(item, a0);
+                for (int kb = 0; kb < nblk; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
                     unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
-                    const int row = (int)(r0 + (int64_t)kb * KR);
+                    const int row = (int)(r0 + (int64_t)(kb % nkb) * KR);
                     mbar_arrive_expect_tx(&bars.raw_full[s], tx);
+                    if (ga.anchors > 0) {
+                        // gathered P: column (kk, c) of anchor `an` lives at X[point, table[an, kk], c]
+                        const int an = a0 + kb / nkb;
+#pragma unroll
+                        for (int a = 0; a < TC_BM / 32; ++a) {
+                            const int cc = p0 + a * 32;
+                            if (cc < Pw) {
+                                const int kk = cc / ga.c;
+                                tma_load_3d(st + a * BOX_BYTES, &map_p, cc - kk * ga.c, __ldg(ga.table + an * ga.kk_n + kk), row, &bars.raw_full[s]);
+                            } else {
+                                tma_load_3d(st + a * BOX_BYTES, &map_p, ga.c, 0, row, &bars.raw_full[s]);   // out of bounds: zeros
+                            }
+                        }
+                        if (BF) {
+#pragma unroll
+                            for (int a = 0; a < BN / 64; ++a) {
+                                tma_load_3d(st + 2 * Cfg::A_BYTES + a * 8192, &map_q, q0 + a * 64, an, row, &bars.raw_full[s]);
+                                tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + a * 8192, &map_q2, q0 + a * 64, an, row, &bars.raw_full[s]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < BN / 32; ++a)
+                                tma_load_3d(st + 2 * Cfg::A_BYTES + a * BOX_BYTES, &map_q, q0 + a * 32, an, row, &bars.raw_full[s]);
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int a = 0; a < TC_BM / 32; ++a)
                         tma_load_2d(st + a * BOX_BYTES, &map_p, p0 + a * 32, row, &bars.raw_full[s]);
@@ -679,6 +741,29 @@ static int make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t
     return VGTKB_OK;
 }
 
+// X [points, anchors, c] fp32 (or bf16) as a 3-D tensor; box = [box_rows points, 1 anchor, 128 bytes of channels]
+static int make_map_3d(CUtensorMap* map, const void* base, int64_t points, int anchors, int c, int box_rows,
+                       CUtensorMapSwizzle swz, bool bf16 = false) {
+    EncodeTiledFn enc = get_encoder();
+    if (enc == nullptr) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return VGTKB_EUNSUP;
+    }
+    const int esz = bf16 ? 2 : 4;
+    const cuuint64_t gdim[3] = {(cuuint64_t)c, (cuuint64_t)anchors, (cuuint64_t)points};
+    const cuuint64_t gstr[2] = {(cuuint64_t)c * esz, (cuuint64_t)c * esz * anchors};
+    const cuuint32_t box[3] = {(cuuint32_t)(128 / esz), 1u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                           const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
+        return VGTKB_ECUDA;
+    }
+    return VGTKB_OK;
+}
+
 static int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -698,10 +783,11 @@ static int default_chunk(int passes) {
 
 template <int BN, bool BF>
 static int launch_nt(int64_t M, int N, int K, const float* A, const void* Bhi, const void* Blo, const float* bias,
-                     float* C, int passes, cudaStream_t st) {
+                     float* C, int passes, cudaStream_t st, TcGather ga = TcGather{0, 0, 0, nullptr}) {
     using Cfg = TcCfg<BN>;
     CUtensorMap ma, mhi, mlo;
-    int rc = make_map_2d(&ma, A, M, K, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = ga.anchors > 0 ? make_map_3d(&ma, A, M, ga.anchors, ga.c, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B)
+                            : make_map_2d(&ma, A, M, K, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = make_map_2d(&mhi, Bhi, N, K, BN, CU_TENSOR_MAP_SWIZZLE_128B, BF);
     if (rc) return rc;
@@ -710,14 +796,29 @@ static int launch_nt(int64_t M, int N, int K, const float* A, const void* Bhi, c
     const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024 + TC_EPI_WARPS * 4096;   // + epilogue staging
     auto kern = tc_gemm_nt_kernel<BN, BF>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t tiles = ceil_div64(M, TC_BM) * ceil_div(N, BN);
+    const int64_t tiles = ceil_div64(M, TC_BM) * ceil_div(N, BN) * (ga.anchors > 0 ? ga.anchors : 1);
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    kern<<<grid, TC_THREADS, smem, st>>>(ma, mhi, mlo, bias, C, M, N, K, passes, BF ? 1 : default_chunk(passes));
+    kern<<<grid, TC_THREADS, smem, st>>>(ma, mhi, mlo, bias, C, M, N, K, passes, BF ? 1 : default_chunk(passes), ga);
     return check_launch("gemm_nt(tcgen05)");
 }
 
+static int tc_gemm_nt_impl(int64_t M, int N, int K, const float* A, const float* B, const float* bias, float* C, int passes,
+                           float* workspace, cudaStream_t st, TcGather ga);
+
 int tc_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const float* bias, float* C, int passes,
                float* workspace, cudaStream_t st) {
+    return tc_gemm_nt_impl(M, N, K, A, B, bias, C, passes, workspace, st, TcGather{0, 0, 0, nullptr});
+}
+
+// C[(pt, an), n] = sum_{kk, c} X[pt, table[an, kk], c] * B[n, kk*c_n + c]   (X: [points, anchors, c_n])
+int tc_gemm_nt_gather(int64_t points, int anchors, int kk_n, int c_n, int N, const int32_t* table, const float* X,
+                      const float* B, const float* bias, float* C, int passes, float* workspace, cudaStream_t st) {
+    if (c_n % 64 != 0 || anchors < 1 || kk_n < 1) return VGTKB_EUNSUP;   // a k-block must not straddle two neighbours
+    return tc_gemm_nt_impl(points, N, kk_n * c_n, X, B, bias, C, passes, workspace, st, TcGather{anchors, kk_n, c_n, table});
+}
+
+static int tc_gemm_nt_impl(int64_t M, int N, int K, const float* A, const float* B, const float* bias, float* C, int passes,
+                           float* workspace, cudaStream_t st, TcGather ga) {
     // shapes the tensor-core path takes; everything else falls back to the FFMA kernel
     if (K % 4 != 0 || K < 8 || M < 1 || ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) != 0)
         return VGTKB_EUNSUP;
@@ -744,42 +845,60 @@ int tc_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const fl
     }
     int rc;
     if (bf) {
-        if (N <= 64) rc = launch_nt<64, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
-        else if (N <= 128) rc = launch_nt<128, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
-        else rc = launch_nt<256, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
-    } else if (N <= 64) rc = launch_nt<64, false>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
-    else if (N <= 128) rc = launch_nt<128, false>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
-    else rc = launch_nt<256, false>(M, N, K, A, Bhi, Blo, bias, C, passes, st);
+        if (N <= 64) rc = launch_nt<64, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st, ga);
+        else if (N <= 128) rc = launch_nt<128, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st, ga);
+        else rc = launch_nt<256, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st, ga);
+    } else if (N <= 64) rc = launch_nt<64, false>(M, N, K, A, Bhi, Blo, bias, C, passes, st, ga);
+    else if (N <= 128) rc = launch_nt<128, false>(M, N, K, A, Bhi, Blo, bias, C, passes, st, ga);
+    else rc = launch_nt<256, false>(M, N, K, A, Bhi, Blo, bias, C, passes, st, ga);
     if (owned != nullptr) cudaFreeAsync(owned, st);
     return rc;
 }
 
 template <int BN, bool BF>
 static int launch_tn(const float* P, int Pw, const void* Q, const void* Q2, int Qw, float* C, int ldc, int64_t R, int passes,
-                     cudaStream_t st) {
+                     cudaStream_t st, TcGather ga = TcGather{0, 0, 0, nullptr}) {
     using Cfg = TcCfg<BN>;
     constexpr int KR = BF ? 64 : TC_BK;
     CUtensorMap mp, mq, mq2;
     const CUtensorMapSwizzle swz = BF ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    int rc = make_map_2d(&mp, P, R, Pw, KR, swz);
-    if (rc) return rc;
-    rc = make_map_2d(&mq, Q, R, Qw, KR, swz, BF);      // BF: bf16 hi, box = 64 columns x 64 rows
-    if (rc) return rc;
-    rc = make_map_2d(&mq2, Q2, R, Qw, KR, swz, BF);    // BF: bf16 lo (tf32 path: unused duplicate)
-    if (rc) return rc;
+    int rc;
+    if (ga.anchors > 0) {   // R = points; P = X [points, anchors, c]; Q = Y [points, anchors, Qw]
+        rc = make_map_3d(&mp, P, R, ga.anchors, ga.c, KR, swz);
+        if (rc) return rc;
+        rc = make_map_3d(&mq, Q, R, ga.anchors, Qw, KR, swz, BF);
+        if (rc) return rc;
+        rc = make_map_3d(&mq2, Q2, R, ga.anchors, Qw, KR, swz, BF);
+        if (rc) return rc;
+    } else {
+        rc = make_map_2d(&mp, P, R, Pw, KR, swz);
+        if (rc) return rc;
+        rc = make_map_2d(&mq, Q, R, Qw, KR, swz, BF);      // BF: bf16 hi, box = 64 columns x 64 rows
+        if (rc) return rc;
+        rc = make_map_2d(&mq2, Q2, R, Qw, KR, swz, BF);    // BF: bf16 lo (tf32 path: unused duplicate)
+        if (rc) return rc;
+    }
     const int tiles = ceil_div(Pw, TC_BM) * ceil_div(Qw, BN);
-    int64_t splits = ceil_div64((int64_t)2 * num_sms(), tiles);
+    int n_groups = 1, ag = 1;
+    if (ga.anchors > 0) {   // parallelism first from anchor groups, then from point splits
+        n_groups = (int)ceil_div64((int64_t)2 * num_sms(), tiles);
+        if (n_groups > ga.anchors) n_groups = ga.anchors;
+        ag = ceil_div(ga.anchors, n_groups);
+        n_groups = ceil_div(ga.anchors, ag);
+    }
+    int64_t splits = ceil_div64((int64_t)2 * num_sms(), (int64_t)tiles * n_groups);
     const int64_t max_splits = ceil_div64(R, 512);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     int64_t rps = ceil_div64(ceil_div64(R, splits), KR) * KR;
     splits = ceil_div64(R, rps);
-    const int64_t items = splits * tiles;
+    const int64_t items = splits * tiles * n_groups;
     const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024;
     auto kern = tc_gemm_tn_kernel<BN, BF>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)(items < num_sms() ? items : num_sms());
-    kern<<<grid, TC_THREADS, smem, st>>>(mp, mq, mq2, Pw, Qw, C, ldc, R, rps, (int)splits, passes, BF ? 1 : default_chunk(passes));
+    kern<<<grid, TC_THREADS, smem, st>>>(mp, mq, mq2, Pw, Qw, C, ldc, R, rps, (int)splits, passes, BF ? 1 : default_chunk(passes),
+                                         ga, ag);
     return check_launch("gemm_tn(tcgen05)");
 }
 
@@ -807,6 +926,32 @@ int tc_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C
     if (M <= 64) return launch_tn<64, false>(B, N, A, A, M, C, N, R, passes, st);
     if (M <= 128) return launch_tn<128, false>(B, N, A, A, M, C, N, R, passes, st);
     return launch_tn<256, false>(B, N, A, A, M, C, N, R, passes, st);
+}
+
+// Weight gradient of the gather-GEMM:  C[m, kk*c_n + c] (+)= sum_{pt, an} Y[(pt, an), m] * X[pt, table[an, kk], c]
+// X: [points, anchors, c_n], Y: [points, anchors, M].  `workspace` (bf16x3): points*anchors*M floats.
+int tc_gemm_tn_gather(int64_t points, int anchors, int kk_n, int c_n, int M, const int32_t* table, const float* X,
+                      const float* Y, float* C, int accumulate, int passes, float* workspace, cudaStream_t st) {
+    const int N = kk_n * c_n;
+    if (c_n % 32 != 0 || M % 4 != 0 || points < 64 || points >= ((int64_t)1 << 31) ||
+        ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) != 0)
+        return VGTKB_EUNSUP;
+    if (passes == 6 && (M % 8 != 0 || workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0)) passes = 3;
+    if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+    const TcGather ga{anchors, kk_n, c_n, table};
+    if (passes == 6) {
+        const int64_t na = points * anchors * (int64_t)M;
+        uint16_t* hi = reinterpret_cast<uint16_t*>(workspace);
+        uint16_t* lo = hi + na;
+        const int blocks = (int)(ceil_div64(na, 256) < 2368 ? ceil_div64(na, 256) : 2368);
+        split_bf16_kernel<<<blocks, 256, 0, st>>>(na, Y, hi, lo);
+        if (M <= 64) return launch_tn<64, true>(X, N, hi, lo, M, C, N, points, 3, st, ga);
+        if (M <= 128) return launch_tn<128, true>(X, N, hi, lo, M, C, N, points, 3, st, ga);
+        return launch_tn<256, true>(X, N, hi, lo, M, C, N, points, 3, st, ga);
+    }
+    if (M <= 64) return launch_tn<64, false>(X, N, Y, Y, M, C, N, points, passes, st, ga);
+    if (M <= 128) return launch_tn<128, false>(X, N, Y, Y, M, C, N, points, passes, st, ga);
+    return launch_tn<256, false>(X, N, Y, Y, M, C, N, points, passes, st, ga);
 }
 
 }  // namespace vgtkb

@@ -108,6 +108,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
         "l"(tmap), "r"(smem_u32(bar)), "r"(crd_inner), "r"(crd_outer)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int crd0, int crd1, int crd2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(crd0), "r"(crd1), "r"(crd2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

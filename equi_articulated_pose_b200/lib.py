@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgtkb200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lib = None
 _device_ok = set()
@@ -34,6 +34,8 @@ SIGNATURES = {
     "vgtkb_row_gather_backward": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_gemm_nt": [c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp],
     "vgtkb_gemm_tn": [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
+    "vgtkb_gather_gemm_nt": [c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp],
+    "vgtkb_gather_gemm_tn": [c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
     "vgtkb_norm_stats": [c_int, c_i64, c_int, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp],
     "vgtkb_norm_act_forward": [c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
     "vgtkb_norm_act_backward": [c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],

@@ -203,6 +203,64 @@ class IntraGroupFn(torch.autograd.Function):
         return gy, None
 
 
+def gather_gemm_nt(x, table, w, bias=None, mode=None):
+    """out[(pt,a), o] = sum_{kk,c} x[pt, table[a,kk], c] * w[o, kk*C + c];  x [points, A, C] -> [points*A, n]."""
+    x, w = _f32(x), _f32(w)
+    pts, a, c = x.shape
+    kk, n = table.shape[1], w.shape[0]
+    assert w.shape[1] == kk * c and table.shape[0] == a and table.dtype == torch.int32
+    mode = _GEMM_MODE if mode is None else mode
+    out = torch.empty((pts * a, n), dtype=torch.float32, device=x.device)
+    ws = torch.empty(2 * n * kk * c, dtype=torch.float32, device=x.device)
+    call("vgtkb_gather_gemm_nt", x.device, pts, a, kk, c, n, ptr(table), ptr(x), ptr(w),
+         ptr(bias.contiguous()) if bias is not None else None, ptr(out), mode, ptr(ws))
+    return out
+
+
+def gather_gemm_tn(x, table, y, mode=None):
+    """out[o, kk*C + c] = sum_{pt,a} y[(pt,a), o] * x[pt, table[a,kk], c];  -> [m, kk*C]."""
+    x, y = _f32(x), _f32(y)
+    pts, a, c = x.shape
+    kk, m = table.shape[1], y.shape[1]
+    assert y.shape[0] == pts * a
+    mode = _GEMM_MODE if mode is None else mode
+    out = torch.empty((m, kk * c), dtype=torch.float32, device=x.device)
+    ws = torch.empty(pts * a * m, dtype=torch.float32, device=x.device) if mode == 3 else None
+    call("vgtkb_gather_gemm_tn", x.device, pts, a, kk, c, m, ptr(table), ptr(x), ptr(y), ptr(out), 0, mode, ptr(ws))
+    return out
+
+
+def gather_gemm_supported(c_in, c_out, points):
+    """Shapes the fused intra-conv path takes (else: materialised gather + GEMM)."""
+    return _GEMM_MODE != 0 and c_in % 64 == 0 and c_out % 64 == 0 and points >= 64
+
+
+class IntraConvFn(torch.autograd.Function):
+    """Intra-anchor group convolution as gather-GEMMs (forward, data gradient with the inverse table, weight
+    gradient); x [points, A, C] channels-last, w_kc [Co, KK*C] -> [points*A, Co].  No gathered tensor exists."""
+
+    @staticmethod
+    def forward(ctx, x, w_kc, table, table_inv):
+        x, w_kc = _f32(x), _f32(w_kc)
+        ctx.save_for_backward(x, w_kc, table, table_inv)
+        return gather_gemm_nt(x, table, w_kc)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w_kc, table, table_inv = ctx.saved_tensors
+        pts, a, c = x.shape
+        kk, co = table.shape[1], w_kc.shape[0]
+        gy = _f32(gy)
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            # gx[(pt,a'), c] = sum_{kk,o} gy[pt, inv[a',kk], o] * w_kc[o, kk*C + c]
+            wt = w_kc.view(co, kk, c).permute(2, 1, 0).reshape(c, kk * co).contiguous()
+            gx = gather_gemm_nt(gy.view(pts, a, co), table_inv, wt).view(pts, a, c)
+        if ctx.needs_input_grad[1]:
+            gw = gather_gemm_tn(x, table, gy)
+        return gx, gw, None, None
+
+
 class LinearFn(torch.autograd.Function):
     """y[M,N] = x[M,K] @ w[N,K]^T + bias  (the BasicSO3Conv contraction / 1x1 skip conv)."""
 

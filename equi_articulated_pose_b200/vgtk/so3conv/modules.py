@@ -118,10 +118,32 @@ class IntraSO3Conv(nn.Module):
         self.basic_conv = BasicSO3Conv(dim_in, dim_out, self.kernel_size)
         self.register_buffer('anchors', torch.from_numpy(np.ascontiguousarray(anchors)))
         self.register_buffer('intra_idx', torch.from_numpy(np.ascontiguousarray(intra_idx)).long())
+        self._tables = None
+
+    def tables(self):
+        """int32 neighbour table [A,12] and its per-column inverse (every column of the icosahedral table is a
+        permutation of the anchors) for the gather-GEMM path."""
+        if self._tables is None or self._tables[0].device != self.intra_idx.device:
+            t = self.intra_idx.to(torch.int32).contiguous()
+            inv = torch.empty_like(t)
+            na, kk = t.shape
+            cols = torch.arange(kk, device=t.device).view(1, kk).expand(na, kk)
+            inv[t.long(), cols] = torch.arange(na, device=t.device, dtype=torch.int32).view(na, 1).expand(na, kk)
+            is_perm = bool((torch.sort(t, dim=0)[0] == torch.arange(na, device=t.device, dtype=torch.int32).view(na, 1)).all())
+            self._tables = (t, inv.contiguous(), is_perm)
+        return self._tables
 
     def forward(self, x):
-        feats = L.intra_so3conv_grouping(self.intra_idx, x.feats)
-        feats = self.basic_conv(feats)
+        nb, c, npt, na = x.feats.shape
+        t, inv, is_perm = self.tables()
+        if x.feats.is_cuda and is_perm and _ops.gather_gemm_supported(c, self.dim_out, nb * npt):
+            # fused: the [b,c,12,p,a] gather of the reference (functional.py:2565-2567) is never materialised
+            rows = _ops.IntraConvFn.apply(x.feats.permute(0, 2, 3, 1).contiguous().view(nb * npt, na, c),
+                                          self.basic_conv.weight_kc(), t, inv)
+            feats = rows.view(nb, npt, na, self.dim_out).permute(0, 3, 1, 2)
+        else:
+            feats = L.intra_so3conv_grouping(self.intra_idx, x.feats)
+            feats = self.basic_conv(feats)
         return SphericalPointCloud(x.xyz, feats, self.anchors)
 
 

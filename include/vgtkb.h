@@ -132,6 +132,19 @@ int vgtkb_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const
 int vgtkb_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C,
                   int accumulate, int mode, float* workspace, void* stream);
 
+/* Intra-anchor convolution as ONE gather-GEMM: intra_so3conv_grouping (so3conv/functional.py:2553-2567) fused
+ * into BasicSO3Conv.forward (so3conv/modules.py:48-55); the 12x gathered tensor [b,c,12,p,a] is never built.
+ * x [points, anchors, c] channels-last, table [anchors, kk] int32 (the 60x12 neighbour table, or its per-column
+ * inverse for the data gradient), w [n, kk*c] (column = kk*c + channel):
+ *   gather_gemm_nt: out[(pt,a), o]   = sum_{kk,ch} x[pt, table[a,kk], ch] * w[o, kk*c + ch] (+ bias[o])
+ *   gather_gemm_tn: out[o, kk*c + ch] (+)= sum_{pt,a} y[(pt,a), o] * x[pt, table[a,kk], ch]      (y [points*anchors, m])
+ * The operand tiles are regular boxes of x (3-D TMA loads with the anchor coordinate looked up in `table`).
+ * Tensor-core modes only (1, 2, 3); c % 64 == 0.  workspace: nt 2*n*kk*c floats, tn (mode 3) points*anchors*m floats. */
+int vgtkb_gather_gemm_nt(int64_t points, int anchors, int kk, int c, int n, const int32_t* table, const float* x,
+                         const float* w, const float* bias, float* out, int mode, float* workspace, void* stream);
+int vgtkb_gather_gemm_tn(int64_t points, int anchors, int kk, int c, int m, const int32_t* table, const float* x,
+                         const float* y, float* out, int accumulate, int mode, float* workspace, void* stream);
+
 /* Normalisation + leaky_relu on channels-last rows X[groups][rows_per_group][c].
  * groups == 1 : BatchNorm2d training statistics (base_so3conv.py:113,125-131)
  * groups == b : InstanceNorm2d(affine=False)            (base_so3conv.py:47-64)

@@ -248,6 +248,41 @@ def test_config1_intra_so3conv_forward(dev, ops):
     assert rel_err(out.feats, want) < FP32_TOL
 
 
+@pytest.mark.parametrize("mode", [1, 3])
+@pytest.mark.parametrize("pts,c,co", [(200, 64, 64), (129, 128, 64), (64, 64, 256), (300, 256, 128)])
+def test_intra_conv_gather_gemm_fwd_bwd(dev, ops, mode, pts, c, co):
+    """The fused intra conv (3-D TMA gather-GEMMs: forward, data gradient through the inverse table, weight
+    gradient) against the oracle's materialised gather + matmul in fp64."""
+    from oracle import so3 as O
+    from equi_articulated_pose_b200 import so3_constants as C
+    g = torch.Generator().manual_seed(pts + c)
+    ii = torch.from_numpy(C.intra_idx())
+    f = torch.randn(1, c, pts, 60, generator=g, dtype=torch.float64, requires_grad=True)
+    W = (torch.randn(co, c * 12, generator=g, dtype=torch.float64) / (c * 12) ** 0.5).requires_grad_(True)
+    out_ref = O.basic_conv(W, O.intra_group_feats(ii, f))                     # [1,co,pts,60]
+    go = torch.randn(out_ref.shape, generator=g, dtype=torch.float64)
+    (out_ref * go).sum().backward()
+
+    t = ii.to(torch.int32).to(dev).contiguous()
+    inv = torch.empty_like(t)
+    cols = torch.arange(12, device=dev).view(1, 12).expand(60, 12)
+    inv[t.long(), cols] = torch.arange(60, device=dev, dtype=torch.int32).view(60, 1).expand(60, 12)
+    x = f.detach().float().permute(0, 2, 3, 1).reshape(pts, 60, c).contiguous().to(dev).requires_grad_(True)
+    w_kc = W.detach().float().view(co, c, 12).transpose(1, 2).reshape(co, 12 * c).contiguous().to(dev).requires_grad_(True)
+    prev = ops.get_gemm_mode()
+    ops.set_gemm_mode(mode)
+    try:
+        rows = ops.IntraConvFn.apply(x, w_kc, t, inv)                          # [pts*60, co]
+        (rows * go.float().permute(0, 2, 3, 1).reshape(pts * 60, co).to(dev)).sum().backward()
+    finally:
+        ops.set_gemm_mode(prev)
+    tol = 5e-6 if mode == 1 else 3e-5
+    assert rel_err(rows.view(pts, 60, co), out_ref[0].permute(1, 2, 0)) < tol
+    assert rel_err(x.grad, f.grad[0].permute(1, 2, 0)) < tol
+    gw_ref = W.grad.view(co, c, 12).transpose(1, 2).reshape(co, 12 * c)
+    assert rel_err(w_kc.grad, gw_ref) < tol
+
+
 def test_intra_group_backward(dev, ops):
     from oracle import so3 as O
     from equi_articulated_pose_b200 import so3_constants as C
