@@ -115,5 +115,6 @@ def call(name, device, *args):
 COUNTERS = {"launch_calls": 0, "kernels": 0}
 PROFILE = None  # set to a list to record (entry point, args, start event, end event) per call
 # device kernels launched per entry point (memsets not counted); used for bench.py's gpu_launches
-KERNELS_PER_CALL = {"vgtkb_chamfer_forward": 2, "vgtkb_chamfer_backward": 4, "vgtkb_norm_stats": 2,
+KERNELS_PER_CALL = {"vgtkb_gemm_nt": 2, "vgtkb_gemm_tn": 2, "vgtkb_gather_gemm_nt": 2, "vgtkb_gather_gemm_tn": 2,
+                    "vgtkb_chamfer_forward": 2, "vgtkb_chamfer_backward": 4, "vgtkb_norm_stats": 2,
                     "vgtkb_norm_act_backward": 3, "vgtkb_col_sum": 2}

@@ -480,3 +480,49 @@ def test_config2_full_size_equivariance(dev):
             err = rel_err(f1, f0[..., perm])
             # ball-query membership can flip for pairs exactly at the radius; allow a loose bound
             assert err < 5e-3, (gidx, err)
+
+
+def test_config4_dense_scan_with_chamfer(dev, ops):
+    """BASELINE config 4: classic backbone at N=4096 (first stride 8: 4096 -> 512), batch 32, loss
+    feats.square().mean() + ChamferDistance(Y, X) with Y = X[:, :1024] + noise (requires grad).  Full size,
+    so the checks are size-independent: the first-layer FPS / ball-query indices of two clouds are bit-exact
+    against the oracle, the output has the reference shape walk, everything is finite, the chamfer gradient
+    equals 2 (y - nn(y)) / (B n) + the reverse-direction term on a sampled row, and a second run is bit-identical
+    in the forward (no atomics on the forward path)."""
+    import equi_articulated_pose_b200 as eap
+    eap.install()
+    from extensions.chamfer_dist import ChamferDistance
+    from oracle import so3 as O, cops
+    B, N = 32, 4096
+    params = O.backbone_params(input_num=N)
+    assert params[0][0]['args']['stride'] == 8 and params[0][0]['args']['n_neighbor'] == 32
+    net = build_backbone(params, O.init_backbone_state(params, seed=4), dev).train()
+    pts = O.synthetic_cloud(B, N, 4000)
+    X = pts.to(dev)
+    g = torch.Generator().manual_seed(4)
+    Y = (pts[:, :1024] + 0.01 * torch.randn(B, 1024, 3, generator=g)).to(dev).requires_grad_(True)
+    out = net(X)
+    assert tuple(out.feats.shape) == (B, 256, 64, 60) and tuple(out.xyz.shape) == (B, 3, 64)
+    loss = out.feats.square().mean() + ChamferDistance()(Y, X)
+    loss.backward()
+    assert torch.isfinite(loss) and torch.isfinite(Y.grad).all()
+    assert all(torch.isfinite(p.grad).all() for p in net.parameters())
+    # index ops of the first layer, two clouds, against the oracle
+    xyz2 = pts[:2].permute(0, 2, 1).contiguous()
+    fps_ref = cops.furthest_point_sampling(xyz2.numpy(), 512)
+    fps = ops.furthest_point_sampling(xyz2.to(dev), 512)
+    assert np.array_equal(fps.cpu().numpy(), fps_ref)
+    q = cops.gather_points_forward(xyz2.numpy(), fps_ref)
+    a0 = params[0][0]['args']
+    assert np.array_equal(ops.ball_query(torch.from_numpy(q).to(dev), xyz2.to(dev), a0['radius'], 32).cpu().numpy(),
+                          cops.ball_query(q, xyz2.numpy(), a0['radius'], 32))
+    # chamfer gradient on one cloud against the closed form
+    with torch.no_grad():
+        d = ((Y[0, :, None] - X[0, None]) ** 2).sum(-1)
+        i1 = d.argmin(1)
+        i2 = d.argmin(0)
+        gref = 2 * (Y[0] - X[0][i1]) / (B * 1024)
+        gref.index_add_(0, i2, -2 * (X[0] - Y[0][i2]) / (B * N))
+    assert rel_err(Y.grad[0], gref) < 1e-4
+    with torch.no_grad():
+        assert torch.equal(net(X).feats, net(X).feats)
