@@ -94,6 +94,11 @@ inter_group_fwd_kernel(int n, int p, int nn, int a, int k, int ci, const float* 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     load_neighbourhood(b, pi, n, p, nn, xyz, sxyz, idx, s_j, s_g);
     __syncthreads();
+    // neighbour rows as 32-bit element offsets j * A * Ci (the 64-bit index arithmetic per neighbour was a
+    // quarter of the issued instructions); s_j is reused in place, every thread only rewrites its own entries
+    uint32_t* s_off = reinterpret_cast<uint32_t*>(s_j);
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) s_off[i] = (uint32_t)s_j[i] * (uint32_t)(a * ci);
+    __syncthreads();
     float* w_a = s_w + warp * nn * IG_KP;
     const int chunks = ci / (32 * CPL);
     const float* fb = feats + (size_t)b * n * a * ci;
@@ -114,7 +119,7 @@ inter_group_fwd_kernel(int n, int p, int nn, int a, int k, int ci, const float* 
                     for (int u = 0; u < CPL; ++u) acc[i][u] = 0.f;
 #pragma unroll 4
                 for (int ni = 0; ni < nn; ++ni) {
-                    const V xv = __ldg(reinterpret_cast<const V*>(fcol + (size_t)s_j[ni] * a * ci));
+                    const V xv = __ldg(reinterpret_cast<const V*>(fcol + s_off[ni]));
                     const float* xs = reinterpret_cast<const float*>(&xv);
                     const float4* wr = reinterpret_cast<const float4*>(w_a + ni * IG_KP + kg);
 #pragma unroll
@@ -159,6 +164,10 @@ inter_group_bwd_kernel(int n, int p, int nn, int a, int k, int ci, const float* 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     load_neighbourhood(b, pi, n, p, nn, xyz, sxyz, idx, s_j, s_g);
     __syncthreads();
+    uint32_t* s_off = reinterpret_cast<uint32_t*>(s_j);   // 32-bit element offsets j * A * Ci (see the forward kernel)
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) s_off[i] = (uint32_t)s_j[i] * (uint32_t)(a * ci);
+    __syncthreads();
+    float* gb = gfeats + (size_t)b * n * a * ci;
     float* w_a = s_w + warp * nn * IG_KP;
     const int chunks = ci / (32 * CPL);
     for (int ai = warp; ai < a; ai += IG_WARPS) {
@@ -195,7 +204,7 @@ inter_group_bwd_kernel(int n, int p, int nn, int a, int k, int ci, const float* 
 #pragma unroll
                         for (int u = 0; u < CPL; ++u) val[u] = fmaf(ws[i], dg[k4 * 4 + i][u], val[u]);
                 }
-                float* dst = gfeats + (((size_t)b * n + s_j[ni]) * a + ai) * ci + c0;
+                float* dst = gb + (size_t)ai * ci + c0 + s_off[ni];
                 V o;
                 float* os = reinterpret_cast<float*>(&o);
 #pragma unroll
