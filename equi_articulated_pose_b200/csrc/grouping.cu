@@ -50,14 +50,37 @@ __device__ __forceinline__ void load_neighbourhood(int b, int pi, int n, int p, 
     }
 }
 
-// w_a[nn][IG_KP] for anchor ai, computed by one warp
+// w_a[nn][IG_KP] for anchor ai, computed by one warp: lane <-> kernel point (its rotated position stays in
+// three registers), loop over the neighbours; lanes >= k write the zero padding
 __device__ __forceinline__ void warp_weights(int lane, int ai, int nn, int k, const float* rk, float inv_sigma,
                                              const float* s_g, float* w_a) {
+    if (lane < IG_KP) {
+        const bool live = lane < k;
+        float kx = 0.f, ky = 0.f, kz = 0.f;
+        if (live) {
+            const float* kp = rk + (ai * k + lane) * 3;
+            kx = __ldg(kp);
+            ky = __ldg(kp + 1);
+            kz = __ldg(kp + 2);
+        }
+#pragma unroll 4
+        for (int ni = 0; ni < nn; ++ni) {
+            const float dx = s_g[ni * 3] - kx, dy = s_g[ni * 3 + 1] - ky, dz = s_g[ni * 3 + 2] - kz;
+            const float w = fmaxf(0.f, 1.f - (dx * dx + dy * dy + dz * dz) * inv_sigma);
+            w_a[ni * IG_KP + lane] = live ? w : 0.f;
+        }
+    }
+}
+
+// element-parallel variant (lane <-> (neighbour, kernel point) pairs): faster inside the register-capped
+// forward kernel, slower in the backward one (measured both ways)
+__device__ __forceinline__ void warp_weights_flat(int lane, int ai, int nn, int k, const float* rk, float inv_sigma,
+                                                  const float* s_g, float* w_a) {
     for (int e = lane; e < nn * IG_KP; e += 32) {
         const int ni = e / IG_KP, ki = e % IG_KP;
         float w = 0.f;
         if (ki < k) {
-            const float* kp = rk + ((size_t)ai * k + ki) * 3;
+            const float* kp = rk + (ai * k + ki) * 3;
             const float dx = s_g[ni * 3] - __ldg(kp), dy = s_g[ni * 3 + 1] - __ldg(kp + 1),
                         dz = s_g[ni * 3 + 2] - __ldg(kp + 2);
             w = fmaxf(0.f, 1.f - (dx * dx + dy * dy + dz * dz) * inv_sigma);
@@ -104,7 +127,7 @@ inter_group_fwd_kernel(int n, int p, int nn, int a, int k, int ci, const float* 
     const float* fb = feats + (size_t)b * n * a * ci;
     for (int ai = warp; ai < a; ai += IG_WARPS) {
         __syncwarp();
-        warp_weights(lane, ai, nn, k, rk, inv_sigma, s_g, w_a);
+        warp_weights_flat(lane, ai, nn, k, rk, inv_sigma, s_g, w_a);
         __syncwarp();
         float* out = grouped + (((size_t)b * p + pi) * a + ai) * (size_t)k * ci;
         for (int ch = 0; ch < chunks; ++ch) {
