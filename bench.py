@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gemm-mode", type=int, default=None, help="0 fp32 FFMA, 1 tcgen05 3xTF32 (default), 2 1xTF32")
+    ap.add_argument("--gemm-mode", type=int, default=None, help="contraction arithmetic: 0 fp32 FFMA, 1 tcgen05 3xTF32, 2 tcgen05 1xTF32, 3 tcgen05 bf16x3 (default)")
     return ap.parse_args()
 
 
@@ -161,6 +161,10 @@ def algorithmic_work(name, a):
     if name == "vgtkb_gemm_tn":
         M, N, R = a[0], a[1], a[2]
         return "flop", 2.0 * M * N * R
+    if name == "vgtkb_gather_gemm_nt":      # points, anchors, kk, c, n
+        return "flop", 2.0 * a[0] * a[1] * a[2] * a[3] * a[4]
+    if name == "vgtkb_gather_gemm_tn":      # points, anchors, kk, c, m
+        return "flop", 2.0 * a[0] * a[1] * a[2] * a[3] * a[4]
     if name in ("vgtkb_inter_group_forward", "vgtkb_inter_group_backward"):
         b, n, p, nn, an, k, ci = a[:7]
         return "byte", 4.0 * b * an * ci * (n + p * k) + 12.0 * b * n + 4.0 * b * p * nn
@@ -193,8 +197,9 @@ def summarize_profile(records, steps, peaks):
         d[kind] += amt
     shapes = {}
     for name, a, e0, e1 in records:
-        if name in ("vgtkb_gemm_nt", "vgtkb_gemm_tn", "vgtkb_inter_group_forward", "vgtkb_inter_group_backward"):
-            key = name[6:] + str(tuple(int(v) for v in (a[:3] if "gemm" in name else a[:7])))
+        if name in ("vgtkb_gemm_nt", "vgtkb_gemm_tn", "vgtkb_gather_gemm_nt", "vgtkb_gather_gemm_tn",
+                    "vgtkb_inter_group_forward", "vgtkb_inter_group_backward"):
+            key = name[6:] + str(tuple(int(v) for v in (a[:5] if "gather" in name else (a[:3] if "gemm" in name else a[:7]))))
             d = shapes.setdefault(key, [0.0, 0])
             d[0] += e0.elapsed_time(e1)
             d[1] += 1
