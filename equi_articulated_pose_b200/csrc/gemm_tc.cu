@@ -162,6 +162,9 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     constexpr int KBE = BF ? 64 : TC_BK;     // K elements per k-block (one 128-byte operand row)
     constexpr int UK = BF ? 16 : 8;          // K elements per MMA
     const int nkb = (K + KBE - 1) / KBE;
+    // every CTA walks the reduction dimension from a different starting k-block: all SMs stream the SAME weight
+    // operand, and in lockstep they would hammer the same few L2 slices (the sum does not care about the order)
+    const int krot = (int)(((int64_t)blockIdx.x * nkb) / gridDim.x);
 
     if (threadIdx.x == 0) tc_init_barriers<STAGES>(bars);
     if (warp == TC_MMA_WARP) tmem_alloc(&bars.tmem_base, Cfg::TMEM_COLS);
@@ -281,7 +284,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         const uint32_t a_lo = a_hi + Cfg::A_BYTES;
                         const uint32_t b_hi = a_lo + Cfg::A_BYTES;
                         const uint32_t b_lo = b_hi + Cfg::B_BYTES;
-                        const int krem = K - kb * KBE;
+                        const int kba = (kb + krot) % nkb;
+                        const int krem = K - kba * KBE;
                         const int ksteps = krem >= KBE ? KBE / UK : (krem + UK - 1) / UK;
                         for (int ks = 0; ks < ksteps; ++ks) {
                             const uint32_t koff = ks * 32;  // 8 tf32 / 16 bf16 = 32 bytes inside the 128 B swizzle row
@@ -328,18 +332,19 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
                     unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&bars.raw_full[s], tx);
+                    const int kba = (kb + krot) % nkb;
                     if (ga.anchors > 0) {
-                        const int kcol = kb * KBE, kk = kcol / ga.c, c0 = kcol - kk * ga.c;
+                        const int kcol = kba * KBE, kk = kcol / ga.c, c0 = kcol - kk * ga.c;
                         const int mid = __ldg(ga.table + an * ga.kk_n + kk);
                         tma_load_3d(st, &map_a, c0, mid, mt * TC_BM, &bars.raw_full[s]);
                         if (BF) tma_load_3d(st + Cfg::A_BYTES, &map_a, c0 + 32, mid, mt * TC_BM, &bars.raw_full[s]);
                     } else {
-                        tma_load_2d(st, &map_a, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
-                        if (BF) tma_load_2d(st + Cfg::A_BYTES, &map_a, kb * KBE + 32, mt * TC_BM, &bars.raw_full[s]);
+                        tma_load_2d(st, &map_a, kba * KBE, mt * TC_BM, &bars.raw_full[s]);
+                        if (BF) tma_load_2d(st + Cfg::A_BYTES, &map_a, kba * KBE + 32, mt * TC_BM, &bars.raw_full[s]);
                     }
-                    tma_load_2d(st + 2 * Cfg::A_BYTES, &map_bhi, kb * KBE, nt * BN, &bars.raw_full[s]);
+                    tma_load_2d(st + 2 * Cfg::A_BYTES, &map_bhi, kba * KBE, nt * BN, &bars.raw_full[s]);
                     if (BF || passes == 3)
-                        tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &map_blo, kb * KBE, nt * BN, &bars.raw_full[s]);
+                        tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &map_blo, kba * KBE, nt * BN, &bars.raw_full[s]);
                 }
             }
         }
