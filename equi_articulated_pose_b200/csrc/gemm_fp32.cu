@@ -143,8 +143,48 @@ int sgemm_nt(int64_t M, int N, int K, const float* A, const float* B, const floa
     return check_launch("gemm_nt(fp32)");
 }
 
+// C[m, n] += sum_r A[r, m] B[r, n] for a very narrow B (N <= 4: the first layer's Ci = 1 skip conv):
+// thread <-> column m of A, a CTA owns a slice of rows, one atomic per (CTA, m, n)
+constexpr int NARROW_T = 256;
+__global__ void __launch_bounds__(NARROW_T)
+sgemm_tn_narrow_kernel(int M, int N, int64_t R, int64_t rows_per_cta, const float* __restrict__ A,
+                       const float* __restrict__ B, float* __restrict__ C) {
+    const int tx = min(M, NARROW_T), ty = NARROW_T / tx;
+    const int lx = threadIdx.x % tx, ly = threadIdx.x / tx;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = min(R, r0 + rows_per_cta);
+    __shared__ float red[NARROW_T][4];
+    for (int m = lx; m < M; m += tx) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ly < ty)
+            for (int64_t r = r0 + ly; r < r1; r += ty) {
+                const float av = A[r * M + m];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < N) acc[j] = fmaf(av, B[r * N + j], acc[j]);
+            }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[threadIdx.x][j] = acc[j];
+        __syncthreads();
+        if (ly == 0) {
+            for (int q = 1; q < ty; ++q)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] += red[q * tx + lx][j];
+            for (int j = 0; j < N; ++j) atomicAdd(C + (size_t)m * N + j, acc[j]);
+        }
+        __syncthreads();
+    }
+}
+
 int sgemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C, int accumulate, cudaStream_t st) {
     if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+    if (N <= 4 && M <= 4096) {
+        int64_t rpc = ceil_div64(R, (int64_t)kNumSMs * 4);
+        if (rpc < 64) rpc = 64;
+        const unsigned grid = (unsigned)ceil_div64(R, rpc);
+        sgemm_tn_narrow_kernel<<<grid, NARROW_T, 0, st>>>(M, N, R, rpc, A, B, C);
+        return check_launch("gemm_tn(fp32, narrow)");
+    }
     const int tiles = ceil_div(M, GB) * ceil_div(N, GB);
     int64_t splits = ceil_div64((int64_t)kNumSMs * 4, tiles);
     if (splits < 1) splits = 1;

@@ -264,6 +264,34 @@ __global__ void inter_group_fwd_generic_kernel(int n, int p, int nn, int a, int 
     }
 }
 
+// ci == 1 (first layer: occupancy features): warp <-> anchor, lane <-> kernel point, the rotated kernel point
+// stays in registers and the neighbours are a loop -- no per-item weight recomputation
+__global__ void __launch_bounds__(IG_WARPS * 32)
+inter_group_fwd_c1_kernel(int n, int p, int nn, int a, int k, const float* __restrict__ xyz,
+                          const float* __restrict__ sxyz, const int32_t* __restrict__ idx, const float* __restrict__ rk,
+                          float inv_sigma, const float* __restrict__ feats, float* __restrict__ grouped) {
+    __shared__ float s_g[IG_MAXNN * 3];
+    __shared__ int s_j[IG_MAXNN];
+    const int pi = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    load_neighbourhood(b, pi, n, p, nn, xyz, sxyz, idx, s_j, s_g);
+    __syncthreads();
+    const float* fb = feats + (size_t)b * n * a;
+    for (int ai = warp; ai < a; ai += IG_WARPS) {
+        if (lane < k) {
+            const float* kp = rk + (ai * k + lane) * 3;
+            const float kx = __ldg(kp), ky = __ldg(kp + 1), kz = __ldg(kp + 2);
+            float acc = 0.f;
+            for (int ni = 0; ni < nn; ++ni) {
+                const float dx = s_g[ni * 3] - kx, dy = s_g[ni * 3 + 1] - ky, dz = s_g[ni * 3 + 2] - kz;
+                const float w = fmaxf(0.f, 1.f - (dx * dx + dy * dy + dz * dz) * inv_sigma);
+                acc = fmaf(w, __ldg(fb + (size_t)s_j[ni] * a + ai), acc);
+            }
+            grouped[(((size_t)b * p + pi) * a + ai) * (size_t)k + lane] = acc;
+        }
+    }
+}
+
 __global__ void inter_group_bwd_generic_kernel(int n, int p, int nn, int a, int k, int ci,
                                                const float* __restrict__ xyz, const float* __restrict__ sxyz,
                                                const int32_t* __restrict__ idx, const float* __restrict__ rk,
@@ -416,6 +444,11 @@ extern "C" int vgtkb_inter_group_forward(int b, int n, int p, int nn, int a, int
         return launch_inter<4>(true, b, n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels, sigma, feats, grouped, st);
     if (k <= IG_KP && ci % 64 == 0 && al)
         return launch_inter<2>(true, b, n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels, sigma, feats, grouped, st);
+    if (ci == 1 && k <= 32) {
+        inter_group_fwd_c1_kernel<<<dim3(p, b), IG_WARPS * 32, 0, st>>>(n, p, nn, a, k, xyz, sample_xyz, idx, rot_kernels,
+                                                                         1.0f / sigma, feats, grouped);
+        return check_launch("inter_group_forward(ci=1)");
+    }
     inter_group_fwd_generic_kernel<<<dim3(p, b), 256, 0, st>>>(n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels,
                                                               1.0f / sigma, feats, grouped);
     return check_launch("inter_group_forward(generic)");

@@ -302,7 +302,8 @@ def test_intra_group_backward(dev, ops):
 
 # ------------------------------------------------------------------------------ GEMM / norm
 @pytest.mark.parametrize("mode", [0, 1, 3])
-@pytest.mark.parametrize("M,N,K", [(128 * 60, 64, 24), (3000, 64, 1536), (7680, 256, 3072), (999, 24, 192), (257, 130, 33)])
+@pytest.mark.parametrize("M,N,K", [(128 * 60, 64, 24), (3000, 64, 1536), (7680, 256, 3072), (999, 24, 192), (257, 130, 33),
+                                   (5000, 64, 1), (3000, 24, 3)])
 def test_gemm_nt_tn(dev, ops, mode, M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
     A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
