@@ -7,7 +7,7 @@
 
 #include "../../include/vgtkb.h"
 
-#define VGTKB_ABI_VERSION 4
+#define VGTKB_ABI_VERSION 5
 
 namespace vgtkb {
 

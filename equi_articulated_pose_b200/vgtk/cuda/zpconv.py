@@ -1,46 +1,55 @@
-"""vgtk.cuda.zpconv (reference: vgtk/vgtk/cuda/zpconv_cuda.cpp:113-118).
+"""vgtk.cuda.zpconv (reference: vgtk/vgtk/cuda/zpconv_cuda.cpp:113-118), served by libvgtkb200.so.
 
-In the reference these four entry points are dead code (the Python calls the `*_naive` torch
-versions).  Here the slot carries the fused grouping kernels with the reference's tensor layouts:
+Reference tensor layouts, explicit index / weight tensors:
     inter_zpconv_forward(idx[B,P,A,K,ann] int32, w[B,P,A,K,ann], feats[B,C,Nq,A]) -> [B,C,K,P,A]
     intra_zpconv_forward(idx[Aout,ann] int32, w[Aout,K,ann], feats[B,C,P,Ain])    -> [B,C,K,P,Aout]
-These literal (explicit idx/weight) forms are evaluated with index arithmetic in torch on the
-device; the SO(3) path does not go through them (see vgtk.so3conv.functional)."""
+In the reference these are dead code on the SO(3) path; they are the grouping of the legacy S^2 ZPConv modules."""
 import torch
+
+from equi_articulated_pose_b200 import lib as _lib
+
+call, ptr = _lib.call, _lib.ptr
+
+
+def _prep(idx, w, x):
+    for t, name in ((idx, "idx"), (w, "weights"), (x, "feats")):
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor")
+    return idx.to(torch.int32).contiguous(), w.float().contiguous(), x.float().contiguous()
 
 
 def inter_zpconv_forward(idx, w, feats):
+    idx, w, feats = _prep(idx, w, feats)
     b, p, a, k, ann = idx.shape
-    c = feats.shape[1]
-    f = feats.permute(0, 3, 2, 1)                                   # [B,A,Nq,C]
-    ar = torch.arange(a, device=feats.device).view(1, 1, a, 1, 1).expand(b, p, a, k, ann)
-    br = torch.arange(b, device=feats.device).view(b, 1, 1, 1, 1).expand(b, p, a, k, ann)
-    g = f[br, ar, idx.long()]                                       # [B,P,A,K,ann,C]
-    out = (g * w.unsqueeze(-1)).sum(4)                              # [B,P,A,K,C]
-    return out.permute(0, 4, 3, 1, 2).contiguous()
+    c, nq = feats.shape[1], feats.shape[2]
+    out = torch.empty((b, c, k, p, a), dtype=torch.float32, device=feats.device)
+    call("vgtkb_inter_zpconv_forward", feats.device, b, c, nq, p, a, k, ann, ptr(idx), ptr(w), ptr(feats), ptr(out))
+    return out
 
 
 def inter_zpconv_backward(idx, w, grad_out, nq):
+    idx, w, grad_out = _prep(idx, w, grad_out)
     b, p, a, k, ann = idx.shape
     c = grad_out.shape[1]
-    go = grad_out.permute(0, 3, 4, 2, 1)                            # [B,P,A,K,C]
-    contrib = go.unsqueeze(4) * w.unsqueeze(-1)                     # [B,P,A,K,ann,C]
-    gf = torch.zeros(b, a, nq, c, device=grad_out.device, dtype=grad_out.dtype)
-    ar = torch.arange(a, device=idx.device).view(1, 1, a, 1, 1).expand_as(idx)
-    br = torch.arange(b, device=idx.device).view(b, 1, 1, 1, 1).expand_as(idx)
-    gf.index_put_((br, ar, idx.long()), contrib, accumulate=True)
-    return gf.permute(0, 3, 2, 1).contiguous()
+    gf = torch.empty((b, c, int(nq), a), dtype=torch.float32, device=grad_out.device)
+    call("vgtkb_inter_zpconv_backward", grad_out.device, b, c, int(nq), p, a, k, ann, ptr(idx), ptr(w), ptr(grad_out), ptr(gf))
+    return gf
 
 
 def intra_zpconv_forward(idx, w, feats):
-    g = feats[..., idx.long()]                                      # [B,C,P,Aout,ann]
-    return torch.einsum('bcpan,akn->bckpa', g, w).contiguous()
+    idx, w, feats = _prep(idx, w, feats)
+    aout, ann = idx.shape
+    k = w.shape[1]
+    b, c, p, ain = feats.shape
+    out = torch.empty((b, c, k, p, aout), dtype=torch.float32, device=feats.device)
+    call("vgtkb_intra_zpconv_forward", feats.device, b, c, p, ain, aout, k, ann, ptr(idx), ptr(w), ptr(feats), ptr(out))
+    return out
 
 
-def intra_zpconv_backward(idx, w, grad_out, ain=None):
-    b, c, k, p, aout = grad_out.shape
-    ain = ain if ain is not None else int(idx.max().item()) + 1
-    contrib = torch.einsum('bckpa,akn->bcpan', grad_out, w)
-    gf = torch.zeros(b, c, p, ain, device=grad_out.device, dtype=grad_out.dtype)
-    gf.index_add_(3, idx.long().reshape(-1), contrib.reshape(b, c, p, -1))
+def intra_zpconv_backward(idx, w, grad_out, ain):
+    idx, w, grad_out = _prep(idx, w, grad_out)
+    aout, ann = idx.shape
+    b, c, k, p, _ = grad_out.shape
+    gf = torch.empty((b, c, p, int(ain)), dtype=torch.float32, device=grad_out.device)
+    call("vgtkb_intra_zpconv_backward", grad_out.device, b, c, p, int(ain), aout, k, ann, ptr(idx), ptr(w), ptr(grad_out), ptr(gf))
     return gf

@@ -11,6 +11,82 @@ import vgtk.pc as pctk
 from equi_articulated_pose_b200 import ops as _ops
 
 
+# ---- legacy S^2 anchors / intra kernel weights (reference :20-39, :142-207); constants of the legacy ZPConv modules
+def get_anchors(anchor):
+    """12 S^2 direction anchors = the unit icosahedron vertices of data/anchors/sphere12.ply (norm filter > 0.5)."""
+    if isinstance(anchor, torch.Tensor):
+        return anchor.detach().cpu()
+    if isinstance(anchor, int) and anchor == 12:
+        from equi_articulated_pose_b200 import so3_constants as _C
+        pts = _C._load()["ico_vertices"].astype("float32")
+    elif isinstance(anchor, str):
+        pts = pctk.load_ply(anchor).astype("float32")
+    else:
+        raise ValueError(f"Not recognized anchor type {type(anchor)} (only the 12-vertex sphere ships with this package)")
+    norms = np.sqrt(np.sum(pts ** 2, axis=1))
+    keep = norms > 0.5
+    return torch.from_numpy(pts[keep] / norms[keep, None])
+
+
+def get_intra_kernels(aperature, kernel_size):
+    return torch.from_numpy(np.linspace(0, 0.5 * aperature, kernel_size, dtype=np.float32))
+
+
+def acos_safe(x, eps=1e-4):
+    """acos continued linearly outside [-1+eps, 1-eps] (reference :148-154)."""
+    sign = torch.sign(x)
+    slope = np.arccos(1 - eps) / eps
+    return torch.where(abs(x) <= 1 - eps, torch.acos(x), torch.acos(sign * (1 - eps)) - slope * sign * (abs(x) - 1 + eps))
+
+
+def anchor_knn(a_src, a_tgt, k=3, metric="spherical"):
+    """for every anchor of a_tgt the k nearest anchors of a_src -> (values [a,k], indices [a,k]) (reference :156-175)."""
+    a_src, a_tgt = a_src.unsqueeze(0), a_tgt.unsqueeze(1)
+    if metric == "spherical":
+        return (torch.sum(a_src * a_tgt, dim=2) - 1.0).topk(k=k, dim=1, largest=True)
+    if metric == "angular":
+        return acos_safe(torch.sum(a_src * a_tgt, dim=2)).topk(k=k, dim=1, largest=False)
+    return torch.sum((a_src - a_tgt) ** 2, dim=2).topk(k=k, dim=1, largest=False)
+
+
+def get_intra_kernel_weights(anchor_in, anchor_out, kernels, ann, aperature, sigma=1e-1, use_suppression=False):
+    """idx [a_out, ann] int32 (nearest input anchors by angle) and the linear angular kernel weights
+    influence [a_out, ks, ann] = relu(1 - |angle - kernel| / pi / (3 sqrt(sigma/2)))  (reference :179-218)."""
+    anchor_out = anchor_in if anchor_out is None else anchor_out
+    angles, idx = anchor_knn(anchor_in, anchor_out, k=ann, metric="angular")
+    influence = (angles.unsqueeze(1) - kernels.unsqueeze(0).unsqueeze(-1)).abs() / np.pi
+    influence = F.relu(1.0 - influence / (3 * (sigma / 2.0) ** 0.5))
+    if use_suppression:
+        influence = influence * angles.le(0.5 * aperature).unsqueeze(1).expand(-1, kernels.size(0), -1).float()
+    return idx.int().contiguous(), influence.contiguous()
+
+
+class IntraZPConvGrouping(torch.autograd.Function):
+    """[nb,c,np,na_in] -> [nb,c,ks,np,na_out] with explicit (idx, w) (reference :222-248), on the CUDA slot kernels."""
+
+    @staticmethod
+    def forward(ctx, intra_idx, intra_w, feats):
+        import vgtk.cuda.zpconv as cuda_zpconv
+        ctx.save_for_backward(intra_idx, intra_w)
+        ctx.ain = feats.shape[3]
+        return cuda_zpconv.intra_zpconv_forward(intra_idx, intra_w, feats)
+
+    @staticmethod
+    def backward(ctx, grad):
+        import vgtk.cuda.zpconv as cuda_zpconv
+        intra_idx, intra_w = ctx.saved_tensors
+        return None, None, cuda_zpconv.intra_zpconv_backward(intra_idx, intra_w, grad.contiguous(), ctx.ain)
+
+
+def intra_zpconv_grouping(intra_idx, intra_w, feats):
+    return IntraZPConvGrouping.apply(intra_idx, intra_w, feats)
+
+
+def intra_zpconv_grouping_naive(intra_idx, intra_w, feats):
+    """G[b,c,k,p,a] = sum_n feats[b,c,p,idx[a,n]] w[a,k,n] (reference :252-272 evaluates index_select + einsum)."""
+    return IntraZPConvGrouping.apply(intra_idx, intra_w, feats)
+
+
 # ---- shadow point / feature (reference :83-96).  Index N is never produced by ball_query, so the
 # fused path does not need them; they are kept for callers of the literal API.
 def add_shadow_point(x):

@@ -107,6 +107,20 @@ int vgtkb_intra_group_forward(int64_t rows, int a, int kk, int c, const int32_t*
 int vgtkb_intra_group_backward(int64_t rows, int a, int kk, int c, const int32_t* intra_idx,
                                const float* grad_grouped, float* grad_y, void* stream);
 
+/* vgtk.cuda.zpconv.{inter,intra}_zpconv_{forward,backward} (zpconv_cuda.cpp:113-118, kernels
+ * zpconv_cuda_kernel.cu:33-195), reference layouts, explicit index/weight tensors:
+ *   inter: idx, w [b,p,a,k,ann]; feats [b,c,nq,a]  -> out [b,c,k,p,a];  backward -> grad_feats [b,c,nq,a] (zeroed here)
+ *   intra: idx [aout,ann], w [aout,k,ann]; feats [b,c,p,ain] -> out [b,c,k,p,aout]; backward -> grad_feats [b,c,p,ain]
+ * Live grouping of the legacy S^2 ZPConv modules (vgtk/vgtk/spconv/modules.py:61-98, config 1b). */
+int vgtkb_inter_zpconv_forward(int b, int c, int nq, int p, int a, int k, int ann, const int32_t* idx, const float* w,
+                               const float* feats, float* out, void* stream);
+int vgtkb_inter_zpconv_backward(int b, int c, int nq, int p, int a, int k, int ann, const int32_t* idx, const float* w,
+                                const float* grad_out, float* grad_feats, void* stream);
+int vgtkb_intra_zpconv_forward(int b, int c, int p, int ain, int aout, int k, int ann, const int32_t* idx, const float* w,
+                               const float* feats, float* out, void* stream);
+int vgtkb_intra_zpconv_backward(int b, int c, int p, int ain, int aout, int k, int ann, const int32_t* idx, const float* w,
+                                const float* grad_out, float* grad_feats, void* stream);
+
 /* Point-row gather used by the skip connection (zptk.functional.batched_index_select(feats, 2,
  * sample_idx), SPConvNets/utils/base_so3conv.py:212-213) on channels-last rows of `width`
  * floats: out[b,j,:] = x[b, idx[b,j], :]; backward accumulates (atomics) into grad_x. */

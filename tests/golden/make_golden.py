@@ -112,6 +112,21 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "ref_blocks_small.npz"), **out)
     print("blocks", x.feats.shape, float(loss))
 
+    # ---- legacy S^2 IntraZPConv (BASELINE config 1b: A = 12 direction anchors, N = 128, batch 1) ------
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(1002)       # own stream: the fixtures above stay bit-identical
+    zp = zptk.IntraZPConv(dim_in=32, dim_out=32, kernel_size=3, aperture=1.0, sigma=0.1, anchor_nn=6, anchor_in=12)
+    fz = torch.randn(1, 32, 128, 12, generator=g, requires_grad=True)
+    oz = zp(zptk.SphericalPointCloud(torch.rand(1, 3, 128, generator=g) - 0.5, fz, None)).feats
+    goz = torch.randn(oz.shape, generator=g)
+    (oz * goz).sum().backward()
+    np.savez_compressed(os.path.join(GOLD, "ref_intrazp_small.npz"), W=zp.basic_conv.W.detach().numpy(),
+                        bias=zp.basic_conv.bias.detach().numpy(), intra_idx=zp.intra_idx.numpy(), intra_w=zp.intra_w.numpy(),
+                        anchors=zp.anchor_out.numpy(), kernels=zp.kernels.numpy(), feats=fz.detach().numpy(),
+                        out=oz.detach().numpy(), grad_out=goz.numpy(), grad_feats=fz.grad.numpy(),
+                        grad_W=zp.basic_conv.W.grad.numpy(), grad_bias=zp.basic_conv.bias.grad.numpy())
+    print("intrazp", oz.shape)
+
 
 if __name__ == "__main__":
     main()
