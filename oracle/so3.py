@@ -56,7 +56,7 @@ def ball_grouping(xyz, stride, radius, n_neighbor, lazy_sample=True):
         sample_xyz = torch.gather(xyz, 2, sidx.long().unsqueeze(1).expand(-1, 3, -1))
     else:
         sample_xyz = xyz
-        sidx = torch.arange(xyz.shape[2], dtype=torch.long).unsqueeze(0).repeat(xyz.shape[0], 1)
+        sidx = torch.arange(xyz.shape[2], dtype=torch.long, device=xyz.device).unsqueeze(0).repeat(xyz.shape[0], 1)
     ball_idx, grouped = ball_query(sample_xyz, xyz, radius, n_neighbor)
     return grouped - sample_xyz.unsqueeze(3), ball_idx, sidx, sample_xyz
 

@@ -1,6 +1,6 @@
 """Developer check (GPU): per-parameter gradient / output error of the classic backbone vs the oracle, per GEMM mode."""
 import sys, os, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from tests.test_gpu_parity import _oracle_case, _oracle_run
 from tests.helpers import rel_err
 from equi_articulated_pose_b200 import ops

@@ -1,6 +1,6 @@
 """Developer check (GPU): tcgen05 GEMMs vs fp64, error + CUDA-event timing per shape."""
 import sys, os, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from equi_articulated_pose_b200 import ops
 
 def t(fn, n=5):

@@ -1,5 +1,5 @@
 import sys, os, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from equi_articulated_pose_b200 import ops
 dev = torch.device("cuda:0")
 torch.set_printoptions(linewidth=200, precision=1, sci_mode=False)
