@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgtkb200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _lib = None
 _device_ok = set()
@@ -30,6 +30,9 @@ SIGNATURES = {
     "vgtkb_inter_group_backward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
     "vgtkb_intra_group_forward": [c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_intra_group_backward": [c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_pose_neighbourhood": [c_int] * 4 + [c_vp] * 7,
+    "vgtkb_inter_pose_group_forward": [c_int] * 6 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
+    "vgtkb_inter_pose_group_backward": [c_int] * 6 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
     "vgtkb_inter_zpconv_forward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_inter_zpconv_backward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_intra_zpconv_forward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_vp],

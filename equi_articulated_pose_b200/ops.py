@@ -179,6 +179,47 @@ class InterGroupFn(torch.autograd.Function):
         return gx, None, None, None, None, None
 
 
+def pose_neighbourhood(xyz, pose, idx, anchors, with_perm=True):
+    """xyz [B,3,N], pose [B,N,4,4], idx [B,N,nn] int32, anchors [A,3,3] -> rotated neighbour offsets [B,N,nn,3] and the
+    anchor permutation table [B,N,nn,A] uint8 (None when with_perm is False)."""
+    xyz, pose, idx, anchors = _f32(xyz), _f32(pose), _i32(idx), _f32(anchors)
+    b, _, n = xyz.shape
+    nn, a = idx.shape[2], anchors.shape[0]
+    rel = torch.empty((b, n, nn, 3), dtype=torch.float32, device=xyz.device)
+    perm = torch.empty((b, n, nn, a), dtype=torch.uint8, device=xyz.device) if with_perm else None
+    call("vgtkb_pose_neighbourhood", xyz.device, b, n, nn, a, ptr(xyz), ptr(pose), ptr(idx), ptr(anchors), ptr(rel), ptr(perm))
+    return rel, perm
+
+
+class PoseGroupFn(torch.autograd.Function):
+    """Pose-aware inter grouping: feats X [B,N,A,Ci] -> G [B,N,A,K*Ci] with rotated offsets and anchor permutation."""
+
+    @staticmethod
+    def forward(ctx, feats, idx, rel_xyz, perm, rot_kernels, sigma):
+        feats = _f32(feats)
+        b, n, a, ci = feats.shape
+        nn, k = idx.shape[2], rot_kernels.shape[1]
+        g = torch.empty((b, n, a, k * ci), dtype=torch.float32, device=feats.device)
+        call("vgtkb_inter_pose_group_forward", feats.device, b, n, nn, a, k, ci, ptr(idx), ptr(rel_xyz), ptr(perm),
+             ptr(rot_kernels), float(sigma), ptr(feats), ptr(g))
+        ctx.save_for_backward(idx, rel_xyz, rot_kernels)
+        ctx.perm = perm
+        ctx.meta = (b, n, nn, a, k, ci, float(sigma))
+        return g
+
+    @staticmethod
+    def backward(ctx, grad_g):
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 6
+        idx, rel_xyz, rot_kernels = ctx.saved_tensors
+        b, n, nn, a, k, ci, sigma = ctx.meta
+        grad_g = _f32(grad_g)
+        gx = torch.zeros((b, n, a, ci), dtype=torch.float32, device=grad_g.device)
+        call("vgtkb_inter_pose_group_backward", grad_g.device, b, n, nn, a, k, ci, ptr(idx), ptr(rel_xyz), ptr(ctx.perm),
+             ptr(rot_kernels), sigma, ptr(grad_g), ptr(gx))
+        return gx, None, None, None, None, None
+
+
 class IntraGroupFn(torch.autograd.Function):
     """Y [R,A,C] -> G [R,A,KK*C] with G[r,a,k,:] = Y[r, intra_idx[a,k], :]."""
 

@@ -83,27 +83,43 @@ class InterSO3Conv(nn.Module):
 
 
 class InterSO3PoseConv(InterSO3Conv):
-    """Pose-aware variant (reference :177-322).  With an identity per-point pose -- the only case the
-    shipped configurations produce (SURVEY.md section 0) -- it is bit-identical to InterSO3Conv;
-    a non-identity pose needs the anchor-permuted gather, which is not built yet."""
+    """Pose-aware variant (reference :177-322).  With an identity per-point pose -- the only case the shipped
+    configurations produce -- it is bit-identical to InterSO3Conv and runs the same tuned
+    kernels.  With arbitrary per-point rotations (stride 1: the no-stride branch of
+    inter_so3poseconv_grouping_strided, functional.py:1061-1261) the neighbour offsets are rotated by R_p R_j^T
+    and, for permute_modes != 0, every neighbour's anchors are permuted by the nearest-anchor table; both are
+    produced by one kernel instead of the reference's [B,N,nn,A,A,3,3] temporary."""
 
     def __init__(self, dim_in, dim_out, kernel_size, stride, radius, sigma, n_neighbor, lazy_sample=True,
                  pooling=None, kanchor=60, permute_modes=0, use_2d=False, use_art_mode=False):
         super().__init__(dim_in, dim_out, kernel_size, stride, radius, sigma, n_neighbor, lazy_sample, pooling, kanchor)
         self.permute_modes, self.use_2d, self.use_art_mode = permute_modes, use_2d, use_art_mode
 
-    def forward(self, x, inter_idx=None, inter_w=None):
+    def forward(self, x, inter_idx=None, inter_w=None, seg=None):
         pose = x.pose
         eye = torch.eye(4, dtype=pose.dtype, device=pose.device)
-        if not torch.equal(pose, eye.expand_as(pose)):
-            raise NotImplementedError("InterSO3PoseConv: only the identity-pose case is implemented")
-        # the reference recomputes the ball query every call and ignores a cached inter_idx (:931,1025)
-        idx, w, sample_idx, out = super().forward(x, None, None)
-        if sample_idx is not None and self.stride > 1:
-            sampled_pose = torch.gather(pose, 1, sample_idx.long().view(*sample_idx.shape, 1, 1).expand(-1, -1, 4, 4))
-        else:
-            sampled_pose = pose
-        return idx, w, sample_idx, SphericalPointCloudPose(out.xyz, out.feats, self.anchors, sampled_pose)
+        if torch.equal(pose, eye.expand_as(pose)):
+            # the reference recomputes the ball query every call and ignores a cached inter_idx (:931,1025)
+            idx, w, sample_idx, out = super().forward(x, None, None)
+            if sample_idx is not None and self.stride > 1:
+                sampled_pose = torch.gather(pose, 1, sample_idx.long().view(*sample_idx.shape, 1, 1).expand(-1, -1, 4, 4))
+            else:
+                sampled_pose = pose
+            return idx, w, sample_idx, SphericalPointCloudPose(out.xyz, out.feats, self.anchors, sampled_pose)
+        if self.use_2d or self.use_art_mode:
+            raise NotImplementedError("InterSO3PoseConv: the 2D / articulation-mode groupings are not reached by the shipped flags")
+        if self.stride != 1:
+            raise NotImplementedError("InterSO3PoseConv with a non-identity pose: only stride 1 (what model 38 builds) is implemented")
+        xyz = x.xyz.contiguous()
+        idx = pctk.ball_query_index(xyz, xyz, self.radius, self.n_neighbor)
+        rel_xyz, perm = _ops.pose_neighbourhood(xyz, pose, idx, self.anchors, with_perm=self.permute_modes != 0)
+        feats_cl = x.feats.permute(0, 2, 3, 1).contiguous()
+        g = _ops.PoseGroupFn.apply(feats_cl, idx, rel_xyz, perm, self.rot_kernels(), self.sigma)
+        b, n, a, kc = g.shape
+        k = self.kernel_size
+        feats = self.basic_conv(g.view(b, n, a, k, kc // k).permute(0, 4, 3, 1, 2))
+        w = L.LazyInterWeights(xyz, xyz, idx, self.rot_kernels(), self.sigma)
+        return idx, w, None, SphericalPointCloudPose(xyz, feats, self.anchors, pose)
 
 
 class IntraSO3Conv(nn.Module):

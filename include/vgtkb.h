@@ -107,6 +107,22 @@ int vgtkb_intra_group_forward(int64_t rows, int a, int kk, int c, const int32_t*
 int vgtkb_intra_group_backward(int64_t rows, int a, int kk, int c, const int32_t* intra_idx,
                                const float* grad_grouped, float* grad_y, void* stream);
 
+/* Pose-aware inter grouping with arbitrary per-point rotations: the no-stride branch of
+ * inter_so3poseconv_grouping_strided (so3conv/functional.py:1061-1261) behind InterSO3PoseConv (so3conv/modules.py:222-322).
+ *   pose_neighbourhood: xyz [b,3,n], pose [b,n,4,4], idx [b,n,nn], anchors [a,3,3] ->
+ *       rel_xyz [b,n,nn,3] = R_p R_j^T (x_j - x_p);  perm [b,n,nn,a] (uint8, may be NULL) = argmax_a' tr((R_rel^T R_a) R_a'^T)
+ *   inter_pose_group_forward: G[b,p,a,k,c] = sum_n relu(1 - |rel_xyz[b,p,n] - R_a kappa_k|^2 / sigma) X[b, idx[b,p,n], perm[b,p,n,a], c]
+ *       (perm NULL = identity: permute_modes 0);  backward accumulates into grad_feats (caller zeroes it).
+ * X / G channels-last as in inter_group_forward.  The identity-pose case runs inter_group_forward instead. */
+int vgtkb_pose_neighbourhood(int b, int n, int nn, int a, const float* xyz, const float* pose, const int32_t* idx,
+                             const float* anchors, float* rel_xyz, uint8_t* perm, void* stream);
+int vgtkb_inter_pose_group_forward(int b, int n, int nn, int a, int k, int ci, const int32_t* idx, const float* rel_xyz,
+                                   const uint8_t* perm, const float* rot_kernels, float sigma, const float* feats,
+                                   float* grouped, void* stream);
+int vgtkb_inter_pose_group_backward(int b, int n, int nn, int a, int k, int ci, const int32_t* idx, const float* rel_xyz,
+                                    const uint8_t* perm, const float* rot_kernels, float sigma, const float* grad_grouped,
+                                    float* grad_feats, void* stream);
+
 /* vgtk.cuda.zpconv.{inter,intra}_zpconv_{forward,backward} (zpconv_cuda.cpp:113-118, kernels
  * zpconv_cuda_kernel.cu:33-195), reference layouts, explicit index/weight tensors:
  *   inter: idx, w [b,p,a,k,ann]; feats [b,c,nq,a]  -> out [b,c,k,p,a];  backward -> grad_feats [b,c,nq,a] (zeroed here)

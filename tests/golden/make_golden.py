@@ -127,6 +127,26 @@ def main():
                         grad_W=zp.basic_conv.W.grad.numpy(), grad_bias=zp.basic_conv.bias.grad.numpy())
     print("intrazp", oz.shape)
 
+    # ---- pose-aware inter grouping with NON-identity per-point rotations (no-stride branch) -------------
+    from scipy.spatial.transform import Rotation
+    g = torch.Generator().manual_seed(1003)
+    nb, npt, nnb, cc = 1, 24, 6, 5
+    pxyz = (torch.rand(nb, 3, npt, generator=g) - 0.5)
+    rot = torch.from_numpy(Rotation.random(nb * npt, random_state=7).as_matrix().astype('float32')).view(nb, npt, 3, 3)
+    ppose = torch.eye(4).repeat(nb, npt, 1, 1)
+    ppose[:, :, :3, :3] = rot
+    pfeats = torch.randn(nb, cc, npt, 60, generator=g)
+    pk = torch.from_numpy(L.get_sphereical_kernel_points_from_ply(0.7 * 0.5, 1))
+    outp = {'xyz': pxyz.numpy(), 'pose': ppose.numpy(), 'feats': pfeats.numpy(), 'kernels': pk.numpy(),
+            'radius': np.float32(0.5), 'sigma': np.float32(0.12), 'nn': np.int32(nnb)}
+    for pm in (0, 1):
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = L.inter_so3poseconv_grouping_strided(pxyz, ppose, pfeats, 1, nnb, anc, pk, 0.5, 0.12, None, None, True,
+                                                     permute_modes=pm)
+        outp[f'grouped_pm{pm}'] = r[3].numpy()
+    np.savez_compressed(os.path.join(GOLD, "ref_pose_group_small.npz"), **outp)
+    print("pose grouping", r[3].shape)
+
 
 if __name__ == "__main__":
     main()

@@ -527,3 +527,57 @@ def test_config4_dense_scan_with_chamfer(dev, ops):
     assert rel_err(Y.grad[0], gref) < 1e-4
     with torch.no_grad():
         assert torch.equal(net(X).feats, net(X).feats)
+
+
+@pytest.mark.parametrize("pm", [0, 1])
+def test_pose_grouping_non_identity_matches_reference_fixture(dev, ops, pm):
+    """InterSO3PoseConv grouping with random per-point rotations (stride 1) against the reference's own output
+    (tests/golden/ref_pose_group_small.npz), forward; backward against the oracle's autograd."""
+    from oracle import so3 as O, cops
+    from equi_articulated_pose_b200 import so3_constants as C
+    import equi_articulated_pose_b200 as eap
+    eap.install()
+    import vgtk.so3conv.functional as L
+    g = np.load(os.path.join(GOLD, "ref_pose_group_small.npz"))
+    xyz, pose = torch.from_numpy(g["xyz"]), torch.from_numpy(g["pose"])
+    feats = torch.from_numpy(g["feats"]).requires_grad_(True)
+    anchors, kern = torch.from_numpy(C.anchors_all()), torch.from_numpy(g["kernels"])
+    idx = torch.from_numpy(cops.ball_query(xyz.numpy(), xyz.numpy(), float(g["radius"]), int(g["nn"])))
+    G_ref, _, pi_ref = O.pose_inter_group_feats(xyz, pose, feats, idx, anchors, kern, float(g["sigma"]), pm)
+    go = torch.randn(G_ref.shape, generator=torch.Generator().manual_seed(3))
+    (G_ref * go).sum().backward()
+
+    rel, perm = ops.pose_neighbourhood(xyz.to(dev), pose.to(dev), idx.to(dev), anchors.to(dev), with_perm=pm != 0)
+    if pm:
+        assert torch.equal(perm.cpu().long(), pi_ref)
+    rk = L.rotated_kernels(anchors.to(dev), kern.to(dev))
+    x = feats.detach().permute(0, 2, 3, 1).contiguous().to(dev).requires_grad_(True)
+    G = ops.PoseGroupFn.apply(x, idx.to(dev), rel, perm, rk, float(g["sigma"]))
+    b, n, a, kc = G.shape
+    G_log = G.view(b, n, a, 24, kc // 24).permute(0, 4, 3, 1, 2)
+    assert rel_err(G_log, torch.from_numpy(g[f"grouped_pm{pm}"])) < 1e-5
+    (G_log * go.to(dev)).sum().backward()
+    assert rel_err(x.grad.permute(0, 3, 1, 2), feats.grad) < 1e-5
+
+
+def test_pose_conv_module_non_identity(dev):
+    """Module level: InterSO3PoseConv with rotated poses runs the general kernels and returns a pose-carrying cloud;
+    with the identity pose it equals InterSO3Conv bit for bit."""
+    import equi_articulated_pose_b200 as eap
+    eap.install()
+    import vgtk.so3conv as sptk
+    import vgtk.spconv as zptk
+    g = np.load(os.path.join(GOLD, "ref_pose_group_small.npz"))
+    torch.manual_seed(0)
+    conv = sptk.InterSO3PoseConv(5, 8, 1, 1, float(g["radius"]), float(g["sigma"]), int(g["nn"]), kanchor=60, permute_modes=1).to(dev)
+    plain = sptk.InterSO3Conv(5, 8, 1, 1, float(g["radius"]), float(g["sigma"]), int(g["nn"]), kanchor=60).to(dev)
+    plain.load_state_dict(conv.state_dict())
+    xyz, feats = torch.from_numpy(g["xyz"]).to(dev), torch.from_numpy(g["feats"]).to(dev)
+    eye = torch.eye(4, device=dev).repeat(1, xyz.shape[2], 1, 1)
+    _, _, _, o_id = conv(zptk.SphericalPointCloudPose(xyz, feats, None, eye))
+    _, _, _, o_pl = plain(zptk.SphericalPointCloud(xyz, feats, None))
+    assert torch.equal(o_id.feats, o_pl.feats)
+    _, _, _, o_rot = conv(zptk.SphericalPointCloudPose(xyz, feats, None, torch.from_numpy(g["pose"]).to(dev)))
+    assert tuple(o_rot.feats.shape) == tuple(o_pl.feats.shape) and torch.isfinite(o_rot.feats).all()
+    assert not torch.allclose(o_rot.feats, o_pl.feats)
+    assert torch.equal(o_rot.pose, torch.from_numpy(g["pose"]).to(dev))

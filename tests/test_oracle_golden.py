@@ -202,3 +202,23 @@ def test_blocks_forward_backward_match_reference(golden_dir):
         if k.startswith("after/"):
             name = k[len("after/"):]
             assert torch.allclose(sd[name], torch.from_numpy(g[k]), atol=1e-5), name
+
+
+def test_pose_grouping_matches_reference(golden_dir):
+    """Non-identity per-point rotations: relative rotation of the neighbour offsets and the anchor permutation
+    (functional.py:1061-1261) against the reference's own outputs, permute_modes 0 and 1."""
+    g = _load(golden_dir, "ref_pose_group_small.npz")
+    xyz, pose, feats = torch.from_numpy(g["xyz"]), torch.from_numpy(g["pose"]), torch.from_numpy(g["feats"])
+    idx, _ = O.ball_query(xyz, xyz, float(g["radius"]), int(g["nn"]))
+    anchors = torch.from_numpy(C.anchors_all())
+    for pm in (0, 1):
+        G, _, pi = O.pose_inter_group_feats(xyz, pose, feats, idx, anchors, torch.from_numpy(g["kernels"]), float(g["sigma"]), pm)
+        ref = torch.from_numpy(g[f"grouped_pm{pm}"])
+        assert (G - ref).abs().max() / ref.abs().max() < 1e-5, pm
+    assert not torch.equal(pi, torch.arange(60).view(1, 1, 1, 60).expand_as(pi))     # the permutation is not trivial here
+    # identity pose reduces to the plain grouping
+    eye = torch.eye(4).repeat(1, xyz.shape[2], 1, 1)
+    G0, gx, pi0 = O.pose_inter_group_feats(xyz, eye, feats, idx, anchors, torch.from_numpy(g["kernels"]), float(g["sigma"]), 1)
+    w = O.anchor_weights(gx, anchors, torch.from_numpy(g["kernels"]), float(g["sigma"]))
+    assert torch.equal(pi0, torch.arange(60).view(1, 1, 1, 60).expand_as(pi0))
+    assert torch.allclose(G0, O.inter_group_feats(idx, w, feats), atol=1e-6)
