@@ -25,6 +25,8 @@
 // TMEM buffer.
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 
 namespace vgtkb {
@@ -780,9 +782,13 @@ static int num_sms() {
     return n;
 }
 
-static int default_chunk(int passes) {
-    // k-blocks (of 32) the tensor core accumulates before the epilogue folds the chunk into registers:
-    // 2 k-blocks = 8 k-steps x passes MMAs.
+static int default_chunk(int passes, bool bf = false) {
+    // k-blocks the tensor core accumulates in TMEM before the epilogue folds the chunk into registers (experiments:
+    // VGTKB_CHUNK_KB).  Draining a 128 x 256 fp32 chunk costs about as much as the MMAs of one k-block, so the chunk
+    // must span several k-blocks; the round-toward-zero drift grows with the MMAs per chunk (12 per k-block).
+    static const int env = getenv("VGTKB_CHUNK_KB") ? atoi(getenv("VGTKB_CHUNK_KB")) : 0;
+    if (env > 0) return env;
+    if (bf) return 4;      // 48 MMAs per chunk: drift ~1e-6, below the 5e-6 of the bf16x3 products
     return passes == 3 ? 2 : 4;
 }
 
@@ -803,7 +809,7 @@ static int launch_nt(int64_t M, int N, int K, const float* A, const void* Bhi, c
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = ceil_div64(M, TC_BM) * ceil_div(N, BN) * (ga.anchors > 0 ? ga.anchors : 1);
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    kern<<<grid, TC_THREADS, smem, st>>>(ma, mhi, mlo, bias, C, M, N, K, passes, BF ? 1 : default_chunk(passes), ga);
+    kern<<<grid, TC_THREADS, smem, st>>>(ma, mhi, mlo, bias, C, M, N, K, passes, default_chunk(passes, BF), ga);
     return check_launch("gemm_nt(tcgen05)");
 }
 
@@ -902,7 +908,7 @@ static int launch_tn(const float* P, int Pw, const void* Q, const void* Q2, int 
     auto kern = tc_gemm_tn_kernel<BN, BF>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)(items < num_sms() ? items : num_sms());
-    kern<<<grid, TC_THREADS, smem, st>>>(mp, mq, mq2, Pw, Qw, C, ldc, R, rps, (int)splits, passes, BF ? 1 : default_chunk(passes),
+    kern<<<grid, TC_THREADS, smem, st>>>(mp, mq, mq2, Pw, Qw, C, ldc, R, rps, (int)splits, passes, default_chunk(passes, BF),
                                          ga, ag);
     return check_launch("gemm_tn(tcgen05)");
 }
