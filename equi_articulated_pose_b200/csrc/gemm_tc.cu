@@ -361,6 +361,232 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------------- NT kernel, CTA pairs
+// bf16x3, N tile 256, two CTAs of a cluster share ONE tcgen05.mma.cta_group::2 (M = 256): CTA r owns rows
+// [2*pair_tile + r]*128.. and HALF of the weight tile (128 of the 256 weight rows), so the weight operand -- two
+// thirds of the L2 -> SM traffic this kernel is bound by -- is fetched once per pair, and a stage shrinks to 64 KB
+// (three stages instead of two).  Only the leader (rank 0) issues MMAs; tcgen05.commit multicasts the "stage free"
+// and "chunk complete" arrivals to both CTAs; the converters and epilogues of both CTAs report to the leader's
+// barriers with remote mbarrier arrives.  Everything else (TMA-fed raw operand split in place, chunked
+// round-to-nearest accumulation, smem-transposed stores, gather addressing) is the single-CTA kernel.
+template <int BN_>
+struct PairCfg {
+    static constexpr int BN = BN_;
+    static constexpr int A_BYTES = TC_BM * 64 * 2;          // 16 KB: one bf16 tile (hi or lo) = one raw fp32 box
+    static constexpr int BH_BYTES = (BN / 2) * 64 * 2;      // this CTA's half of the weight tile, hi or lo
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;   // 64 KB at BN = 256
+    static constexpr int STAGES = (TC_SMEM_BUDGET - 8 * 1024) / STAGE_BYTES > 6 ? 6 : (TC_SMEM_BUDGET - 8 * 1024) / STAGE_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int HALF = BN / 2;
+    static_assert(STAGES >= 3 && BN % 64 == 0, "pair configuration");
+};
+
+template <int BN_>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                       const __grid_constant__ CUtensorMap map_blo, const float* __restrict__ bias, float* __restrict__ C,
+                       int64_t M, int N, int K, int chunk_kb, TcGather ga) {
+    using Cfg = PairCfg<BN_>;
+    constexpr int STAGES = Cfg::STAGES, BN = Cfg::BN, KBE = 64, UK = 16;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    __shared__ __align__(8) TcBarriers bars;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+    const int mp_tiles = (m_tiles + 1) / 2;
+    const int n_tiles = (N + BN - 1) / BN;
+    const int a_cnt = ga.anchors > 0 ? ga.anchors : 1;
+    const int total_tiles = mp_tiles * a_cnt * n_tiles;     // pair tile -> (mtp, an, nt), nt fastest
+    const int nkb = (K + KBE - 1) / KBE;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bars.raw_full[s], 1);                  // local TMA
+            mbar_init(&bars.full[s], 2 * TC_CONV_WARPS);      // converter warps of BOTH CTAs (used in the leader)
+            mbar_init(&bars.empty[s], 1);                     // multicast tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bars.tfull[a], 1);                     // multicast tcgen05.commit
+            mbar_init(&bars.tempty[a], 2 * TC_EPI_WARPS);     // epilogue warps of BOTH CTAs (used in the leader)
+        }
+        fence_barrier_init();
+    }
+    if (warp == TC_MMA_WARP) tmem_alloc_pair(&bars.tmem_base, Cfg::TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars.tmem_base;
+
+    if (warp < TC_EPI_WARPS) {
+        // ============================ epilogue ============================
+        reg_inc_epi();
+        const int q = warp & 3, h = warp >> 2;
+        float acc[Cfg::HALF];
+#pragma unroll
+        for (int i = 0; i < Cfg::HALF; ++i) acc[i] = 0.f;
+        int ci = 0;
+        const bool vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        for (int tile = pair; tile < total_tiles; tile += npairs) {
+            const int nt = tile % n_tiles, an = (tile / n_tiles) % a_cnt, mt = 2 * (tile / (n_tiles * a_cnt)) + (int)rank;
+            for (int kb0 = 0; kb0 < nkb; kb0 += chunk_kb, ++ci) {
+                const int buf = ci & 1;
+                mbar_wait_guard(&bars.tfull[buf], (ci >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < Cfg::HALF / 32; ++j) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * Cfg::HALF + j * 32), v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&bars.tempty[buf], 0);
+            }
+            const uint32_t stg = smem_base + (uint32_t)(STAGES * Cfg::STAGE_BYTES) + (uint32_t)warp * 4096u;
+            const int64_t row0 = (int64_t)mt * TC_BM + q * 32;
+            const int c_base = nt * BN + h * Cfg::HALF;
+#pragma unroll
+            for (int j = 0; j < Cfg::HALF / 32; ++j) {
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4)
+                    st_shared_v4(stg + (uint32_t)(lane * 128 + ((c4 ^ (lane & 7)) << 4)),
+                                 make_float4(acc[j * 32 + c4 * 4], acc[j * 32 + c4 * 4 + 1], acc[j * 32 + c4 * 4 + 2],
+                                             acc[j * 32 + c4 * 4 + 3]));
+                __syncwarp();
+                const int c4 = lane & 7;
+                const int col = c_base + j * 32 + c4 * 4;
+                float bb[4] = {0.f, 0.f, 0.f, 0.f};
+                if (bias != nullptr) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (col + e < N) bb[e] = bias[col + e];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + (lane >> 3);
+                    float4 o = ld_shared_v4(stg + (uint32_t)(rr * 128 + ((c4 ^ (rr & 7)) << 4)));
+                    o.x += bb[0]; o.y += bb[1]; o.z += bb[2]; o.w += bb[3];
+                    const int64_t grow = row0 + rr;
+                    if (grow < M) {
+                        float* dst = C + (grow * a_cnt + an) * N + col;
+                        if (vec_ok && col + 4 <= N) {
+                            *reinterpret_cast<float4*>(dst) = o;
+                        } else {
+                            if (col < N) dst[0] = o.x;
+                            if (col + 1 < N) dst[1] = o.y;
+                            if (col + 2 < N) dst[2] = o.z;
+                            if (col + 3 < N) dst[3] = o.w;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int i = 0; i < Cfg::HALF; ++i) acc[i] = 0.f;
+        }
+    } else if (warp != TC_MMA_WARP && warp != TC_TMA_WARP) {
+        // ============================ converters ============================
+        reg_dec_other();
+        const int ct = warp < TC_MMA_WARP ? threadIdx.x - TC_EPI_WARPS * 32 : threadIdx.x - (TC_TMA_WARP + 1) * 32 + 128;
+        int it = 0;
+        for (int tile = pair; tile < total_tiles; tile += npairs) {
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
+                convert_rows_bf16(smem_base + s * Cfg::STAGE_BYTES, ct >> 5, lane);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&bars.full[s], 0);
+            }
+        }
+    } else if (warp == TC_MMA_WARP) {
+        // ============================ MMA issuer (leader CTA only) ============================
+        reg_dec_other();
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(2 * TC_BM, BN, 0, 0);
+            int it = 0, ci = 0;
+            for (int tile = pair; tile < total_tiles; tile += npairs) {
+                for (int kb0 = 0; kb0 < nkb; kb0 += chunk_kb, ++ci) {
+                    const int buf = ci & 1;
+                    mbar_wait_guard_cluster(&bars.tempty[buf], ((ci >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                    const int kb1 = kb0 + chunk_kb < nkb ? kb0 + chunk_kb : nkb;
+                    for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait_guard_cluster(&bars.full[s], (it / STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
+                        const uint32_t a_lo = a_hi + Cfg::A_BYTES;
+                        const uint32_t b_hi = a_lo + Cfg::A_BYTES;
+                        const uint32_t b_lo = b_hi + Cfg::BH_BYTES;
+                        const int krem = K - kb * KBE;
+                        const int ksteps = krem >= KBE ? KBE / UK : (krem + UK - 1) / UK;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint32_t koff = ks * 32;
+                            const uint64_t da_hi = make_smem_desc(a_hi + koff, 16, 1024);
+                            const uint64_t db_hi = make_smem_desc(b_hi + koff, 16, 1024);
+                            const uint64_t da_lo = make_smem_desc(a_lo + koff, 16, 1024);
+                            const uint64_t db_lo = make_smem_desc(b_lo + koff, 16, 1024);
+                            const uint32_t first = ((kb - kb0) | ks) != 0;
+                            umma_bf16_pair(d_tmem, da_lo, db_hi, idesc, first);
+                            umma_bf16_pair(d_tmem, da_hi, db_lo, idesc, 1);
+                            umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, 1);
+                        }
+                        umma_commit_pair(&bars.empty[s]);
+                    }
+                    umma_commit_pair(&bars.tfull[buf]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============================ TMA producer (both CTAs: own rows, own half of the weights) =========
+        reg_dec_other();
+        if (lane == 0) {
+            tma_prefetch_desc(&map_a);
+            tma_prefetch_desc(&map_bhi);
+            tma_prefetch_desc(&map_blo);
+            const uint32_t tx = 2u * (uint32_t)Cfg::A_BYTES + 2u * (uint32_t)Cfg::BH_BYTES;
+            int it = 0;
+            for (int tile = pair; tile < total_tiles; tile += npairs) {
+                const int nt = tile % n_tiles, an = (tile / n_tiles) % a_cnt, mt = 2 * (tile / (n_tiles * a_cnt)) + (int)rank;
+                const int brow = nt * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
+                    unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&bars.raw_full[s], tx);
+                    if (ga.anchors > 0) {
+                        const int kcol = kb * KBE, kk = kcol / ga.c, c0 = kcol - kk * ga.c;
+                        const int mid = __ldg(ga.table + an * ga.kk_n + kk);
+                        tma_load_3d(st, &map_a, c0, mid, mt * TC_BM, &bars.raw_full[s]);
+                        tma_load_3d(st + Cfg::A_BYTES, &map_a, c0 + 32, mid, mt * TC_BM, &bars.raw_full[s]);
+                    } else {
+                        tma_load_2d(st, &map_a, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
+                        tma_load_2d(st + Cfg::A_BYTES, &map_a, kb * KBE + 32, mt * TC_BM, &bars.raw_full[s]);
+                    }
+                    tma_load_2d(st + 2 * Cfg::A_BYTES, &map_bhi, kb * KBE, brow, &bars.raw_full[s]);
+                    tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::BH_BYTES, &map_blo, kb * KBE, brow, &bars.raw_full[s]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == TC_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
 // hi/lo split of the (small) weight operand into a workspace [2][n]
 __global__ void split_tf32_kernel(int64_t n, const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -816,6 +1042,41 @@ static int launch_nt(int64_t M, int N, int K, const float* A, const void* Bhi, c
 static int tc_gemm_nt_impl(int64_t M, int N, int K, const float* A, const float* B, const float* bias, float* C, int passes,
                            float* workspace, cudaStream_t st, TcGather ga);
 
+// CTA-pair launch (bf16x3, N > 128): clusters of two CTAs, one pair per two SMs
+template <int BN_>
+static int launch_nt_pair(int64_t M, int N, int K, const float* A, const void* Bhi, const void* Blo, const float* bias, float* C,
+                          cudaStream_t st, TcGather ga) {
+    using Cfg = PairCfg<BN_>;
+    CUtensorMap ma, mhi, mlo;
+    int rc = ga.anchors > 0 ? make_map_3d(&ma, A, M, ga.anchors, ga.c, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B)
+                            : make_map_2d(&ma, A, M, K, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_2d(&mhi, Bhi, N, K, Cfg::BN / 2, CU_TENSOR_MAP_SWIZZLE_128B, true);
+    if (rc) return rc;
+    rc = make_map_2d(&mlo, Blo, N, K, Cfg::BN / 2, CU_TENSOR_MAP_SWIZZLE_128B, true);
+    if (rc) return rc;
+    const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024 + TC_EPI_WARPS * 4096;
+    auto kern = tc_gemm_nt_pair_kernel<BN_>;
+    VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t pair_tiles = ceil_div64(ceil_div64(M, TC_BM), 2) * ceil_div(N, Cfg::BN) * (ga.anchors > 0 ? ga.anchors : 1);
+    const int max_pairs = num_sms() / 2;
+    const int pairs = (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VGTKB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mhi, mlo, bias, C, M, N, K, default_chunk(3, true), ga));
+    return check_launch("gemm_nt(tcgen05, cta pairs)");
+}
+
 int tc_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const float* bias, float* C, int passes,
                float* workspace, cudaStream_t st) {
     return tc_gemm_nt_impl(M, N, K, A, B, bias, C, passes, workspace, st, TcGather{0, 0, 0, nullptr});
@@ -855,7 +1116,13 @@ static int tc_gemm_nt_impl(int64_t M, int N, int K, const float* A, const float*
         Blo = ws + nb;
     }
     int rc;
-    if (bf) {
+    // CTA pairs (cta_group::2) are the default for the bf16x3 mode; VGTKB_CTA_PAIRS=0 selects the single-CTA kernels
+    static const int use_pairs = getenv("VGTKB_CTA_PAIRS") ? atoi(getenv("VGTKB_CTA_PAIRS")) : 1;
+    if (bf && use_pairs) {
+        if (N <= 64) rc = launch_nt_pair<64>(M, N, K, A, Bhi, Blo, bias, C, st, ga);
+        else if (N <= 128) rc = launch_nt_pair<128>(M, N, K, A, Bhi, Blo, bias, C, st, ga);
+        else rc = launch_nt_pair<256>(M, N, K, A, Bhi, Blo, bias, C, st, ga);
+    } else if (bf) {
         if (N <= 64) rc = launch_nt<64, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st, ga);
         else if (N <= 128) rc = launch_nt<128, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st, ga);
         else rc = launch_nt<256, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st, ga);
