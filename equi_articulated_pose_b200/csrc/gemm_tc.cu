@@ -932,6 +932,245 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------------- TN kernel, CTA pairs
+// bf16x3 weight gradient with cta_group::2 (M = 256 columns of P per pair): CTA r converts its own 128 columns of P and
+// fetches HALF of the pre-split Q k-block (BN/2 columns, hi and lo), which is two thirds of the single-CTA kernel's
+// L2 -> SM traffic at BN = 256; a stage is 64 KB (three stages).  Work item = (R slice, anchor group, PAIR of P tiles,
+// Q tile); barrier protocol as in tc_gemm_nt_pair_kernel.
+template <int BN_>
+struct TnPairCfg {
+    static constexpr int BN = BN_;
+    static constexpr int A_BYTES = 16384;                   // 64 k-rows x 128 columns of P as bf16 (hi or lo)
+    static constexpr int QH_BYTES = (BN / 2) * 64 * 2;      // this CTA's half of the Q k-block, hi or lo
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * QH_BYTES;
+    static constexpr int STAGES = TC_SMEM_BUDGET / STAGE_BYTES > 6 ? 6 : TC_SMEM_BUDGET / STAGE_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int HALF = BN / 2;
+    static_assert(STAGES >= 3 && BN % 128 == 0, "pair configuration");
+};
+
+template <int BN_>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
+                       const __grid_constant__ CUtensorMap map_q2, int Pw, int Qw, float* __restrict__ C, int ldc, int64_t R,
+                       int64_t rows_per_split, int splits, int chunk_kb, TcGather ga, int anchors_per_item) {
+    using Cfg = TnPairCfg<BN_>;
+    constexpr int STAGES = Cfg::STAGES, BN = Cfg::BN, KR = 64, UK = 16;
+    constexpr uint32_t MN_LBO = 8192, K_SBO = 1024, KSTEP_BYTES = 2048;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    __shared__ __align__(8) TcBarriers bars;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int pp_tiles = ((Pw + TC_BM - 1) / TC_BM + 1) / 2;
+    const int q_tiles = (Qw + BN - 1) / BN;
+    const int tiles = pp_tiles * q_tiles;
+    const int n_groups = ga.anchors > 0 ? (ga.anchors + anchors_per_item - 1) / anchors_per_item : 1;
+    const int items = tiles * n_groups * splits;        // item -> (sp, grp, pair tile), tile fastest
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bars.raw_full[s], 1);
+            mbar_init(&bars.full[s], 2 * TC_CONV_WARPS);
+            mbar_init(&bars.empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bars.tfull[a], 1);
+            mbar_init(&bars.tempty[a], 2 * TC_EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == TC_MMA_WARP) tmem_alloc_pair(&bars.tmem_base, Cfg::TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars.tmem_base;
+
+    auto item_nkb = [&](int item, int64_t& r0) {
+        const int sp = item / (tiles * n_groups);
+        r0 = (int64_t)sp * rows_per_split;
+        const int64_t r1 = r0 + rows_per_split < R ? r0 + rows_per_split : R;
+        return (int)((r1 - r0 + KR - 1) / KR);
+    };
+    auto item_anchors = [&](int item, int& a0) {
+        if (ga.anchors <= 0) { a0 = 0; return 1; }
+        const int grp = (item / tiles) % n_groups;
+        a0 = grp * anchors_per_item;
+        return min(anchors_per_item, ga.anchors - a0);
+    };
+
+    if (warp < TC_EPI_WARPS) {
+        // ============================ epilogue ============================
+        reg_inc_epi();
+        const int q = warp & 3, h = warp >> 2;
+        float acc[Cfg::HALF];
+#pragma unroll
+        for (int i = 0; i < Cfg::HALF; ++i) acc[i] = 0.f;
+        int ci = 0;
+        for (int item = pair; item < items; item += npairs) {
+            const int tile = item % tiles;
+            const int p0 = (2 * (tile / q_tiles) + (int)rank) * TC_BM, q0 = (tile % q_tiles) * BN;
+            int64_t r0;
+            int a0;
+            const int nblk = item_nkb(item, r0) * item_anchors(item, a0);
+            for (int kb0 = 0; kb0 < nblk; kb0 += chunk_kb, ++ci) {
+                const int buf = ci & 1;
+                mbar_wait_guard(&bars.tfull[buf], (ci >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < Cfg::HALF / 32; ++j) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * Cfg::HALF + j * 32), v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&bars.tempty[buf], 0);
+            }
+            const int i = p0 + q * 32 + lane;
+            const int c_base = q0 + h * Cfg::HALF;
+            if (i < Pw) {
+#pragma unroll
+                for (int j = 0; j < Cfg::HALF; ++j)
+                    if (c_base + j < Qw) atomicAdd(C + (size_t)(c_base + j) * ldc + i, acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < Cfg::HALF; ++j) acc[j] = 0.f;
+        }
+    } else if (warp != TC_MMA_WARP && warp != TC_TMA_WARP) {
+        // ============================ converters (own P columns) ============================
+        reg_dec_other();
+        const int ct = warp < TC_MMA_WARP ? threadIdx.x - TC_EPI_WARPS * 32 : threadIdx.x - (TC_TMA_WARP + 1) * 32 + 128;
+        int it = 0;
+        for (int item = pair; item < items; item += npairs) {
+            int64_t r0;
+            int a0;
+            const int nblk = item_nkb(item, r0) * item_anchors(item, a0);
+            for (int kb = 0; kb < nblk; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
+                const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+                for (int task = ct >> 5; task < KR / 4; task += TC_CONV_WARPS) convert_tn_rows4_bf16(st, task * 4, lane);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&bars.full[s], 0);
+            }
+        }
+    } else if (warp == TC_MMA_WARP) {
+        // ============================ MMA issuer (leader CTA only) ============================
+        reg_dec_other();
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(2 * TC_BM, BN, 1, 1);   // MN-major
+            int it = 0, ci = 0;
+            for (int item = pair; item < items; item += npairs) {
+                int64_t r0;
+                int a0;
+                const int nkb = item_nkb(item, r0);
+                const int nblk = nkb * item_anchors(item, a0);
+                const int64_t rows = (r0 + rows_per_split < R ? r0 + rows_per_split : R) - r0;
+                for (int kb0 = 0; kb0 < nblk; kb0 += chunk_kb, ++ci) {
+                    const int buf = ci & 1;
+                    mbar_wait_guard_cluster(&bars.tempty[buf], ((ci >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                    const int kb1 = kb0 + chunk_kb < nblk ? kb0 + chunk_kb : nblk;
+                    for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait_guard_cluster(&bars.full[s], (it / STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t p_hi = smem_base + s * Cfg::STAGE_BYTES;
+                        const uint32_t p_lo = p_hi + Cfg::A_BYTES;
+                        const uint32_t q_hi = p_lo + Cfg::A_BYTES;
+                        const uint32_t q_lo = q_hi + Cfg::QH_BYTES;
+                        const int64_t rrem = rows - (int64_t)(kb % nkb) * KR;
+                        const int ksteps = rrem >= KR ? KR / UK : (int)((rrem + UK - 1) / UK);
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint32_t koff = ks * KSTEP_BYTES;
+                            const uint64_t dp_hi = make_smem_desc(p_hi + koff, MN_LBO, K_SBO, 2);
+                            const uint64_t dq_hi = make_smem_desc(q_hi + koff, MN_LBO, K_SBO, 2);
+                            const uint64_t dp_lo = make_smem_desc(p_lo + koff, MN_LBO, K_SBO, 2);
+                            const uint64_t dq_lo = make_smem_desc(q_lo + koff, MN_LBO, K_SBO, 2);
+                            const uint32_t first = ((kb - kb0) | ks) != 0;
+                            umma_bf16_pair(d_tmem, dp_lo, dq_hi, idesc, first);
+                            umma_bf16_pair(d_tmem, dp_hi, dq_lo, idesc, 1);
+                            umma_bf16_pair(d_tmem, dp_hi, dq_hi, idesc, 1);
+                        }
+                        umma_commit_pair(&bars.empty[s]);
+                    }
+                    umma_commit_pair(&bars.tfull[buf]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============================ TMA producer (both CTAs: own P columns, own half of Q) ============
+        reg_dec_other();
+        if (lane == 0) {
+            tma_prefetch_desc(&map_p);
+            tma_prefetch_desc(&map_q);
+            tma_prefetch_desc(&map_q2);
+            const uint32_t tx = 2u * (uint32_t)Cfg::A_BYTES + 2u * (uint32_t)Cfg::QH_BYTES;
+            int it = 0;
+            for (int item = pair; item < items; item += npairs) {
+                const int tile = item % tiles;
+                const int p0 = (2 * (tile / q_tiles) + (int)rank) * TC_BM;
+                const int q0 = (tile % q_tiles) * BN + (int)rank * (BN / 2);
+                int64_t r0;
+                int a0;
+                const int nkb = item_nkb(item, r0);
+                const int nblk = nkb * item_anchors(item, a0);
+                for (int kb = 0; kb < nblk; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
+                    unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
+                    unsigned char* sq = st + 2 * Cfg::A_BYTES;
+                    const int row = (int)(r0 + (int64_t)(kb % nkb) * KR);
+                    mbar_arrive_expect_tx(&bars.raw_full[s], tx);
+                    if (ga.anchors > 0) {
+                        const int an = a0 + kb / nkb;
+#pragma unroll
+                        for (int a = 0; a < TC_BM / 32; ++a) {
+                            const int cc = p0 + a * 32;
+                            if (cc < Pw) {
+                                const int kk = cc / ga.c;
+                                tma_load_3d(st + a * 8192, &map_p, cc - kk * ga.c, __ldg(ga.table + an * ga.kk_n + kk), row, &bars.raw_full[s]);
+                            } else {
+                                tma_load_3d(st + a * 8192, &map_p, ga.c, 0, row, &bars.raw_full[s]);   // out of bounds: zeros
+                            }
+                        }
+#pragma unroll
+                        for (int a = 0; a < BN / 128; ++a) {
+                            tma_load_3d(sq + a * 8192, &map_q, q0 + a * 64, an, row, &bars.raw_full[s]);
+                            tma_load_3d(sq + Cfg::QH_BYTES + a * 8192, &map_q2, q0 + a * 64, an, row, &bars.raw_full[s]);
+                        }
+                        continue;
+                    }
+#pragma unroll
+                    for (int a = 0; a < TC_BM / 32; ++a)
+                        tma_load_2d(st + a * 8192, &map_p, p0 + a * 32, row, &bars.raw_full[s]);
+#pragma unroll
+                    for (int a = 0; a < BN / 128; ++a) {
+                        tma_load_2d(sq + a * 8192, &map_q, q0 + a * 64, row, &bars.raw_full[s]);
+                        tma_load_2d(sq + Cfg::QH_BYTES + a * 8192, &map_q2, q0 + a * 64, row, &bars.raw_full[s]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == TC_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1180,6 +1419,72 @@ static int launch_tn(const float* P, int Pw, const void* Q, const void* Q2, int 
     return check_launch("gemm_tn(tcgen05)");
 }
 
+// CTA-pair launch of the bf16x3 weight-gradient kernel (Q tile 128 or 256)
+template <int BN_>
+static int launch_tn_pair(const float* P, int Pw, const void* Q, const void* Q2, int Qw, float* C, int ldc, int64_t R,
+                          cudaStream_t st, TcGather ga = TcGather{0, 0, 0, nullptr}) {
+    using Cfg = TnPairCfg<BN_>;
+    constexpr int KR = 64;
+    CUtensorMap mp, mq, mq2;
+    const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;
+    int rc;
+    if (ga.anchors > 0) {
+        rc = make_map_3d(&mp, P, R, ga.anchors, ga.c, KR, swz);
+        if (rc) return rc;
+        rc = make_map_3d(&mq, Q, R, ga.anchors, Qw, KR, swz, true);
+        if (rc) return rc;
+        rc = make_map_3d(&mq2, Q2, R, ga.anchors, Qw, KR, swz, true);
+        if (rc) return rc;
+    } else {
+        rc = make_map_2d(&mp, P, R, Pw, KR, swz);
+        if (rc) return rc;
+        rc = make_map_2d(&mq, Q, R, Qw, KR, swz, true);
+        if (rc) return rc;
+        rc = make_map_2d(&mq2, Q2, R, Qw, KR, swz, true);
+        if (rc) return rc;
+    }
+    const int max_pairs = num_sms() / 2;
+    const int tiles = ceil_div(ceil_div(Pw, TC_BM), 2) * ceil_div(Qw, Cfg::BN);
+    int n_groups = 1, ag = 1;
+    if (ga.anchors > 0) {
+        n_groups = (int)ceil_div64((int64_t)2 * max_pairs, tiles);
+        if (n_groups > ga.anchors) n_groups = ga.anchors;
+        ag = ceil_div(ga.anchors, n_groups);
+        n_groups = ceil_div(ga.anchors, ag);
+    }
+    int64_t splits = ceil_div64((int64_t)2 * max_pairs, (int64_t)tiles * n_groups);
+    const int64_t max_splits = ceil_div64(R, 512);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    int64_t rps = ceil_div64(ceil_div64(R, splits), KR) * KR;
+    splits = ceil_div64(R, rps);
+    const int64_t items = splits * tiles * n_groups;
+    const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024;
+    auto kern = tc_gemm_tn_pair_kernel<BN_>;
+    VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int pairs = (int)(items < max_pairs ? items : max_pairs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VGTKB_CUDA(cudaLaunchKernelEx(&cfg, kern, mp, mq, mq2, Pw, Qw, C, ldc, R, rps, (int)splits, default_chunk(3, true), ga, ag));
+    return check_launch("gemm_tn(tcgen05, cta pairs)");
+}
+
+static bool tn_pairs_enabled() {
+    static const int v = getenv("VGTKB_CTA_PAIRS_TN") ? atoi(getenv("VGTKB_CTA_PAIRS_TN"))
+                         : (getenv("VGTKB_CTA_PAIRS") ? atoi(getenv("VGTKB_CTA_PAIRS")) : 1);
+    return v != 0;
+}
+
 // C[M,N] (+)= A[R,M]^T B[R,N]:  P = B (tiles of 128 over N), Q = A (tiles of <= 256 over M)
 // `workspace` (bf16x3 only): R*M floats, holds the bf16 hi/lo split of A.
 int tc_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C, int accumulate, int passes,
@@ -1198,6 +1503,8 @@ int tc_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C
         const int blocks = (int)(ceil_div64(na, 256) < 2368 ? ceil_div64(na, 256) : 2368);
         split_bf16_kernel<<<blocks, 256, 0, st>>>(na, A, hi, lo);
         if (M <= 64) return launch_tn<64, true>(B, N, hi, lo, M, C, N, R, 3, st);
+        if (tn_pairs_enabled() && N > TC_BM)
+            return M <= 128 ? launch_tn_pair<128>(B, N, hi, lo, M, C, N, R, st) : launch_tn_pair<256>(B, N, hi, lo, M, C, N, R, st);
         if (M <= 128) return launch_tn<128, true>(B, N, hi, lo, M, C, N, R, 3, st);
         return launch_tn<256, true>(B, N, hi, lo, M, C, N, R, 3, st);
     }
@@ -1224,6 +1531,9 @@ int tc_gemm_tn_gather(int64_t points, int anchors, int kk_n, int c_n, int M, con
         const int blocks = (int)(ceil_div64(na, 256) < 2368 ? ceil_div64(na, 256) : 2368);
         split_bf16_kernel<<<blocks, 256, 0, st>>>(na, Y, hi, lo);
         if (M <= 64) return launch_tn<64, true>(X, N, hi, lo, M, C, N, points, 3, st, ga);
+        if (tn_pairs_enabled() && N > TC_BM)
+            return M <= 128 ? launch_tn_pair<128>(X, N, hi, lo, M, C, N, points, st, ga)
+                            : launch_tn_pair<256>(X, N, hi, lo, M, C, N, points, st, ga);
         if (M <= 128) return launch_tn<128, true>(X, N, hi, lo, M, C, N, points, 3, st, ga);
         return launch_tn<256, true>(X, N, hi, lo, M, C, N, points, 3, st, ga);
     }
