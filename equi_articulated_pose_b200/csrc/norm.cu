@@ -161,12 +161,99 @@ col_reduce4_kernel(int64_t rows, int c, int rows_per_cta, const float* __restric
     }
 }
 
+// batched variant for c/4 dividing NT (every power-of-two channel count up to 1024): a thread keeps ONE channel quad,
+// issues U independent 16-byte loads per array before touching any of them (the kernel is latency-bound otherwise:
+// 30% of the HBM rate with one load in flight per thread), and folds them into its fp64 sums.
+template <int MODE, int U>
+__global__ void __launch_bounds__(NT, MODE == 1 ? 3 : 4)
+col_reduce4b_kernel(int64_t rows, int c, int rows_per_cta, const float* __restrict__ x, OpBwd bw, double* __restrict__ scratch) {
+    const int g = blockIdx.y;
+    const int c4 = c >> 2;
+    const int ty = NT / c4;
+    const int q = threadIdx.x % c4, ly = threadIdx.x / c4;
+    const int ch = q * 4;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = min(rows, r0 + rows_per_cta);
+    const float4* xg = reinterpret_cast<const float4*>(x + (size_t)g * rows * c) + q;
+    const float4* gyg = MODE == 1 ? reinterpret_cast<const float4*>(bw.gy + (size_t)g * rows * c) + q : nullptr;
+    __shared__ double sh[NT][8];
+    double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+    float mean[4] = {0.f, 0.f, 0.f, 0.f}, inv[4] = {1.f, 1.f, 1.f, 1.f}, ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            mean[i] = bw.stats[(size_t)g * 2 * c + ch + i];
+            inv[i] = bw.stats[(size_t)g * 2 * c + c + ch + i];
+            if (bw.gamma) ga[i] = bw.gamma[ch + i];
+            if (bw.beta) be[i] = bw.beta[ch + i];
+        }
+    }
+    for (int64_t r = r0 + ly; r < r1; r += (int64_t)ty * U) {
+        float4 v4[U], g4[MODE == 1 ? U : 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t rr = r + (int64_t)u * ty;
+            const bool ok = rr < r1;
+            v4[u] = ok ? __ldg(xg + rr * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE == 1) g4[u] = ok ? __ldg(gyg + rr * c4) : make_float4(0.f, 0.f, 0.f, 0.f);   // gy = 0: no contribution
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float v[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+            if (MODE == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double d = (double)v[i];
+                    s1[i] += d;
+                    s2[i] = fma(d, d, s2[i]);
+                }
+            } else if (MODE == 1) {
+                const float gv[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xh = (v[i] - mean[i]) * inv[i];
+                    const float pre = xh * ga[i] + be[i];
+                    const float d = pre > 0.f ? gv[i] : gv[i] * bw.slope;
+                    s1[i] += (double)d;
+                    s2[i] += (double)d * (double)xh;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s1[i] += (double)v[i];
+            }
+        }
+    }
+    if (ty > 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            sh[threadIdx.x][i] = s1[i];
+            sh[threadIdx.x][4 + i] = s2[i];
+        }
+        __syncthreads();
+        // the NT/c4 partial sums of a channel quad are folded by 8 threads (one per sum) instead of one
+        for (int t = threadIdx.x; t < c4 * 8; t += NT) {
+            const int qq = t >> 3, i = t & 7;
+            if (MODE == 2 && i >= 4) continue;
+            double s = 0.0;
+            for (int j = 0; j < ty; ++j) s += sh[j * c4 + qq][i];
+            atomicAdd(scratch + ((size_t)g * 2 + (i >> 2)) * c + qq * 4 + (i & 3), s);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            atomicAdd(scratch + ((size_t)g * 2 + 0) * c + ch + i, s1[i]);
+            if (MODE != 2) atomicAdd(scratch + ((size_t)g * 2 + 1) * c + ch + i, s2[i]);
+        }
+    }
+}
+
 template <int MODE>
 static void launch_col_reduce(int groups, int64_t rows, int c, int rpc, unsigned gx, const float* x, const OpBwd& bw,
                               double* scratch, cudaStream_t st) {
     const bool v4 = c % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                     (MODE != 1 || (reinterpret_cast<uintptr_t>(bw.gy) & 15) == 0);
-    if (v4) col_reduce4_kernel<MODE><<<dim3(gx, groups), NT, 0, st>>>(rows, c, rpc, x, bw, scratch);
+    if (v4 && NT % (c / 4) == 0) col_reduce4b_kernel<MODE, (MODE == 1 ? 4 : 8)><<<dim3(gx, groups), NT, 0, st>>>(rows, c, rpc, x, bw, scratch);
+    else if (v4) col_reduce4_kernel<MODE><<<dim3(gx, groups), NT, 0, st>>>(rows, c, rpc, x, bw, scratch);
     else col_reduce_kernel<MODE><<<dim3(gx, groups), NT, 0, st>>>(rows, c, rpc, x, bw, scratch);
 }
 
@@ -271,6 +358,97 @@ __global__ void norm_act_bwd_apply4_kernel(int64_t total4, int64_t rows, int c4,
     }
 }
 
+// batched forward / backward apply for c/4 dividing NT: grid (x, groups); the channel quad of a thread never changes
+// (the grid stride is a multiple of c/4), so the per-channel coefficients live in registers and a thread keeps U
+// independent 16-byte loads per array in flight.
+template <int U>
+__global__ void __launch_bounds__(NT, 4)
+norm_act_fwd4b_kernel(int64_t rows4, int c4, const float4* __restrict__ x, const float* __restrict__ stats,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
+                      const float4* __restrict__ res, float4* __restrict__ y) {
+    const int c = c4 * 4, g = blockIdx.y;
+    const int64_t t0 = (int64_t)blockIdx.x * NT + threadIdx.x, stride = (int64_t)gridDim.x * NT;
+    const int ch = (int)(t0 % c4) * 4;
+    const size_t base = (size_t)g * rows4;
+    const float4 mean = *reinterpret_cast<const float4*>(stats + (size_t)g * 2 * c + ch);
+    const float4 inv = *reinterpret_cast<const float4*>(stats + (size_t)g * 2 * c + c + ch);
+    float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gamma) ga = *reinterpret_cast<const float4*>(gamma + ch);
+    if (beta) be = *reinterpret_cast<const float4*>(beta + ch);
+    for (int64_t t = t0; t < rows4; t += stride * U) {
+        float4 v[U], r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t tt = t + u * stride;
+            if (tt < rows4) {
+                v[u] = __ldg(x + base + tt);
+                if (res) r[u] = __ldg(res + base + tt);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t tt = t + u * stride;
+            if (tt < rows4) {
+                float o[4] = {(v[u].x - mean.x) * inv.x * ga.x + be.x, (v[u].y - mean.y) * inv.y * ga.y + be.y,
+                              (v[u].z - mean.z) * inv.z * ga.z + be.z, (v[u].w - mean.w) * inv.w * ga.w + be.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = o[i] > 0.f ? o[i] : o[i] * slope;
+                if (res) { o[0] += r[u].x; o[1] += r[u].y; o[2] += r[u].z; o[3] += r[u].w; }
+                y[base + tt] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
+template <int U>
+__global__ void __launch_bounds__(NT, 3)
+norm_act_bwd_apply4b_kernel(int64_t rows4, int64_t rows, int c4, const float4* __restrict__ x, OpBwd bw,
+                            const double* __restrict__ scratch, float4* __restrict__ gx) {
+    const int c = c4 * 4, g = blockIdx.y;
+    const int64_t t0 = (int64_t)blockIdx.x * NT + threadIdx.x, stride = (int64_t)gridDim.x * NT;
+    const int ch = (int)(t0 % c4) * 4;
+    const size_t base = (size_t)g * rows4;
+    const float4* gy = reinterpret_cast<const float4*>(bw.gy);
+    const double inv_rows = 1.0 / (double)rows;
+    float mean[4], inv[4], ga[4], be[4], m1[4], m2[4], a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        mean[i] = bw.stats[(size_t)g * 2 * c + ch + i];
+        inv[i] = bw.stats[(size_t)g * 2 * c + c + ch + i];
+        ga[i] = bw.gamma ? bw.gamma[ch + i] : 1.f;
+        be[i] = bw.beta ? bw.beta[ch + i] : 0.f;
+        m1[i] = (float)(scratch[((size_t)g * 2 + 0) * c + ch + i] * inv_rows);
+        m2[i] = (float)(scratch[((size_t)g * 2 + 1) * c + ch + i] * inv_rows);
+        a[i] = ga[i] * inv[i];
+    }
+    for (int64_t t = t0; t < rows4; t += stride * U) {
+        float4 xv[U], gv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t tt = t + u * stride;
+            if (tt < rows4) {
+                xv[u] = __ldcs(x + base + tt);      // last use of both tensors
+                gv[u] = __ldcs(gy + base + tt);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t tt = t + u * stride;
+            if (tt < rows4) {
+                const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, gs[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xh = (xs[i] - mean[i]) * inv[i];
+                    const float d = (xh * ga[i] + be[i]) > 0.f ? gs[i] : gs[i] * bw.slope;
+                    o[i] = a[i] * (d - m1[i] - xh * m2[i]);
+                }
+                gx[base + tt] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
 __global__ void affine_grad_kernel(int groups, int c, const double* __restrict__ scratch, float* ggamma, float* gbeta) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= c) return;
@@ -330,7 +508,14 @@ extern "C" int vgtkb_norm_act_forward(int groups, int64_t rows, int c, const flo
                     (!residual || al(residual));
     const int64_t work = v4 ? total / 4 : total;
     const unsigned grid = (unsigned)(ceil_div64(work, NT) < (int64_t)kNumSMs * 16 ? ceil_div64(work, NT) : kNumSMs * 16);
-    if (v4)
+    if (v4 && NT % (c / 4) == 0 && groups <= 65535) {
+        const int64_t rows4 = rows * (c / 4);
+        int64_t gx = ceil_div64(rows4, (int64_t)NT * 4);
+        const int64_t cap = ceil_div64((int64_t)kNumSMs * 8, groups);
+        if (gx > cap) gx = cap;
+        norm_act_fwd4b_kernel<4><<<dim3((unsigned)gx, groups), NT, 0, st>>>(rows4, c / 4, (const float4*)x, stats, gamma, beta, slope,
+                                                                           (const float4*)residual, (float4*)y);
+    } else if (v4)
         norm_act_fwd_kernel<<<grid, NT, 0, st>>>(work, rows, c / 4, (const float4*)x, stats, gamma, beta, slope,
                                                  (const float4*)residual, (float4*)y);
     else
@@ -353,7 +538,14 @@ extern "C" int vgtkb_norm_act_backward(int groups, int64_t rows, int c, const fl
     launch_col_reduce<1>(groups, rows, c, rpc, gx, x, bw, scratch, st);
     const int64_t total = (int64_t)groups * rows * c;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    if (c % 4 == 0 && al16(x) && al16(grad_y) && al16(grad_x)) {
+    if (c % 4 == 0 && NT % (c / 4) == 0 && al16(x) && al16(grad_y) && al16(grad_x)) {
+        const int64_t rows4 = rows * (c / 4);
+        int64_t gx4 = ceil_div64(rows4, (int64_t)NT * 4);
+        const int64_t cap = ceil_div64((int64_t)kNumSMs * 6, groups);
+        if (gx4 > cap) gx4 = cap;
+        norm_act_bwd_apply4b_kernel<4><<<dim3((unsigned)gx4, groups), NT, 0, st>>>(rows4, rows, c / 4, (const float4*)x, bw, scratch,
+                                                                                  (float4*)grad_x);
+    } else if (c % 4 == 0 && al16(x) && al16(grad_y) && al16(grad_x)) {
         const int64_t total4 = total / 4;
         const unsigned grid4 = (unsigned)(ceil_div64(total4, NT) < (int64_t)kNumSMs * 16 ? ceil_div64(total4, NT) : kNumSMs * 16);
         norm_act_bwd_apply4_kernel<<<grid4, NT, 0, st>>>(total4, rows, c / 4, (const float4*)x, bw, scratch, (float4*)grad_x);
