@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sync-bn", action="store_true", help="N>1: keep BatchNorm statistics per rank (default: SyncBatchNorm, as the reference trainer converts its model)")
     ap.add_argument("--gemm-mode", type=int, default=None, help="contraction arithmetic: 0 fp32 FFMA, 1 tcgen05 3xTF32, 2 tcgen05 1xTF32, 3 tcgen05 bf16x3 (default)")
     return ap.parse_args()
 
@@ -257,6 +258,9 @@ def run_ours(args):
     net = blocks.SO3Backbone(params)
     net.load_state_dict(O.init_backbone_state(params, seed=0), strict=False)
     net = net.to(dev).train()
+    sync_bn = world > 1 and not args.no_sync_bn
+    if sync_bn:
+        blocks.convert_sync_batchnorm(net)         # trainer_unsup_arti_align.py:430
     bucket = dp.FlatGradBucket(net.parameters())
     opt = torch.optim.Adam(bucket.params, lr=1e-3, fused=True)
 
@@ -333,7 +337,7 @@ def run_ours(args):
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "clouds_per_gpu": CLOUDS_PER_GPU, "n_points": N_POINTS, "anchors": N_ANCHORS,
-                           "step": "fwd + bwd + gradient all-reduce (N>1) + fused Adam", "parallelism": f"dp{world}",
+                           "step": "fwd + bwd + gradient all-reduce (N>1) + fused Adam", "parallelism": f"dp{world}", "sync_batchnorm": bool(sync_bn),
                            "gemm_mode": ops.get_gemm_mode(),
                            "l2": "256 MiB buffer written between steps (L2 flush); per-step activations >> 126 MB L2"},
                 "e2e": {"value": pts_per_step * args.steps / (ms_e2e * 1e-3), "unit": "points/s",

@@ -57,7 +57,10 @@ def _unrows(rows, b, p, a):
 
 class FusedBatchNorm2d(nn.BatchNorm2d):
     """nn.BatchNorm2d (identical parameters / buffers) whose forward on channels-last rows is one
-    statistics pass + one normalise-activate pass (vgtkb_norm_stats / vgtkb_norm_act_forward)."""
+    statistics pass + one normalise-activate pass (vgtkb_norm_stats / vgtkb_norm_act_forward).
+    `sync_group` (set by convert_sync_batchnorm): statistics over all data-parallel ranks, nn.SyncBatchNorm semantics."""
+
+    sync_group = None
 
     def forward_rows(self, rows, slope, residual=None):
         training = self.training or not self.track_running_stats
@@ -67,7 +70,7 @@ class FusedBatchNorm2d(nn.BatchNorm2d):
         return _ops.norm_act(rows.unsqueeze(0), self.weight, self.bias, None if residual is None else residual.unsqueeze(0),
                              self.running_mean if training else self.running_mean,
                              self.running_var if training else self.running_var,
-                             mom, self.eps, slope, use_running=not training).squeeze(0)
+                             mom, self.eps, slope, use_running=not training, sync_group=self.sync_group).squeeze(0)
 
 
 class FusedInstanceNorm2d(nn.InstanceNorm2d):
@@ -77,6 +80,16 @@ class FusedInstanceNorm2d(nn.InstanceNorm2d):
         m, c = rows.shape
         res = None if residual is None else residual.view(batch, m // batch, c)
         return _ops.norm_act(rows.view(batch, m // batch, c), None, None, res, None, None, 0.1, self.eps, slope).view(m, c)
+
+
+def convert_sync_batchnorm(module, process_group=None):
+    """Counterpart of nn.SyncBatchNorm.convert_sync_batchnorm (the reference trainer applies it to the whole model,
+    SPConvNets/trainer_unsup_arti_align.py:430): every fused BatchNorm of `module` takes its statistics over all ranks of
+    `process_group` (None = the default group).  InstanceNorm layers are per-sample and stay local."""
+    for m in module.modules():
+        if isinstance(m, FusedBatchNorm2d):
+            m.sync_group = True if process_group is None else process_group
+    return module
 
 
 def _make_norm(norm, dim):

@@ -7,7 +7,7 @@
 
 #include "../../include/vgtkb.h"
 
-#define VGTKB_ABI_VERSION 6
+#define VGTKB_ABI_VERSION 7
 
 namespace vgtkb {
 

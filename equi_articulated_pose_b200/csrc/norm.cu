@@ -263,14 +263,14 @@ __global__ void stats_finalize_kernel(int groups, int64_t rows, int c, float eps
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= groups * c) return;
     const int g = t / c, ch = t % c;
-    const double n = (double)rows;
+    const double n = rows > 0 ? (double)rows : scratch[(size_t)groups * 2 * c];   // rows <= 0: count stored after the sums
     const double mean = scratch[((size_t)g * 2 + 0) * c + ch] / n;
     double var = scratch[((size_t)g * 2 + 1) * c + ch] / n - mean * mean;
     if (var < 0.0) var = 0.0;
     stats[(size_t)g * 2 * c + ch] = (float)mean;
     stats[(size_t)g * 2 * c + c + ch] = (float)(1.0 / sqrt(var + (double)eps));
     if (running_mean != nullptr && g == 0) {  // BatchNorm (groups == 1): torch uses the unbiased variance here
-        const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+        const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
         running_mean[ch] = (float)((1.0 - momentum) * running_mean[ch] + momentum * mean);
         running_var[ch] = (float)((1.0 - momentum) * running_var[ch] + momentum * unbiased);
     }
@@ -318,26 +318,27 @@ __global__ void norm_act_fwd_scalar_kernel(int64_t total, int64_t rows, int c, c
 }
 
 // dx = gamma*invstd*(dyp - S1/n - xhat*S2/n)
-__global__ void norm_act_bwd_apply_kernel(int64_t total, int64_t rows, int c, const float* __restrict__ x,
+__global__ void norm_act_bwd_apply_kernel(int64_t total, int64_t rows, int64_t nrows, int c, const float* __restrict__ x,
                                           OpBwd bw, const double* __restrict__ scratch, float* __restrict__ gx) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int ch = (int)(t % c);
         const int g = (int)(t / (rows * c));
         float xh;
         const float d = bw.dyp(x[t], bw.gy[t], g, ch, xh);
-        const float m1 = (float)(scratch[((size_t)g * 2 + 0) * c + ch] / (double)rows);
-        const float m2 = (float)(scratch[((size_t)g * 2 + 1) * c + ch] / (double)rows);
+        const double nn = nrows > 0 ? (double)nrows : scratch[(size_t)(total / (rows * c)) * 2 * c];   // count behind the sums
+        const float m1 = (float)(scratch[((size_t)g * 2 + 0) * c + ch] / nn);
+        const float m2 = (float)(scratch[((size_t)g * 2 + 1) * c + ch] / nn);
         const float inv = bw.stats[(size_t)g * 2 * c + c + ch];
         const float ga = bw.gamma ? bw.gamma[ch] : 1.f;
         gx[t] = ga * inv * (d - m1 - xh * m2);
     }
 }
 
-__global__ void norm_act_bwd_apply4_kernel(int64_t total4, int64_t rows, int c4, const float4* __restrict__ x, OpBwd bw,
+__global__ void norm_act_bwd_apply4_kernel(int64_t total4, int64_t rows, int64_t nrows, int c4, const float4* __restrict__ x, OpBwd bw,
                                            const double* __restrict__ scratch, float4* __restrict__ gx) {
     const int c = c4 * 4;
     const float4* gy = reinterpret_cast<const float4*>(bw.gy);
-    const double inv_rows = 1.0 / (double)rows;
+    const double inv_rows = 1.0 / (nrows > 0 ? (double)nrows : scratch[(size_t)(total4 / (rows * c4)) * 2 * c]);
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (int64_t)gridDim.x * blockDim.x) {
         const int ch = (int)(t % c4) * 4;
         const int g = (int)(t / (rows * c4));
@@ -402,14 +403,14 @@ norm_act_fwd4b_kernel(int64_t rows4, int c4, const float4* __restrict__ x, const
 
 template <int U>
 __global__ void __launch_bounds__(NT, 3)
-norm_act_bwd_apply4b_kernel(int64_t rows4, int64_t rows, int c4, const float4* __restrict__ x, OpBwd bw,
+norm_act_bwd_apply4b_kernel(int64_t rows4, int64_t rows, int64_t nrows, int c4, const float4* __restrict__ x, OpBwd bw,
                             const double* __restrict__ scratch, float4* __restrict__ gx) {
     const int c = c4 * 4, g = blockIdx.y;
     const int64_t t0 = (int64_t)blockIdx.x * NT + threadIdx.x, stride = (int64_t)gridDim.x * NT;
     const int ch = (int)(t0 % c4) * 4;
     const size_t base = (size_t)g * rows4;
     const float4* gy = reinterpret_cast<const float4*>(bw.gy);
-    const double inv_rows = 1.0 / (double)rows;
+    const double inv_rows = 1.0 / (nrows > 0 ? (double)nrows : scratch[(size_t)gridDim.y * 2 * c]);
     float mean[4], inv[4], ga[4], be[4], m1[4], m2[4], a[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -481,10 +482,10 @@ static int reduce_geometry(int64_t rows, int c, int groups, int& rows_per_cta, u
 
 using namespace vgtkb;
 
-extern "C" int vgtkb_norm_stats(int groups, int64_t rows, int c, const float* x, float eps, double* scratch,
-                                float* stats, float* running_mean, float* running_var, float momentum, void* stream) {
-    VGTKB_REQUIRE(groups > 0 && rows > 0 && c > 0, "norm_stats: bad size");
-    VGTKB_REQUIRE(groups <= 65535, "norm_stats: too many groups");
+// phase 1 of the statistics: local fp64 sums (sum x, sum x^2) per (group, channel) into scratch [groups][2][c]
+extern "C" int vgtkb_norm_sums(int groups, int64_t rows, int c, const float* x, double* scratch, void* stream) {
+    VGTKB_REQUIRE(groups > 0 && rows > 0 && c > 0, "norm_sums: bad size");
+    VGTKB_REQUIRE(groups <= 65535, "norm_sums: too many groups");
     cudaStream_t st = (cudaStream_t)stream;
     VGTKB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (size_t)groups * 2 * c, st));
     int rpc;
@@ -492,9 +493,24 @@ extern "C" int vgtkb_norm_stats(int groups, int64_t rows, int c, const float* x,
     reduce_geometry(rows, c, groups, rpc, gx);
     OpBwd dummy{};
     launch_col_reduce<0>(groups, rows, c, rpc, gx, x, dummy, scratch, st);
-    stats_finalize_kernel<<<ceil_div(groups * c, 128), 128, 0, st>>>(groups, rows, c, eps, scratch, stats, running_mean,
+    return check_launch("norm_sums");
+}
+
+// phase 2: (mean, invstd) and the running statistics from sums over `total_rows` rows (all ranks' rows under SyncBN)
+extern "C" int vgtkb_norm_finalize(int groups, int64_t total_rows, int c, float eps, const double* scratch, float* stats,
+                                   float* running_mean, float* running_var, float momentum, void* stream) {
+    VGTKB_REQUIRE(groups > 0 && c > 0, "norm_finalize: bad size");
+    cudaStream_t st = (cudaStream_t)stream;
+    stats_finalize_kernel<<<ceil_div(groups * c, 128), 128, 0, st>>>(groups, total_rows, c, eps, scratch, stats, running_mean,
                                                                     running_var, momentum);
-    return check_launch("norm_stats");
+    return check_launch("norm_finalize");
+}
+
+extern "C" int vgtkb_norm_stats(int groups, int64_t rows, int c, const float* x, float eps, double* scratch,
+                                float* stats, float* running_mean, float* running_var, float momentum, void* stream) {
+    const int rc = vgtkb_norm_sums(groups, rows, c, x, scratch, stream);
+    if (rc != 0) return rc;
+    return vgtkb_norm_finalize(groups, rows, c, eps, scratch, stats, running_mean, running_var, momentum, stream);
 }
 
 extern "C" int vgtkb_norm_act_forward(int groups, int64_t rows, int c, const float* x, const float* stats,
@@ -523,12 +539,13 @@ extern "C" int vgtkb_norm_act_forward(int groups, int64_t rows, int c, const flo
     return check_launch("norm_act_forward");
 }
 
-extern "C" int vgtkb_norm_act_backward(int groups, int64_t rows, int c, const float* x, const float* stats,
-                                       const float* gamma, const float* beta, float slope, const float* grad_y,
-                                       double* scratch, float* grad_x, float* grad_gamma, float* grad_beta,
-                                       void* stream) {
-    VGTKB_REQUIRE(groups > 0 && rows > 0 && c > 0, "norm_act_backward: bad size");
-    VGTKB_REQUIRE(groups <= 65535, "norm_act_backward: too many groups");
+// backward phase 1: local fp64 sums (sum dyp, sum dyp*xhat) into scratch; grad_gamma / grad_beta are LOCAL sums
+// (under data parallelism they are reduced with the other parameter gradients, as torch's SyncBatchNorm does)
+extern "C" int vgtkb_norm_bwd_sums(int groups, int64_t rows, int c, const float* x, const float* stats, const float* gamma,
+                                   const float* beta, float slope, const float* grad_y, double* scratch, float* grad_gamma,
+                                   float* grad_beta, void* stream) {
+    VGTKB_REQUIRE(groups > 0 && rows > 0 && c > 0, "norm_bwd_sums: bad size");
+    VGTKB_REQUIRE(groups <= 65535, "norm_bwd_sums: too many groups");
     cudaStream_t st = (cudaStream_t)stream;
     VGTKB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (size_t)groups * 2 * c, st));
     OpBwd bw{grad_y, stats, gamma, beta, slope, c};
@@ -536,6 +553,19 @@ extern "C" int vgtkb_norm_act_backward(int groups, int64_t rows, int c, const fl
     unsigned gx;
     reduce_geometry(rows, c, groups, rpc, gx);
     launch_col_reduce<1>(groups, rows, c, rpc, gx, x, bw, scratch, st);
+    if (grad_gamma || grad_beta)
+        affine_grad_kernel<<<ceil_div(c, 128), 128, 0, st>>>(groups, c, scratch, grad_gamma, grad_beta);
+    return check_launch("norm_bwd_sums");
+}
+
+// backward phase 2: dx = gamma*invstd*(dyp - S1/n - xhat*S2/n) with n = total_rows (all ranks' rows under SyncBN)
+extern "C" int vgtkb_norm_bwd_apply(int groups, int64_t rows, int64_t total_rows, int c, const float* x, const float* stats,
+                                    const float* gamma, const float* beta, float slope, const float* grad_y,
+                                    const double* scratch, float* grad_x, void* stream) {
+    VGTKB_REQUIRE(groups > 0 && rows > 0 && (total_rows <= 0 || total_rows >= rows) && c > 0, "norm_bwd_apply: bad size");
+    VGTKB_REQUIRE(groups <= 65535, "norm_bwd_apply: too many groups");
+    cudaStream_t st = (cudaStream_t)stream;
+    OpBwd bw{grad_y, stats, gamma, beta, slope, c};
     const int64_t total = (int64_t)groups * rows * c;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if (c % 4 == 0 && NT % (c / 4) == 0 && al16(x) && al16(grad_y) && al16(grad_x)) {
@@ -543,19 +573,26 @@ extern "C" int vgtkb_norm_act_backward(int groups, int64_t rows, int c, const fl
         int64_t gx4 = ceil_div64(rows4, (int64_t)NT * 4);
         const int64_t cap = ceil_div64((int64_t)kNumSMs * 6, groups);
         if (gx4 > cap) gx4 = cap;
-        norm_act_bwd_apply4b_kernel<4><<<dim3((unsigned)gx4, groups), NT, 0, st>>>(rows4, rows, c / 4, (const float4*)x, bw, scratch,
-                                                                                  (float4*)grad_x);
+        norm_act_bwd_apply4b_kernel<4><<<dim3((unsigned)gx4, groups), NT, 0, st>>>(rows4, rows, total_rows, c / 4, (const float4*)x, bw,
+                                                                                  scratch, (float4*)grad_x);
     } else if (c % 4 == 0 && al16(x) && al16(grad_y) && al16(grad_x)) {
         const int64_t total4 = total / 4;
         const unsigned grid4 = (unsigned)(ceil_div64(total4, NT) < (int64_t)kNumSMs * 16 ? ceil_div64(total4, NT) : kNumSMs * 16);
-        norm_act_bwd_apply4_kernel<<<grid4, NT, 0, st>>>(total4, rows, c / 4, (const float4*)x, bw, scratch, (float4*)grad_x);
+        norm_act_bwd_apply4_kernel<<<grid4, NT, 0, st>>>(total4, rows, total_rows, c / 4, (const float4*)x, bw, scratch, (float4*)grad_x);
     } else {
         const unsigned grid = (unsigned)(ceil_div64(total, NT) < (int64_t)kNumSMs * 16 ? ceil_div64(total, NT) : kNumSMs * 16);
-        norm_act_bwd_apply_kernel<<<grid, NT, 0, st>>>(total, rows, c, x, bw, scratch, grad_x);
+        norm_act_bwd_apply_kernel<<<grid, NT, 0, st>>>(total, rows, total_rows, c, x, bw, scratch, grad_x);
     }
-    if (grad_gamma || grad_beta)
-        affine_grad_kernel<<<ceil_div(c, 128), 128, 0, st>>>(groups, c, scratch, grad_gamma, grad_beta);
-    return check_launch("norm_act_backward");
+    return check_launch("norm_bwd_apply");
+}
+
+extern "C" int vgtkb_norm_act_backward(int groups, int64_t rows, int c, const float* x, const float* stats,
+                                       const float* gamma, const float* beta, float slope, const float* grad_y,
+                                       double* scratch, float* grad_x, float* grad_gamma, float* grad_beta,
+                                       void* stream) {
+    const int rc = vgtkb_norm_bwd_sums(groups, rows, c, x, stats, gamma, beta, slope, grad_y, scratch, grad_gamma, grad_beta, stream);
+    if (rc != 0) return rc;
+    return vgtkb_norm_bwd_apply(groups, rows, rows, c, x, stats, gamma, beta, slope, grad_y, scratch, grad_x, stream);
 }
 
 extern "C" int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream) {

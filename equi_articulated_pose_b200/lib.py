@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgtkb200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _lib = None
 _device_ok = set()
@@ -44,6 +44,10 @@ SIGNATURES = {
     "vgtkb_gather_gemm_nt": [c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp],
     "vgtkb_gather_gemm_tn": [c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
     "vgtkb_norm_stats": [c_int, c_i64, c_int, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp],
+    "vgtkb_norm_sums": [c_int, c_i64, c_int, c_vp, c_vp, c_vp],
+    "vgtkb_norm_finalize": [c_int, c_i64, c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp],
+    "vgtkb_norm_bwd_sums": [c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_norm_bwd_apply": [c_int, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_norm_act_forward": [c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
     "vgtkb_norm_act_backward": [c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_col_sum": [c_i64, c_int, c_vp, c_vp, c_vp, c_vp],
@@ -124,4 +128,4 @@ PROFILE = None  # set to a list to record (entry point, args, start event, end e
 # device kernels launched per entry point (memsets not counted); used for bench.py's gpu_launches
 KERNELS_PER_CALL = {"vgtkb_gemm_nt": 2, "vgtkb_gemm_tn": 2, "vgtkb_gather_gemm_nt": 2, "vgtkb_gather_gemm_tn": 2,
                     "vgtkb_chamfer_forward": 2, "vgtkb_chamfer_backward": 4, "vgtkb_norm_stats": 2,
-                    "vgtkb_norm_act_backward": 3, "vgtkb_col_sum": 2}
+                    "vgtkb_norm_act_backward": 3, "vgtkb_norm_bwd_sums": 2, "vgtkb_col_sum": 2}

@@ -350,27 +350,53 @@ class RowGatherFn(torch.autograd.Function):
         return gx, None
 
 
+def _sync_world(group):
+    """Number of ranks a SyncBatchNorm reduction spans (1 = plain BatchNorm).  `group`: False/None = off,
+    True = the default process group, or a torch.distributed process group."""
+    if group is None or group is False:
+        return 1
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        return 1
+    return dist.get_world_size(None if group is True else group)
+
+
+def _all_reduce_sums(scratch, group):
+    import torch.distributed as dist
+    dist.all_reduce(scratch, op=dist.ReduceOp.SUM, group=None if group is True else group)
+
+
 class NormActFn(torch.autograd.Function):
     """leaky_relu(norm(x)) [+ residual] on rows x [groups, rows, C].
 
     groups == 1: BatchNorm2d in training mode (batch statistics; running stats updated in place)
     groups == B: InstanceNorm2d(affine=False).  With `use_running` the running statistics are
-    used instead (eval-mode BatchNorm)."""
+    used instead (eval-mode BatchNorm).
+    `sync_group` (groups == 1 only): SyncBatchNorm -- the fp64 channel sums (and the row count riding behind them) are
+    all-reduced over the ranks between the two phases of the statistics and of the backward
+    (nn.SyncBatchNorm semantics: SPConvNets/trainer_unsup_arti_align.py:430 converts every BatchNorm)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, momentum, eps, slope, use_running):
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, momentum, eps, slope, use_running, sync_group=None):
         x = _f32(x)
         g, rows, c = x.shape
         dev = x.device
         stats = torch.empty((g, 2, c), dtype=torch.float32, device=dev)
+        sync = (not use_running) and g == 1 and _sync_world(sync_group) > 1
+        rm = ptr(running_mean) if running_mean is not None else None
+        rv = ptr(running_var) if running_var is not None else None
         if use_running:
             stats[:, 0] = running_mean
             stats[:, 1] = torch.rsqrt(running_var + eps)
+        elif sync:
+            scratch = torch.empty(2 * c + 1, dtype=torch.float64, device=dev)
+            scratch[2 * c:].fill_(float(rows))
+            call("vgtkb_norm_sums", dev, 1, rows, c, ptr(x), ptr(scratch))
+            _all_reduce_sums(scratch, sync_group)
+            call("vgtkb_norm_finalize", dev, 1, 0, c, float(eps), ptr(scratch), ptr(stats), rm, rv, float(momentum))
         else:
             scratch = torch.empty((g, 2, c), dtype=torch.float64, device=dev)
-            call("vgtkb_norm_stats", dev, g, rows, c, ptr(x), float(eps), ptr(scratch), ptr(stats),
-                 ptr(running_mean) if running_mean is not None else None,
-                 ptr(running_var) if running_var is not None else None, float(momentum))
+            call("vgtkb_norm_stats", dev, g, rows, c, ptr(x), float(eps), ptr(scratch), ptr(stats), rm, rv, float(momentum))
         y = torch.empty_like(x)
         gam = gamma.contiguous() if gamma is not None else None
         bet = beta.contiguous() if beta is not None else None
@@ -378,29 +404,38 @@ class NormActFn(torch.autograd.Function):
         call("vgtkb_norm_act_forward", dev, g, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), float(slope), ptr(res),
              ptr(y))
         ctx.save_for_backward(x, stats, gam, bet)
-        ctx.meta = (g, rows, c, float(slope), use_running, residual is not None)
+        ctx.meta = (g, rows, c, float(slope), use_running, residual is not None, sync_group if sync else None)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, stats, gam, bet = ctx.saved_tensors
-        g, rows, c, slope, use_running, has_res = ctx.meta
+        g, rows, c, slope, use_running, has_res, sync_group = ctx.meta
         if use_running:
             raise NotImplementedError("backward through eval-mode BatchNorm is not part of the hot path")
         gy = _f32(gy)
         dev = gy.device
-        scratch = torch.empty((g, 2, c), dtype=torch.float64, device=dev)
         gx = torch.empty_like(x)
         ggam = torch.empty(c, dtype=torch.float32, device=dev) if gam is not None else None
         gbet = torch.empty(c, dtype=torch.float32, device=dev) if bet is not None else None
-        call("vgtkb_norm_act_backward", dev, g, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), slope, ptr(gy),
-             ptr(scratch), ptr(gx), ptr(ggam), ptr(gbet))
-        return gx, ggam, gbet, (gy if has_res else None), None, None, None, None, None, None
+        if sync_group is not None:
+            scratch = torch.empty(2 * c + 1, dtype=torch.float64, device=dev)
+            scratch[2 * c:].fill_(float(rows))
+            call("vgtkb_norm_bwd_sums", dev, 1, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), slope, ptr(gy),
+                 ptr(scratch), ptr(ggam), ptr(gbet))       # affine gradients: local sums, reduced with the other parameters
+            _all_reduce_sums(scratch, sync_group)
+            call("vgtkb_norm_bwd_apply", dev, 1, rows, 0, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), slope, ptr(gy),
+                 ptr(scratch), ptr(gx))
+        else:
+            scratch = torch.empty((g, 2, c), dtype=torch.float64, device=dev)
+            call("vgtkb_norm_act_backward", dev, g, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), slope, ptr(gy),
+                 ptr(scratch), ptr(gx), ptr(ggam), ptr(gbet))
+        return gx, ggam, gbet, (gy if has_res else None), None, None, None, None, None, None, None
 
 
 def norm_act(x, gamma=None, beta=None, residual=None, running_mean=None, running_var=None, momentum=0.1, eps=1e-5,
-             slope=LEAKY_SLOPE, use_running=False):
-    return NormActFn.apply(x, gamma, beta, residual, running_mean, running_var, momentum, eps, slope, use_running)
+             slope=LEAKY_SLOPE, use_running=False, sync_group=None):
+    return NormActFn.apply(x, gamma, beta, residual, running_mean, running_var, momentum, eps, slope, use_running, sync_group)
 
 
 class ChamferFn(torch.autograd.Function):

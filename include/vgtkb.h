@@ -192,6 +192,22 @@ int vgtkb_norm_act_backward(int groups, int64_t rows_per_group, int c, const flo
                             const float* gamma, const float* beta, float slope, const float* grad_y,
                             double* scratch, float* grad_x, float* grad_gamma, float* grad_beta, void* stream);
 
+/* The same two operations in two phases each, for SyncBatchNorm across data-parallel ranks (the reference converts its
+ * BatchNorm layers with nn.SyncBatchNorm.convert_sync_batchnorm, SPConvNets/trainer_unsup_arti_align.py:430): the caller
+ * all-reduces `scratch` (fp64 sums) between the phases and passes the global row count as total_rows.
+ *   vgtkb_norm_stats        == vgtkb_norm_sums     + vgtkb_norm_finalize(total_rows = rows)
+ *   vgtkb_norm_act_backward == vgtkb_norm_bwd_sums + vgtkb_norm_bwd_apply(total_rows = rows)
+ * grad_gamma / grad_beta of bwd_sums are the LOCAL sums (reduced with the other parameter gradients). */
+int vgtkb_norm_sums(int groups, int64_t rows_per_group, int c, const float* x, double* scratch, void* stream);
+int vgtkb_norm_finalize(int groups, int64_t total_rows, int c, float eps, const double* scratch, float* stats,
+                        float* running_mean, float* running_var, float momentum, void* stream);
+int vgtkb_norm_bwd_sums(int groups, int64_t rows_per_group, int c, const float* x, const float* stats, const float* gamma,
+                        const float* beta, float slope, const float* grad_y, double* scratch, float* grad_gamma,
+                        float* grad_beta, void* stream);
+int vgtkb_norm_bwd_apply(int groups, int64_t rows_per_group, int64_t total_rows, int c, const float* x, const float* stats,
+                         const float* gamma, const float* beta, float slope, const float* grad_y, const double* scratch,
+                         float* grad_x, void* stream);
+
 /* column sums of a row-major [rows, c] matrix (bias gradient of the skip conv) */
 int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream);
 

@@ -74,3 +74,73 @@ def test_flat_bucket_allreduce_matches_full_batch():
     for rank, flat, views in got:
         assert torch.allclose(flat, want, atol=1e-6), rank
         assert all(views), "gradients must stay views of the flat bucket"
+
+
+# ---------------------------------------------------------------------------------- SyncBatchNorm protocol
+def _syncbn_worker(rank, world, port, q):
+    """The two-phase SyncBatchNorm protocol of ops.NormActFn (sums -> all-reduce of [2C sums | row count] -> finalize /
+    apply), with the four C-ABI phases restated in torch fp64 on the CPU; unequal shards exercise the count that rides
+    behind the sums."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dp.init_from_env(backend="gloo")
+    from equi_articulated_pose_b200 import ops
+    assert ops._sync_world(True) == world and ops._sync_world(None) == 1
+    g = torch.Generator().manual_seed(7)
+    c, slope, eps = 6, 0.01, 1e-5
+    x_all = torch.randn(8, c, generator=g, dtype=torch.float64) * 2 + 0.5
+    gy_all = torch.randn(8, c, generator=g, dtype=torch.float64)
+    gamma = torch.rand(c, generator=g, dtype=torch.float64) + 0.5
+    beta = torch.randn(c, generator=g, dtype=torch.float64) * 0.1
+    lo, hi = (0, 5) if rank == 0 else (5, 8)
+    x, gy = x_all[lo:hi], gy_all[lo:hi]
+    rows = x.shape[0]
+    # vgtkb_norm_sums
+    scratch = torch.cat([x.sum(0), (x * x).sum(0), torch.tensor([float(rows)], dtype=torch.float64)])
+    ops._all_reduce_sums(scratch, True)
+    # vgtkb_norm_finalize (total_rows = 0: count from the buffer)
+    n = scratch[2 * c]
+    mean = scratch[:c] / n
+    inv = torch.rsqrt((scratch[c:2 * c] / n - mean * mean).clamp_min(0) + eps)
+    xh = (x - mean) * inv
+    pre = xh * gamma + beta
+    y = torch.where(pre > 0, pre, pre * slope)
+    # vgtkb_norm_bwd_sums (affine gradients = local sums)
+    dyp = torch.where(pre > 0, gy, gy * slope)
+    s = torch.cat([dyp.sum(0), (dyp * xh).sum(0), torch.tensor([float(rows)], dtype=torch.float64)])
+    gbeta, ggamma = s[:c].clone(), s[c:2 * c].clone()
+    ops._all_reduce_sums(s, True)
+    # vgtkb_norm_bwd_apply
+    gx = gamma * inv * (dyp - s[:c] / s[2 * c] - xh * s[c:2 * c] / s[2 * c])
+    q.put((rank, lo, hi, y, gx, ggamma, gbeta, float(n)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_syncbn_protocol_matches_full_batch_batchnorm():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_syncbn_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(7)
+    c, slope, eps = 6, 0.01, 1e-5
+    x_all = (torch.randn(8, c, generator=g, dtype=torch.float64) * 2 + 0.5).requires_grad_(True)
+    gy_all = torch.randn(8, c, generator=g, dtype=torch.float64)
+    gamma = (torch.rand(c, generator=g, dtype=torch.float64) + 0.5).requires_grad_(True)
+    beta = (torch.randn(c, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True)
+    y_ref = torch.nn.functional.leaky_relu(
+        torch.nn.functional.batch_norm(x_all, None, None, gamma, beta, training=True, eps=eps), slope)
+    y_ref.backward(gy_all)
+    y = torch.cat([r[3] for r in res])
+    gx = torch.cat([r[4] for r in res])
+    assert res[0][7] == 8.0 and res[1][7] == 8.0
+    assert torch.allclose(y, y_ref.detach(), atol=1e-12)
+    assert torch.allclose(gx, x_all.grad, atol=1e-12)
+    assert torch.allclose(res[0][5] + res[1][5], gamma.grad, atol=1e-12)      # local sums add up to the global gradient
+    assert torch.allclose(res[0][6] + res[1][6], beta.grad, atol=1e-12)
