@@ -12,6 +12,7 @@ The reference's own, unmodified base_so3conv.py also runs on top of the `vgtk` m
 package (module-level drop-in); this file is the faster block-level path the benchmark uses.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -82,13 +83,25 @@ class FusedInstanceNorm2d(nn.InstanceNorm2d):
         return _ops.norm_act(rows.view(batch, m // batch, c), None, None, res, None, None, 0.1, self.eps, slope).view(m, c)
 
 
-def convert_sync_batchnorm(module, process_group=None):
+def convert_sync_batchnorm(module, process_group=None, peer_memory=True):
     """Counterpart of nn.SyncBatchNorm.convert_sync_batchnorm (the reference trainer applies it to the whole model,
     SPConvNets/trainer_unsup_arti_align.py:430): every fused BatchNorm of `module` takes its statistics over all ranks of
-    `process_group` (None = the default group).  InstanceNorm layers are per-sample and stay local."""
+    `process_group` (None = the default group).  InstanceNorm layers are per-sample and stay local.
+    peer_memory: exchange the sums through NVLink peer mailboxes (one node; csrc/peer.cu) when they can be set up on
+    every rank, NCCL all-reduces otherwise.  Collective: call it on all ranks."""
+    import torch.distributed as dist
     for m in module.modules():
         if isinstance(m, FusedBatchNorm2d):
             m.sync_group = True if process_group is None else process_group
+    if peer_memory and dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1 \
+            and dist.get_backend(process_group) == "nccl" and _ops._PEER_MAILBOX is None \
+            and os.environ.get("VGTKB_PEER_SYNCBN", "1") != "0":
+        from . import dataparallel as _dp
+        dev = next(module.parameters()).device
+        try:
+            _ops.set_peer_mailbox(_dp.PeerMailbox(dev, process_group))
+        except RuntimeError:
+            _ops.set_peer_mailbox(None)              # every rank raised (agreed outcome): NCCL path
     return module
 
 

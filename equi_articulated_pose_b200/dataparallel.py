@@ -79,3 +79,81 @@ class FlatGradBucket:
 
     def nbytes(self):
         return self.flat.numel() * 4
+
+
+class PeerMailbox:
+    """SyncBatchNorm exchanges over NVLink peer memory (csrc/peer.cu) instead of NCCL all-reduces.
+
+    Every rank cudaMallocs a mailbox, the IPC handles are exchanged once over the process group, every rank maps its
+    peers' mailboxes; after that an exchange is one single-CTA kernel (stores into the peers' HBM + flags).
+    Construction is collective and returns a usable object on ALL ranks or raises on all of them (the outcome is
+    agreed with one all-reduce), so callers can fall back to NCCL consistently."""
+
+    def __init__(self, device, group=None):
+        import ctypes
+        from . import lib
+        self.device, self.group = device, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.seq = 0
+        self._own, self._opened = None, []
+        ok, err = 1, ""
+        handle = bytes(64)
+        try:
+            nbytes = ctypes.c_int64(0)
+            lib.setup_call("vgtkb_peer_mailbox_bytes", device, self.world, ctypes.byref(nbytes))
+            own = ctypes.c_void_p(0)
+            hbuf = ctypes.create_string_buffer(64)
+            lib.setup_call("vgtkb_peer_alloc", device, nbytes.value, ctypes.byref(own), ctypes.cast(hbuf, ctypes.c_void_p))
+            self._own, handle = own.value, hbuf.raw
+        except Exception as e:                      # agreed below
+            ok, err = 0, str(e)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (ok, handle), group=group)
+        ptrs = [None] * self.world
+        if all(h[0] for h in handles):
+            try:
+                for r, (_, h) in enumerate(handles):
+                    if r == self.rank:
+                        ptrs[r] = self._own
+                    else:
+                        q = ctypes.c_void_p(0)
+                        hb = ctypes.create_string_buffer(h, 64)
+                        lib.setup_call("vgtkb_peer_open", device, ctypes.cast(hb, ctypes.c_void_p), ctypes.byref(q))
+                        ptrs[r] = q.value
+                        self._opened.append(q.value)
+            except Exception as e:
+                ok, err = 0, str(e)
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device if dist.get_backend(group) == "nccl" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self.close()
+            raise RuntimeError(f"peer mailboxes unavailable on at least one rank ({err or 'another rank failed'})")
+        self.ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        dist.barrier(group=group)
+
+    def next_seq(self):
+        self.seq += 1
+        return self.seq
+
+    def all_reduce_sums(self, buf):
+        """buf (fp64, <= 2049 elements) <- sum over ranks, in place, on the current stream."""
+        from . import lib
+        lib.call("vgtkb_peer_allreduce_f64", self.device, buf.numel(), lib.ptr(buf), self.rank, self.world, self.ptrs,
+                 self.next_seq())
+
+    def close(self):
+        from . import lib
+        for q in self._opened:
+            try:
+                lib.setup_call("vgtkb_peer_close", self.device, q)
+            except Exception:
+                pass
+        self._opened = []
+        if self._own:
+            try:
+                lib.setup_call("vgtkb_peer_free", self.device, self._own)
+            except Exception:
+                pass
+            self._own = None

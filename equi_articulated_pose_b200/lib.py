@@ -51,6 +51,16 @@ SIGNATURES = {
     "vgtkb_norm_act_forward": [c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
     "vgtkb_norm_act_backward": [c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_col_sum": [c_i64, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_peer_allreduce_f64": [c_int, c_vp, c_int, c_int, c_vp, ctypes.c_uint64, c_vp],
+    "vgtkb_norm_finalize_peer": [c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_int, c_vp, ctypes.c_uint64, c_vp],
+}
+# entry points without a stream argument (setup of the peer mailboxes); status int like the others
+SETUP_SIGNATURES = {
+    "vgtkb_peer_mailbox_bytes": [c_int, ctypes.POINTER(c_i64)],
+    "vgtkb_peer_alloc": [c_i64, ctypes.POINTER(c_vp), c_vp],
+    "vgtkb_peer_open": [c_vp, ctypes.POINTER(c_vp)],
+    "vgtkb_peer_close": [c_vp],
+    "vgtkb_peer_free": [c_vp],
 }
 NO_STATUS = {"vgtkb_last_error": (ctypes.c_char_p, []), "vgtkb_version": (c_int, []),
              "vgtkb_device_check": (c_int, [])}
@@ -72,7 +82,7 @@ def load():
     for name, (res, args) in NO_STATUS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    for name, args in SIGNATURES.items():
+    for name, args in list(SIGNATURES.items()) + list(SETUP_SIGNATURES.items()):
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = c_int, args
     if lib.vgtkb_version() != ABI_VERSION:
@@ -89,6 +99,17 @@ def _ensure_device(dev_index):
         if lib.vgtkb_device_check() != 0:
             raise VgtkbError(lib.vgtkb_last_error().decode())
     _device_ok.add(dev_index)
+
+
+def setup_call(name, device, *args):
+    """Invoke a stream-less setup entry point with `device` current; raise on a non-zero status."""
+    lib = load()
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    _ensure_device(idx)
+    with torch.cuda.device(idx):
+        rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise VgtkbError(f"{name} failed ({rc}): {lib.vgtkb_last_error().decode()}")
 
 
 def ptr(t):

@@ -361,7 +361,18 @@ def _sync_world(group):
     return dist.get_world_size(None if group is True else group)
 
 
+_PEER_MAILBOX = None     # dataparallel.PeerMailbox: SyncBatchNorm exchanges over NVLink peer memory instead of NCCL
+
+
+def set_peer_mailbox(mailbox):
+    global _PEER_MAILBOX
+    _PEER_MAILBOX = mailbox
+
+
 def _all_reduce_sums(scratch, group):
+    if _PEER_MAILBOX is not None and scratch.is_cuda:
+        _PEER_MAILBOX.all_reduce_sums(scratch)
+        return
     import torch.distributed as dist
     dist.all_reduce(scratch, op=dist.ReduceOp.SUM, group=None if group is True else group)
 
@@ -392,8 +403,13 @@ class NormActFn(torch.autograd.Function):
             scratch = torch.empty(2 * c + 1, dtype=torch.float64, device=dev)
             scratch[2 * c:].fill_(float(rows))
             call("vgtkb_norm_sums", dev, 1, rows, c, ptr(x), ptr(scratch))
-            _all_reduce_sums(scratch, sync_group)
-            call("vgtkb_norm_finalize", dev, 1, 0, c, float(eps), ptr(scratch), ptr(stats), rm, rv, float(momentum))
+            mb = _PEER_MAILBOX
+            if mb is not None:      # exchange + finalize in one kernel over peer memory
+                call("vgtkb_norm_finalize_peer", dev, c, float(eps), ptr(scratch), ptr(stats), rm, rv, float(momentum),
+                     mb.rank, mb.world, mb.ptrs, mb.next_seq())
+            else:
+                _all_reduce_sums(scratch, sync_group)
+                call("vgtkb_norm_finalize", dev, 1, 0, c, float(eps), ptr(scratch), ptr(stats), rm, rv, float(momentum))
         else:
             scratch = torch.empty((g, 2, c), dtype=torch.float64, device=dev)
             call("vgtkb_norm_stats", dev, g, rows, c, ptr(x), float(eps), ptr(scratch), ptr(stats), rm, rv, float(momentum))

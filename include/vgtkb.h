@@ -208,6 +208,25 @@ int vgtkb_norm_bwd_apply(int groups, int64_t rows_per_group, int64_t total_rows,
                          const float* gamma, const float* beta, float slope, const float* grad_y, const double* scratch,
                          float* grad_x, void* stream);
 
+/* SyncBatchNorm exchange over NVLink peer memory instead of an NCCL all-reduce (csrc/peer.cu): every rank owns a
+ * mailbox in its HBM that its peers (other processes of the node, cudaIpc-mapped) store their fp64 sums into.
+ *   vgtkb_peer_mailbox_bytes: size of one mailbox for `world` ranks (<= 16)
+ *   vgtkb_peer_alloc:  cudaMalloc + zero a mailbox on the current device, export its IPC handle (64 bytes)
+ *   vgtkb_peer_open / vgtkb_peer_close: map / unmap a peer's mailbox from its handle;  vgtkb_peer_free: own mailbox
+ *   vgtkb_peer_allreduce_f64: buf[0..n) <- sum over ranks, n <= 2049; one single-CTA kernel; `mailboxes` = HOST array of
+ *       `world` device pointers (entry `rank` = own mailbox); `seq` = 1, 2, 3, ... identical on all ranks per call
+ *   vgtkb_norm_finalize_peer: the exchange of scratch [2c sums | row count] fused with vgtkb_norm_finalize (groups = 1)
+ * Every rank must issue the same sequence of exchanges; a peer that does not show up within 30 s traps the kernel. */
+#define VGTKB_IPC_HANDLE_BYTES 64
+int vgtkb_peer_mailbox_bytes(int world, int64_t* bytes);
+int vgtkb_peer_alloc(int64_t bytes, void** dev_ptr, void* ipc_handle);
+int vgtkb_peer_open(const void* ipc_handle, void** dev_ptr);
+int vgtkb_peer_close(void* dev_ptr);
+int vgtkb_peer_free(void* dev_ptr);
+int vgtkb_peer_allreduce_f64(int n, double* buf, int rank, int world, void* const* mailboxes, uint64_t seq, void* stream);
+int vgtkb_norm_finalize_peer(int c, float eps, double* scratch, float* stats, float* running_mean, float* running_var,
+                             float momentum, int rank, int world, void* const* mailboxes, uint64_t seq, void* stream);
+
 /* column sums of a row-major [rows, c] matrix (bias gradient of the skip conv) */
 int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream);
 

@@ -31,7 +31,7 @@ def _build(dev, n_points):
     return net.to(dev).train()
 
 
-def _worker(rank, world, port, n_points, q):
+def _worker(rank, world, port, n_points, peer, q):
     import torch.distributed as dist
     from equi_articulated_pose_b200 import blocks, ops, dataparallel as dp
     from oracle import so3 as O
@@ -39,6 +39,18 @@ def _worker(rank, world, port, n_points, q):
                       LOCAL_RANK=str(rank))
     dp.init_from_env(backend="nccl")
     dev = torch.device("cuda", rank)
+    peer_ok = None
+    if peer:
+        # NVLink peer mailboxes: 300 back-to-back exchanges of varying length (slot reuse), rank-order sums
+        mb = dp.PeerMailbox(dev)
+        ops.set_peer_mailbox(mb)
+        peer_ok = True
+        for i in range(300):
+            n = 1 + (i * 37) % 2049
+            buf = (torch.arange(n, dtype=torch.float64, device=dev) + 1) * (rank + 1) * (i + 1)
+            mb.all_reduce_sums(buf)
+            want = (torch.arange(n, dtype=torch.float64, device=dev) + 1) * (i + 1) * (world * (world + 1) // 2)
+            peer_ok = peer_ok and bool(torch.equal(buf, want))
     clouds = O.synthetic_cloud(2 * world, n_points, 4321)
     lo, hi = dp.shard_range(2 * world, rank, world)
 
@@ -57,7 +69,8 @@ def _worker(rank, world, port, n_points, q):
     norm_out = (y.detach().cpu(), x.grad.cpu(), ga.grad.cpu(), be.grad.cpu(), rm.cpu(), rv.cpu())
 
     net = _build(dev, n_points)
-    blocks.convert_sync_batchnorm(net)
+    blocks.convert_sync_batchnorm(net, peer_memory=peer)
+    assert (ops._PEER_MAILBOX is not None) == bool(peer)
     bucket = dp.FlatGradBucket(net.parameters())
     bucket.zero_()
     out = net(clouds[lo:hi].to(dev))
@@ -65,20 +78,21 @@ def _worker(rank, world, port, n_points, q):
     loss.backward()
     bucket.all_reduce_mean()
     torch.cuda.synchronize()
-    q.put((rank, out.feats.detach().cpu(), float(loss), bucket.flat.cpu(), norm_out))
+    q.put((rank, out.feats.detach().cpu(), float(loss), bucket.flat.cpu(), norm_out, peer_ok))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 CUDA devices")
-def test_two_rank_syncbn_matches_single_process():
+@pytest.mark.parametrize("peer", [False, True], ids=["nccl", "peer_memory"])
+def test_two_rank_syncbn_matches_single_process(peer):
     import torch.multiprocessing as mp
     from equi_articulated_pose_b200 import ops, dataparallel as dp
     from oracle import so3 as O
     world, n_points, port = 2, 256, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_points, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_points, peer, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
@@ -86,6 +100,8 @@ def test_two_rank_syncbn_matches_single_process():
         p.join(timeout=120)
         assert p.exitcode == 0
 
+    if peer:
+        assert res[0][5] is True and res[1][5] is True
     dev = torch.device("cuda", 0)
     # ---- norm_act: full batch on one device
     g = torch.Generator().manual_seed(5)
