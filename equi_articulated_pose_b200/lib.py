@@ -25,6 +25,8 @@ SIGNATURES = {
     "vgtkb_gather_points_backward": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_chamfer_forward": [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_chamfer_backward": [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_anchor_chamfer_forward": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_anchor_chamfer_backward": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_inter_weights": [c_int] * 6 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp],
     "vgtkb_inter_group_forward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
     "vgtkb_inter_group_backward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
@@ -148,5 +150,5 @@ COUNTERS = {"launch_calls": 0, "kernels": 0}
 PROFILE = None  # set to a list to record (entry point, args, start event, end event) per call
 # device kernels launched per entry point (memsets not counted); used for bench.py's gpu_launches
 KERNELS_PER_CALL = {"vgtkb_gemm_nt": 2, "vgtkb_gemm_tn": 2, "vgtkb_gather_gemm_nt": 2, "vgtkb_gather_gemm_tn": 2,
-                    "vgtkb_chamfer_forward": 2, "vgtkb_chamfer_backward": 4, "vgtkb_norm_stats": 2,
+                    "vgtkb_chamfer_forward": 2, "vgtkb_chamfer_backward": 4, "vgtkb_anchor_chamfer_forward": 2, "vgtkb_anchor_chamfer_backward": 2, "vgtkb_norm_stats": 2,
                     "vgtkb_norm_act_backward": 3, "vgtkb_norm_bwd_sums": 2, "vgtkb_col_sum": 2}

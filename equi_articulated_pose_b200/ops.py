@@ -454,6 +454,48 @@ def norm_act(x, gamma=None, beta=None, residual=None, running_mean=None, running
     return NormActFn.apply(x, gamma, beta, residual, running_mean, running_var, momentum, eps, slope, use_running, sync_group)
 
 
+class AnchorChamferFn(torch.autograd.Function):
+    """Chamfer terms of A rigidly transformed copies of a reconstruction against one input cloud, fused
+    (SPConvNets/models/unsup_seg_so3_pose_conv_pn_38_multi_stage.py:429-436):
+        Y[b,a] = rot[b,a] canon[b] + trans[b,a];  dist1 [B,A,M] = Y -> ori,  dist2 [B,A,N] = ori -> Y.
+    canon [B,M,3], rot [B,A,3,3], trans [B,A,3], ori [B,N,3]."""
+
+    @staticmethod
+    def forward(ctx, canon, rot, trans, ori):
+        canon, rot, trans, ori = _f32(canon), _f32(rot), _f32(trans), _f32(ori)
+        b, m, _ = canon.shape
+        a, n, dev = rot.shape[1], ori.shape[1], canon.device
+        d1 = torch.empty((b, a, m), dtype=torch.float32, device=dev)
+        d2 = torch.empty((b, a, n), dtype=torch.float32, device=dev)
+        i1 = torch.empty((b, a, m), dtype=torch.int32, device=dev)
+        i2 = torch.empty((b, a, n), dtype=torch.int32, device=dev)
+        call("vgtkb_anchor_chamfer_forward", dev, b, a, m, ptr(canon), ptr(rot), ptr(trans), n, ptr(ori), ptr(d1), ptr(d2),
+             ptr(i1), ptr(i2))
+        ctx.save_for_backward(canon, rot, trans, ori, i1, i2)
+        ctx.mark_non_differentiable(i1, i2)
+        return d1, d2, i1, i2
+
+    @staticmethod
+    def backward(ctx, g1, g2, _gi1, _gi2):
+        canon, rot, trans, ori, i1, i2 = ctx.saved_tensors
+        b, m, _ = canon.shape
+        a, n, dev = rot.shape[1], ori.shape[1], canon.device
+        gy = torch.empty((b, a, m, 3), dtype=torch.float32, device=dev)
+        gori = torch.empty_like(ori) if ctx.needs_input_grad[3] else None
+        call("vgtkb_anchor_chamfer_backward", dev, b, a, m, ptr(canon), ptr(rot), ptr(trans), n, ptr(ori), ptr(i1), ptr(i2),
+             ptr(_f32(g1)), ptr(_f32(g2)), ptr(gy), ptr(gori))
+        # fold dL/dY into the pose and the canonical points (B*A*M*3 values: tiny next to the matching)
+        g_rot = torch.einsum('bamj,bmk->bajk', gy, canon) if ctx.needs_input_grad[1] else None
+        g_trans = gy.sum(2) if ctx.needs_input_grad[2] else None
+        g_canon = torch.einsum('bajk,bamj->bmk', rot, gy) if ctx.needs_input_grad[0] else None
+        return g_canon, g_rot, g_trans, gori
+
+
+def anchor_chamfer(canon, rot, trans, ori):
+    """-> dist1 [B,A,M] (transformed reconstruction -> input), dist2 [B,A,N] (input -> reconstruction), idx1, idx2."""
+    return AnchorChamferFn.apply(canon, rot, trans, ori)
+
+
 class ChamferFn(torch.autograd.Function):
     """extensions/chamfer_dist/__init__.py:13-26 (ChamferFunction)."""
 

@@ -72,6 +72,17 @@ int vgtkb_chamfer_backward(int b, int n, const float* xyz1, int m, const float* 
                            const float* grad_dist1, const float* grad_dist2,
                            float* grad_xyz1, float* grad_xyz2, void* stream);
 
+/* Anchor chamfer: the reconstruction loss of model 38 (SPConvNets/models/unsup_seg_so3_pose_conv_pn_38_multi_stage.py:
+ * 429-436) without its [B,A,M,3] transformed tensor and its A-fold replicated input cloud.
+ *   Y[b,a,i] = rot[b,a] canon[b,i] + trans[b,a];  dist1/idx1 [b,a,m]: Y -> ori[b];  dist2/idx2 [b,a,n]: ori[b] -> Y[b,a]
+ * canon [b,m,3], rot [b,a,3,3] row-major, trans [b,a,3], ori [b,n,3].  Backward: grad_y [b,a,m,3] (gradient w.r.t. the
+ * transformed points; the caller folds it into rot / trans / canon) and grad_ori [b,n,3] (may be NULL). */
+int vgtkb_anchor_chamfer_forward(int b, int a, int m, const float* canon, const float* rot, const float* trans, int n,
+                                 const float* ori, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, void* stream);
+int vgtkb_anchor_chamfer_backward(int b, int a, int m, const float* canon, const float* rot, const float* trans, int n,
+                                  const float* ori, const int32_t* idx1, const int32_t* idx2, const float* grad_dist1,
+                                  const float* grad_dist2, float* grad_y, float* grad_ori, void* stream);
+
 /* ---------------------------------------------------------------- fused SO(3) conv path ---- */
 
 /* Kernel-point correlation, materialised (API parity only; the fused path never stores it):

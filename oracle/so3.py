@@ -250,3 +250,24 @@ def synthetic_cloud(batch, n, seed):
     d = d / d.norm(dim=2, keepdim=True)
     r = 0.85 + 0.15 * torch.rand(batch, n, 1, generator=g)
     return (d * r).float()
+
+
+def anchor_orbit_chamfer(canon, rot, trans, ori, glb_single_cd=0):
+    """Model 38's anchor-orbit reconstruction loss, the reference way
+    (SPConvNets/models/unsup_seg_so3_pose_conv_pn_38_multi_stage.py:429-450): transform the reconstruction by every
+    anchor pose, replicate the input cloud A times, chamfer on [B*A, ., 3], mean over points, min over anchors.
+
+    canon [B,3,M], rot [B,A,3,3], trans [B,A,3], ori [B,3,N]  (the reference's layouts)
+    -> dict(d1 [B,A,M], d2 [B,A,N], i1, i2, cd_r2o [B,A], cd_o2r [B,A], minn [B], orbit [B])"""
+    bz, na = rot.shape[0], rot.shape[1]
+    m, n = canon.shape[2], ori.shape[2]
+    transformed = torch.matmul(rot, canon.unsqueeze(1)).transpose(-1, -2) + trans.unsqueeze(-2)       # :429-430
+    expanded = ori.transpose(-1, -2).unsqueeze(1).contiguous().repeat(1, na, 1, 1)                    # :431
+    d1, d2, i1, i2 = cops.chamfer_forward(transformed.contiguous().view(bz * na, m, 3).numpy(),
+                                          expanded.contiguous().view(bz * na, n, 3).numpy())          # :433-435
+    d1, d2 = torch.from_numpy(d1).view(bz, na, m), torch.from_numpy(d2).view(bz, na, n)
+    cd_r2o, cd_o2r = d1.mean(-1), d2.mean(-1)                                                         # :437-439
+    total = cd_o2r if glb_single_cd == 1 else cd_r2o + cd_o2r                                         # :443-446
+    minn, orbit = torch.min(total, dim=-1)                                                            # :449
+    return dict(d1=d1, d2=d2, i1=torch.from_numpy(i1).view(bz, na, m), i2=torch.from_numpy(i2).view(bz, na, n),
+                cd_r2o=cd_r2o, cd_o2r=cd_o2r, minn=minn, orbit=orbit, transformed=transformed)

@@ -581,3 +581,60 @@ def test_pose_conv_module_non_identity(dev):
     assert tuple(o_rot.feats.shape) == tuple(o_pl.feats.shape) and torch.isfinite(o_rot.feats).all()
     assert not torch.allclose(o_rot.feats, o_pl.feats)
     assert torch.equal(o_rot.pose, torch.from_numpy(g["pose"]).to(dev))
+
+
+# ------------------------------------------------------------------------------ anchor-orbit chamfer (model 38 loss)
+def _orbit_case(b, a, m, n, seed):
+    from oracle import so3 as O
+    from equi_articulated_pose_b200 import so3_constants as C
+    g = torch.Generator().manual_seed(seed)
+    anchors = torch.from_numpy(np.ascontiguousarray(C.get_anchors(60)))[:a].float()
+    # predicted rotation (random, orthonormalised) composed with the anchors, as the model builds glb_R
+    q, _ = torch.linalg.qr(torch.randn(b, 3, 3, generator=g))
+    rot = torch.matmul(q.unsqueeze(1), anchors.unsqueeze(0)).contiguous()
+    trans = (torch.randn(b, a, 3, generator=g) * 0.05).contiguous()
+    ori = O.synthetic_cloud(b, n, seed).permute(0, 2, 1).contiguous() * 0.5             # [B,3,N]
+    canon = (torch.randn(b, 3, m, generator=g) * 0.3).contiguous()
+    return canon, rot, trans, ori
+
+
+@pytest.mark.parametrize("b,a,m,n", [(2, 60, 256, 512), (1, 7, 100, 3000), (3, 20, 513, 64)])
+def test_anchor_chamfer_matches_unfused_reference_path(dev, ops, b, a, m, n):
+    from oracle import so3 as O
+    canon, rot, trans, ori = _orbit_case(b, a, m, n, 77 + m)
+    want = O.anchor_orbit_chamfer(canon, rot, trans, ori)
+    d1, d2, i1, i2 = ops.anchor_chamfer(canon.transpose(1, 2).contiguous().to(dev), rot.to(dev), trans.to(dev),
+                                        ori.transpose(1, 2).contiguous().to(dev))
+    # the transformed points differ from torch.matmul's by rounding only; the matching is the pinned chamfer kernel's
+    for got, ref, gi, ri in ((d1, want["d1"], i1, want["i1"]), (d2, want["d2"], i2, want["i2"])):
+        got, gi = got.cpu(), gi.cpu()
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-7)
+        assert float((gi != ri).float().mean()) < 1e-3                       # near-ties only
+    # unfused composition on the GPU through the bit-exact chamfer kernel: same transformed points -> identical
+    y = want["transformed"].contiguous().view(b * a, m, 3).to(dev)
+    e = ori.transpose(1, 2).unsqueeze(1).repeat(1, a, 1, 1).contiguous().view(b * a, n, 3).to(dev)
+    u1, u2, _, _ = ops.chamfer_forward(y, e)
+    assert rel_err(d1.view(b * a, m), u1) < 1e-5 and rel_err(d2.view(b * a, n), u2) < 1e-5
+    # module: per-anchor means, orbit minimum and its index (SPConvNets/models/...38...py:437-450)
+    import equi_articulated_pose_b200 as eap
+    eap.install()
+    from extensions.chamfer_dist import AnchorChamferDistance
+    minn, orbit, r2o, o2r = AnchorChamferDistance()(canon.to(dev), rot.to(dev), trans.to(dev), ori.to(dev))
+    assert rel_err(r2o, want["cd_r2o"]) < 1e-5 and rel_err(o2r, want["cd_o2r"]) < 1e-5
+    assert torch.equal(orbit.cpu(), want["orbit"]) and rel_err(minn, want["minn"]) < 1e-5
+
+
+def test_anchor_chamfer_gradients(dev, ops):
+    canon, rot, trans, ori = _orbit_case(2, 12, 96, 160, 5)
+    leaves = [t.to(dev).requires_grad_(True) for t in (canon.transpose(1, 2).contiguous(), rot, trans,
+                                                       ori.transpose(1, 2).contiguous())]
+    d1, d2, _, _ = ops.anchor_chamfer(*leaves)
+    g = torch.Generator().manual_seed(3)
+    w1, w2 = torch.rand(d1.shape, generator=g).to(dev), torch.rand(d2.shape, generator=g).to(dev)
+    ((d1 * w1).sum() + (d2 * w2).sum()).backward()
+    dl = [t.detach().double().requires_grad_(True) for t in leaves]
+    y = torch.einsum('bajk,bmk->bamj', dl[1], dl[0]) + dl[2].unsqueeze(2)
+    D = ((y[:, :, :, None] - dl[3][:, None, None]) ** 2).sum(-1)             # [B,A,M,N]
+    ((D.min(3)[0] * w1.double()).sum() + (D.min(2)[0] * w2.double()).sum()).backward()
+    for got, ref in zip(leaves, dl):
+        assert rel_err(got.grad, ref.grad) < 2e-5

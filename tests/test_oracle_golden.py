@@ -222,3 +222,23 @@ def test_pose_grouping_matches_reference(golden_dir):
     w = O.anchor_weights(gx, anchors, torch.from_numpy(g["kernels"]), float(g["sigma"]))
     assert torch.equal(pi0, torch.arange(60).view(1, 1, 1, 60).expand_as(pi0))
     assert torch.allclose(G0, O.inter_group_feats(idx, w, feats), atol=1e-6)
+
+
+def test_anchor_orbit_chamfer_oracle_vs_fp64_bruteforce():
+    """oracle.so3.anchor_orbit_chamfer (the unfused reference path of model 38's reconstruction loss, built on the pinned
+    chamfer restatement) against a float64 brute-force evaluation."""
+    from oracle import so3 as O
+    g = torch.Generator().manual_seed(0)
+    b, a, m, n = 2, 5, 40, 60
+    q, _ = torch.linalg.qr(torch.randn(b, a, 3, 3, generator=g))
+    canon, ori = torch.randn(b, 3, m, generator=g), torch.randn(b, 3, n, generator=g)
+    tr = torch.randn(b, a, 3, generator=g) * 0.1
+    r = O.anchor_orbit_chamfer(canon, q.contiguous(), tr, ori)
+    y = torch.einsum('bajk,bkm->bamj', q.double(), canon.double()) + tr.double().unsqueeze(2)
+    D = ((y[:, :, :, None] - ori.double().transpose(1, 2)[:, None, None]) ** 2).sum(-1)
+    assert float((D.min(3)[0] - r['d1']).abs().max()) < 1e-5 and float((D.min(2)[0] - r['d2']).abs().max()) < 1e-5
+    assert torch.equal(r['i1'].long(), D.min(3)[1]) and torch.equal(r['i2'].long(), D.min(2)[1])
+    total = D.min(3)[0].mean(-1) + D.min(2)[0].mean(-1)
+    assert torch.equal(r['orbit'], total.argmin(-1))
+    single = O.anchor_orbit_chamfer(canon, q.contiguous(), tr, ori, glb_single_cd=1)
+    assert torch.equal(single['orbit'], D.min(2)[0].mean(-1).argmin(-1))
