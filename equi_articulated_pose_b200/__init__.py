@@ -24,4 +24,7 @@ def install():
         mod = sys.modules.get(name)
         if mod is not None and not os.path.abspath(getattr(mod, "__file__", "") or "").startswith(_HERE):
             raise RuntimeError(f"another `{name}` is already imported from {getattr(mod, '__file__', None)}")
+    shims = os.path.join(_HERE, "shims")          # torch_cluster.fps on the new FPS kernel; a real installation wins
+    if shims not in sys.path:
+        sys.path.append(shims)
     return importlib.import_module("vgtk")

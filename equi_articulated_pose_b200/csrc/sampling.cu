@@ -121,7 +121,7 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 // bitrev(k mod bs) * iters + (k div bs); the smallest rank among equal distances wins.
 template <int PPT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-fps_kernel(int n, int m, int log2bs, int iters, const float* __restrict__ xyz, int32_t* __restrict__ idxs) {
+fps_kernel(int n, int m, int log2bs, int iters, int plain, const float* __restrict__ xyz, int32_t* __restrict__ idxs) {
     extern __shared__ __align__(16) float sp[];  // x[n] y[n] z[n]
     __shared__ unsigned long long red[2][THREADS / 32];
     const int b = blockIdx.x;
@@ -151,10 +151,11 @@ fps_kernel(int n, int m, int log2bs, int iters, const float* __restrict__ xyz, i
             py[i] = sy[k];
             pz[i] = sz[k];
             const float mag = sq3(px[i], py[i], pz[i]);
-            valid[i] = !((double)mag <= 1e-3);  // double literal in the reference (:386)
+            valid[i] = plain || !((double)mag <= 1e-3);  // double literal in the reference (:386)
             const uint32_t tr = (uint32_t)k & (uint32_t)(bs - 1);
             const uint32_t br = log2bs ? (__brev(tr) >> (32 - log2bs)) : 0u;
-            inv[i] = 0xffffffffu - (br * (uint32_t)iters + ((uint32_t)k >> log2bs));
+            // plain (torch_cluster-style) sampling: no skipped points, the lowest index wins ties
+            inv[i] = 0xffffffffu - (plain ? (uint32_t)k : br * (uint32_t)iters + ((uint32_t)k >> log2bs));
         }
     }
     int old = 0;
@@ -182,7 +183,7 @@ fps_kernel(int n, int m, int log2bs, int iters, const float* __restrict__ xyz, i
             const uint32_t rank = 0xffffffffu - (uint32_t)v;
             const uint32_t br = rank / (uint32_t)iters, it = rank % (uint32_t)iters;
             const uint32_t tr = log2bs ? (__brev(br) >> (32 - log2bs)) : 0u;
-            old = (int)(it * (uint32_t)bs + tr);
+            old = plain ? (int)rank : (int)(it * (uint32_t)bs + tr);
         } else {
             old = 0;  // every point skipped: the reference's tree returns besti = 0
         }
@@ -260,15 +261,15 @@ extern "C" int vgtkb_ball_query(int b, int n, int m, float radius, int nsample, 
 }
 
 template <int PPT, int THREADS>
-static int launch_fps(int b, int n, int m, int log2bs, int iters, const float* xyz, int32_t* idx, cudaStream_t st) {
+static int launch_fps(int b, int n, int m, int log2bs, int iters, int plain, const float* xyz, int32_t* idx, cudaStream_t st) {
     const size_t smem = (size_t)n * 12;
     auto kern = fps_kernel<PPT, THREADS>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    kern<<<b, THREADS, smem, st>>>(n, m, log2bs, iters, xyz, idx);
+    kern<<<b, THREADS, smem, st>>>(n, m, log2bs, iters, plain, xyz, idx);
     return check_launch("furthest_point_sampling");
 }
 
-extern "C" int vgtkb_furthest_point_sampling(int b, int n, int m, const float* xyz, int32_t* idx, void* stream) {
+static int fps_dispatch(int b, int n, int m, int plain, const float* xyz, int32_t* idx, void* stream) {
     VGTKB_REQUIRE(b >= 0 && n >= 0 && m >= 0, "fps: negative size");
     if (b == 0 || m <= 0) return VGTKB_OK;
     VGTKB_REQUIRE(n >= 1, "fps: empty cloud");
@@ -279,12 +280,22 @@ extern "C" int vgtkb_furthest_point_sampling(int b, int n, int m, const float* x
     while ((2 << log2bs) <= n && log2bs < 10) ++log2bs;
     const int bs = 1 << log2bs;
     const int iters = (n + bs - 1) / bs;
-    if (n <= 512) return launch_fps<1, 512>(b, n, m, log2bs, iters, xyz, idx, st);
-    if (n <= 1024) return launch_fps<2, 512>(b, n, m, log2bs, iters, xyz, idx, st);
-    if (n <= 2048) return launch_fps<4, 512>(b, n, m, log2bs, iters, xyz, idx, st);
-    if (n <= 4096) return launch_fps<8, 512>(b, n, m, log2bs, iters, xyz, idx, st);
-    if (n <= 8192) return launch_fps<8, 1024>(b, n, m, log2bs, iters, xyz, idx, st);
-    return launch_fps<16, 1024>(b, n, m, log2bs, iters, xyz, idx, st);
+    if (n <= 512) return launch_fps<1, 512>(b, n, m, log2bs, iters, plain, xyz, idx, st);
+    if (n <= 1024) return launch_fps<2, 512>(b, n, m, log2bs, iters, plain, xyz, idx, st);
+    if (n <= 2048) return launch_fps<4, 512>(b, n, m, log2bs, iters, plain, xyz, idx, st);
+    if (n <= 4096) return launch_fps<8, 512>(b, n, m, log2bs, iters, plain, xyz, idx, st);
+    if (n <= 8192) return launch_fps<8, 1024>(b, n, m, log2bs, iters, plain, xyz, idx, st);
+    return launch_fps<16, 1024>(b, n, m, log2bs, iters, plain, xyz, idx, st);
+}
+
+extern "C" int vgtkb_furthest_point_sampling(int b, int n, int m, const float* xyz, int32_t* idx, void* stream) {
+    return fps_dispatch(b, n, m, 0, xyz, idx, stream);
+}
+
+// plain farthest point sampling (start at point 0, every point eligible, lowest index on ties): what
+// torch_cluster.fps(random_start=False) computes for the reference's wrappers (SPConvNets/models/model_util.py:183-200)
+extern "C" int vgtkb_fps_plain(int b, int n, int m, const float* xyz, int32_t* idx, void* stream) {
+    return fps_dispatch(b, n, m, 1, xyz, idx, stream);
 }
 
 extern "C" int vgtkb_gather_points_forward(int b, int c, int n, int m, const float* points, const int32_t* idx,

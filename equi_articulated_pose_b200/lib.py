@@ -21,6 +21,7 @@ c_int, c_i64, c_f32, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes
 SIGNATURES = {
     "vgtkb_ball_query": [c_int, c_int, c_int, c_f32, c_int, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_furthest_point_sampling": [c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    "vgtkb_fps_plain": [c_int, c_int, c_int, c_vp, c_vp, c_vp],
     "vgtkb_gather_points_forward": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_gather_points_backward": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_chamfer_forward": [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
@@ -53,6 +54,9 @@ SIGNATURES = {
     "vgtkb_norm_act_forward": [c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
     "vgtkb_norm_act_backward": [c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_col_sum": [c_i64, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_pointnet_pool_forward": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_pointnet_embed_xyz": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_pointnet_pool_backward": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_peer_allreduce_f64": [c_int, c_vp, c_int, c_int, c_vp, ctypes.c_uint64, c_vp],
     "vgtkb_norm_finalize_peer": [c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_int, c_vp, ctypes.c_uint64, c_vp],
 }

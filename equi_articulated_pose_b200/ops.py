@@ -57,6 +57,15 @@ def furthest_point_sampling(xyz, m):
     return idx
 
 
+def fps_plain(xyz, m):
+    """Plain farthest point sampling (torch_cluster.fps semantics, start at point 0): xyz [B,3,N] -> int32 [B,m]."""
+    xyz = _f32(xyz)
+    b, _, n = xyz.shape
+    idx = torch.zeros((b, m), dtype=torch.int32, device=xyz.device)
+    call("vgtkb_fps_plain", xyz.device, b, n, int(m), ptr(xyz), ptr(idx))
+    return idx
+
+
 def gather_points_forward(points, idx):
     """vgtk.cuda.gathering.gather_points_forward: points [B,C,N], idx [B,M] -> [B,C,M]."""
     points, idx = _f32(points), _i32(idx)
@@ -324,6 +333,50 @@ class LinearFn(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = col_sum(gy)
         return gx, gw, gb
+
+
+class PointnetPoolFn(torch.autograd.Function):
+    """out[b,o,a] = max_n (e[b,n,a,o] + v[a,o,:] . xc[b,:,n])  -- the pooled PointnetSO3Conv output
+    (vgtk/vgtk/so3conv/modules.py:404-412); e [B,N,A,Co] rows of the feature part of the embedding, v [A,Co,3],
+    xc [B,3,N] centred coordinates."""
+
+    @staticmethod
+    def forward(ctx, e, v, xc):
+        e, v, xc = _f32(e), _f32(v), _f32(xc)
+        b, n, a, co = e.shape
+        out = torch.empty((b, co, a), dtype=torch.float32, device=e.device)
+        arg = torch.empty((b, a, co), dtype=torch.int32, device=e.device)
+        call("vgtkb_pointnet_pool_forward", e.device, b, n, a, co, ptr(e), ptr(v), ptr(xc), ptr(out), ptr(arg))
+        ctx.save_for_backward(v, xc, arg)
+        ctx.meta = (b, n, a, co)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        v, xc, arg = ctx.saved_tensors
+        b, n, a, co = ctx.meta
+        gout = _f32(gout)
+        ge = gv = gxc = None
+        if ctx.needs_input_grad[0]:
+            ge = torch.empty((b, n, a, co), dtype=torch.float32, device=gout.device)
+            call("vgtkb_pointnet_pool_backward", gout.device, b, n, a, co, ptr(gout), ptr(arg), ptr(ge))
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            g = gout.permute(0, 2, 1)                                               # [B,A,Co]
+            idx = arg.long().reshape(b, 1, a * co).expand(b, 3, a * co)
+            if ctx.needs_input_grad[1]:
+                xsel = torch.gather(xc, 2, idx).view(b, 3, a, co)                   # xc[b, :, arg[b,a,o]]
+                gv = torch.einsum('bao,bjao->aoj', g, xsel)
+            if ctx.needs_input_grad[2]:
+                contrib = (g.unsqueeze(1) * v.permute(2, 0, 1).unsqueeze(0)).reshape(b, 3, a * co)
+                gxc = torch.zeros_like(xc).scatter_add_(2, idx, contrib)
+        return ge, gv, gxc
+
+
+def pointnet_embed_xyz_(e, v, xc):
+    """e [B,N,A,Co] += v[a,o,:] . xc[b,:,n] in place (PointnetSO3Conv with return_raw=True; inference only)."""
+    b, n, a, co = e.shape
+    call("vgtkb_pointnet_embed_xyz", e.device, b, n, a, co, ptr(e), ptr(_f32(v)), ptr(_f32(xc)))
+    return e
 
 
 class RowGatherFn(torch.autograd.Function):

@@ -170,8 +170,10 @@ class IntraSO3Conv2D(nn.Module):
 
 
 class PointnetSO3Conv(nn.Module):
-    """Equivariant PointNet pooling head (reference :376-413): anchor-rotated xyz concatenated to
-    the features, 1x1 conv, max over points."""
+    """Equivariant PointNet pooling head (reference :376-413): anchor-rotated centred xyz concatenated to the features,
+    1x1 conv, max over points.  Same parameters (`embed.weight [Co, C+3, 1, 1]`, `embed.bias`, buffer `anchors`); the
+    [B, C+3, N, A] concatenation is never built: the feature part of the conv is the tcgen05 contraction on the
+    channels-last rows, the coordinate part (three FMAs per output) is folded into the pooling pass."""
 
     def __init__(self, dim_in, dim_out, kanchor=60, return_raw=False):
         super().__init__()
@@ -183,14 +185,21 @@ class PointnetSO3Conv(nn.Module):
     def forward(self, x):
         xyz, feats = x.xyz, x.feats
         nb, nc, npt, na = feats.shape
-        xyz = xyz - xyz.mean(2, keepdim=True)
+        xc = (xyz - xyz.mean(2, keepdim=True)).contiguous()
+        w = self.embed.weight.view(self.dim_out, self.dim_in)
+        w_f, w_x = w[:, :nc].contiguous(), w[:, nc:]
         if na == 1:
-            feats = torch.cat([x.feats, xyz[..., None]], 1)
+            v = w_x.unsqueeze(0)                                        # xyz itself is concatenated (:400-401)
         else:
-            xyzr = torch.einsum('aji,bjn->bina', self.anchors, xyz)
-            feats = torch.cat([x.feats, xyzr], 1)
-        feats = self.embed(feats)
-        return feats if self.return_raw else torch.max(feats, 2)[0]
+            v = torch.einsum('oi,aji->aoj', w_x, self.anchors)          # W_x applied to R_a^T xyz (:404)
+        rows = L._channels_last(feats).view(nb * npt * na, nc)
+        e = _ops.LinearFn.apply(rows, w_f, self.embed.bias).view(nb, npt, na, self.dim_out)
+        if self.return_raw:
+            if torch.is_grad_enabled() and (e.requires_grad or v.requires_grad):
+                term = torch.einsum('aoj,bjn->bnao', v, xc)             # differentiable form of the same three FMAs
+                return (e + term).permute(0, 3, 1, 2)
+            return _ops.pointnet_embed_xyz_(e, v.contiguous(), xc).permute(0, 3, 1, 2)
+        return _ops.PointnetPoolFn.apply(e, v.contiguous(), xc)
 
 
 class PointnetSO3PoseConv(PointnetSO3Conv):

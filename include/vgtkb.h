@@ -54,6 +54,11 @@ int vgtkb_ball_query(int b, int n, int m, float radius, int nsample,
  * block-size dependent tie-break of the reference's shared-memory tree and the |p|^2 <= 1e-3
  * skip rule. */
 int vgtkb_furthest_point_sampling(int b, int n, int m, const float* xyz, int32_t* idx, void* stream);
+/* Plain farthest point sampling, same layouts: start at point 0, every point eligible (no |p|^2 <= 1e-3 exclusion),
+ * lowest index on ties.  Backs the torch_cluster.fps(pos, batch, ratio, random_start=False) shim the reference's
+ * wrappers call (SPConvNets/models/model_util.py:183-200, ...38_multi_stage.py:1739); torch_cluster==1.5.9 is not
+ * under /root/reference and no reference test pins its tie-break: parity unpinned. */
+int vgtkb_fps_plain(int b, int n, int m, const float* xyz, int32_t* idx, void* stream);
 
 /* vgtk.cuda.gathering.gather_points_forward / backward (gathering_cuda.cpp:29-58, kernels
  * gathering_cuda_kernel.cu:43-98).  points [b,c,n], idx [b,m] -> out [b,c,m];
@@ -237,6 +242,17 @@ int vgtkb_peer_free(void* dev_ptr);
 int vgtkb_peer_allreduce_f64(int n, double* buf, int rank, int world, void* const* mailboxes, uint64_t seq, void* stream);
 int vgtkb_norm_finalize_peer(int c, float eps, double* scratch, float* stats, float* running_mean, float* running_var,
                              float momentum, int rank, int world, void* const* mailboxes, uint64_t seq, void* stream);
+
+/* PointnetSO3Conv pooling head (vgtk/vgtk/so3conv/modules.py:376-413).  e [b, n, a, co]: rows of the feature part of
+ * the 1x1 conv (vgtkb_gemm_nt with the bias); v [a, co, 3] = sum_i W_x[o,i] anchors[a,j,i]; xc [b, 3, n] centred xyz.
+ *   pool_forward:  out [b, co, a] = max_n (e + v . xc), arg [b, a, co] = first arg-max (int32)
+ *   embed_xyz:     e += v . xc in place (the module's return_raw=True output)
+ *   pool_backward: grad_e [b, n, a, co] = grad_out scattered to the arg-max rows (zero elsewhere) */
+int vgtkb_pointnet_pool_forward(int b, int n, int a, int co, const float* e, const float* v, const float* xc, float* out,
+                                int32_t* arg, void* stream);
+int vgtkb_pointnet_embed_xyz(int b, int n, int a, int co, float* e, const float* v, const float* xc, void* stream);
+int vgtkb_pointnet_pool_backward(int b, int n, int a, int co, const float* grad_out, const int32_t* arg, float* grad_e,
+                                 void* stream);
 
 /* column sums of a row-major [rows, c] matrix (bias gradient of the skip conv) */
 int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream);

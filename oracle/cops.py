@@ -63,6 +63,14 @@ def furthest_point_sampling(xyz, m):
     return idx
 
 
+def fps_plain(xyz, m):
+    xyz = _f(xyz)
+    b, _, n = xyz.shape
+    idx = np.zeros((b, m), np.int32)
+    lib().oracle_fps_plain(b, n, int(m), _p(xyz), _p(idx))
+    return idx
+
+
 def gather_points_forward(points, idx):
     points, idx = _f(points), _i(idx)
     b, c, n = points.shape

@@ -111,6 +111,36 @@ void oracle_fps(int b, int n, int m, const float* xyz, int32_t* idxs) {
     free(temp); free(dists); free(dists_i);
 }
 
+/* plain farthest point sampling (the published algorithm of torch_cluster.fps with random_start=False, torch-cluster
+ * 1.5.9, env.yaml:13 -- not vendored under /root/reference, tie-break unpinned): start at point 0, keep the running
+ * minimum squared distance to the chosen set, take the first maximum.  Distances with the same FMUL,FFMA,FFMA
+ * contraction as the other kernels. */
+void oracle_fps_plain(int b, int n, int m, const float* xyz, int32_t* idxs) {
+    if (m <= 0) return;
+    float* temp = (float*)malloc(sizeof(float) * (size_t)n);
+    for (int bi = 0; bi < b; ++bi) {
+        const float* d = xyz + (size_t)bi * 3 * n;
+        int32_t* out = idxs + (size_t)bi * m;
+        for (int k = 0; k < n; ++k) temp[k] = 1e10f;
+        int old = 0;
+        out[0] = 0;
+        for (int j = 1; j < m; ++j) {
+            const float x1 = d[old], y1 = d[n + old], z1 = d[2 * n + old];
+            int besti = 0;
+            float best = -1.f;
+            for (int k = 0; k < n; ++k) {
+                const float dd = sq3(d[k] - x1, d[n + k] - y1, d[2 * n + k] - z1);
+                const float d2 = fminf(dd, temp[k]);
+                temp[k] = d2;
+                if (d2 > best) { besti = k; best = d2; }
+            }
+            old = besti;
+            out[j] = old;
+        }
+    }
+    free(temp);
+}
+
 /* points [b,c,n], idx [b,m] -> out [b,c,m] */
 void oracle_gather_fwd(int b, int c, int n, int m, const float* points, const int32_t* idx, float* out) {
     for (int bi = 0; bi < b; ++bi)

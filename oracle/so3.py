@@ -271,3 +271,18 @@ def anchor_orbit_chamfer(canon, rot, trans, ori, glb_single_cd=0):
     minn, orbit = torch.min(total, dim=-1)                                                            # :449
     return dict(d1=d1, d2=d2, i1=torch.from_numpy(i1).view(bz, na, m), i2=torch.from_numpy(i2).view(bz, na, n),
                 cd_r2o=cd_r2o, cd_o2r=cd_o2r, minn=minn, orbit=orbit, transformed=transformed)
+
+
+def pointnet_so3conv(weight, bias, anchors, xyz, feats, return_raw=False):
+    """PointnetSO3Conv.forward (vgtk/vgtk/so3conv/modules.py:392-413): centre xyz, rotate it into every anchor frame,
+    concatenate to the features, 1x1 conv, max over points.
+    weight [Co, C+3] (embed.weight squeezed), bias [Co], anchors [A,3,3], xyz [B,3,N], feats [B,C,N,A]."""
+    na = feats.shape[3]
+    xyz = xyz - xyz.mean(2, keepdim=True)                                            # :398
+    if na == 1:
+        cat = torch.cat([feats, xyz[..., None]], 1)                                  # :400-401
+    else:
+        xyzr = torch.einsum('aji,bjn->bina', anchors.to(xyz.dtype), xyz)             # :404
+        cat = torch.cat([feats, xyzr], 1)                                            # :405
+    out = torch.einsum('oc,bcna->bona', weight.view(weight.shape[0], -1), cat) + bias.view(1, -1, 1, 1)   # :407
+    return out if return_raw else torch.max(out, 2)[0]                               # :408-412

@@ -10,6 +10,7 @@ Writes (all small):
   tests/golden/ref_blocks_small.npz   2 stacked separable blocks, fwd + bwd, train mode
   tests/golden/ref_intra_small.npz    one IntraSO3Conv (BASELINE config 1a, reduced size)
   tests/golden/ref_weights_small.npz  inter_so3conv_grouping_anchor + grouping einsum
+  tests/golden/ref_intrazp_small.npz, ref_pose_group_small.npz, ref_pointnet_small.npz (`make_golden.py pointnet`)
 """
 import contextlib
 import io
@@ -39,8 +40,35 @@ def small_params():
             [layer(8, 16, 2, 1.0, 0.5, 12, True)]]
 
 
+def make_pointnet():
+    """PointnetSO3Conv head (so3conv/modules.py:376-413), fwd + bwd, A = 60 and A = 1, raw and pooled."""
+    H.import_blocks()
+    import vgtk.so3conv as sptk
+    out = {}
+    for na in (60, 1):
+        torch.manual_seed(0)
+        g = torch.Generator().manual_seed(1004 + na)
+        nb, c, npt, co = 2, 16, 40, 24
+        head = sptk.PointnetSO3Conv(c, co, kanchor=na)
+        feats = torch.randn(nb, c, npt, na, generator=g, requires_grad=True)
+        xyz = torch.rand(nb, 3, npt, generator=g) - 0.5
+        pooled = head(sptk.SphericalPointCloud(xyz, feats, None))
+        gout = torch.randn(pooled.shape, generator=g)
+        (pooled * gout).sum().backward()
+        head.return_raw = True
+        raw = head(sptk.SphericalPointCloud(xyz, feats.detach(), None))
+        out.update({f'a{na}_weight': head.embed.weight.detach().numpy(), f'a{na}_bias': head.embed.bias.detach().numpy(),
+                    f'a{na}_feats': feats.detach().numpy(), f'a{na}_xyz': xyz.numpy(), f'a{na}_pooled': pooled.detach().numpy(),
+                    f'a{na}_raw': raw.detach().numpy(), f'a{na}_grad_out': gout.numpy(), f'a{na}_grad_feats': feats.grad.numpy(),
+                    f'a{na}_grad_weight': head.embed.weight.grad.numpy(), f'a{na}_grad_bias': head.embed.bias.grad.numpy()})
+    np.savez_compressed(os.path.join(GOLD, "ref_pointnet_small.npz"), **out)
+    print("pointnet", out['a60_pooled'].shape, out['a1_pooled'].shape)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1 and sys.argv[1] == "pointnet":      # only this fixture (the others stay untouched)
+        return make_pointnet()
     M = H.import_blocks()
     import vgtk.so3conv as sptk
     import vgtk.so3conv.functional as L
@@ -146,6 +174,7 @@ def main():
         outp[f'grouped_pm{pm}'] = r[3].numpy()
     np.savez_compressed(os.path.join(GOLD, "ref_pose_group_small.npz"), **outp)
     print("pose grouping", r[3].shape)
+    make_pointnet()
 
 
 if __name__ == "__main__":

@@ -638,3 +638,82 @@ def test_anchor_chamfer_gradients(dev, ops):
     ((D.min(3)[0] * w1.double()).sum() + (D.min(2)[0] * w2.double()).sum()).backward()
     for got, ref in zip(leaves, dl):
         assert rel_err(got.grad, ref.grad) < 2e-5
+
+
+# ------------------------------------------------------------------------------ plain FPS / torch_cluster shim
+@pytest.mark.parametrize("b,n,m,kind", [(4, 512, 128, "shell"), (2, 2048, 512, "uniform"), (3, 1000, 1000, "grid"),
+                                        (1, 4096, 1024, "shell")])
+def test_fps_plain_bit_exact_vs_oracle(dev, ops, b, n, m, kind):
+    from oracle import cops
+    xyz = _cloud(b, n, 31 + n, kind)
+    xyz[:, :, 3] = 0.0                                   # a point at the origin is eligible here (it is not in the vgtk kernel)
+    got = ops.fps_plain(xyz.to(dev), m).cpu().numpy()
+    assert np.array_equal(got, cops.fps_plain(xyz.numpy(), m))
+
+
+def test_torch_cluster_shim_matches_reference_wrapper_semantics(dev):
+    """farthest_point_sampling of SPConvNets/models/model_util.py:183-200: flat indices, segment after segment."""
+    import equi_articulated_pose_b200 as eap
+    eap.install()
+    import torch_cluster
+    from oracle import cops
+    bz, n, ns = 3, 600, 150
+    pos = _cloud(bz, n, 5, "uniform").permute(0, 2, 1).contiguous()                      # [bz, N, 3]
+    batch = torch.arange(bz).view(bz, 1).repeat(1, n).view(-1)
+    idx = torch_cluster.fps(pos.view(-1, 3).to(dev), batch.to(dev), ratio=float(ns / n), random_start=False)
+    want = cops.fps_plain(pos.permute(0, 2, 1).contiguous().numpy(), ns).astype(np.int64) + np.arange(bz)[:, None] * n
+    assert idx.dtype == torch.int64 and np.array_equal(idx.cpu().numpy(), want.reshape(-1))
+
+
+# ------------------------------------------------------------------------------ PointnetSO3Conv head
+@pytest.mark.parametrize("na", [60, 1])
+def test_pointnet_head_matches_reference_fixture(dev, na):
+    """vgtk.so3conv.PointnetSO3Conv (drop-in, fused kernels) against the reference's own module, fwd + bwd."""
+    import equi_articulated_pose_b200 as eap
+    eap.install()
+    import vgtk.so3conv as sptk
+    g = np.load(os.path.join(GOLD, "ref_pointnet_small.npz"))
+    t = {k[len(f'a{na}_'):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(f'a{na}_')}
+    head = sptk.PointnetSO3Conv(t['feats'].shape[1], t['pooled'].shape[1], kanchor=na).to(dev)
+    head.load_state_dict({'embed.weight': t['weight'], 'embed.bias': t['bias'], 'anchors': head.anchors.cpu()})
+    feats = t['feats'].to(dev).requires_grad_(True)
+    pooled = head(sptk.SphericalPointCloud(t['xyz'].to(dev), feats, None))
+    assert pooled.shape == t['pooled'].shape and rel_err(pooled, t['pooled']) < FP32_TOL
+    (pooled * t['grad_out'].to(dev)).sum().backward()
+    assert rel_err(feats.grad, t['grad_feats']) < FP32_TOL
+    assert rel_err(head.embed.weight.grad, t['grad_weight']) < FP32_TOL
+    assert rel_err(head.embed.bias.grad, t['grad_bias']) < FP32_TOL
+    head.return_raw = True
+    with torch.no_grad():
+        raw = head(sptk.SphericalPointCloud(t['xyz'].to(dev), feats.detach(), None))
+    assert raw.shape == t['raw'].shape and rel_err(raw, t['raw']) < FP32_TOL
+    raw_g = head(sptk.SphericalPointCloud(t['xyz'].to(dev), feats, None))      # differentiable raw path
+    assert rel_err(raw_g, t['raw']) < FP32_TOL
+
+
+def test_pointnet_head_backbone_size_vs_oracle(dev):
+    """Config-2 tail size: feats [8, 256, 64, 60] -> [8, 128, 60]; first-maximum arg-max, xyz gradient."""
+    import equi_articulated_pose_b200 as eap
+    eap.install()
+    import vgtk.so3conv as sptk
+    from oracle import so3 as O
+    g = torch.Generator().manual_seed(11)
+    nb, c, npt, na, co = 8, 256, 64, 60, 128
+    head = sptk.PointnetSO3Conv(c, co, kanchor=na).to(dev)
+    feats = torch.randn(nb, c, npt, na, generator=g)
+    xyz = (torch.rand(nb, 3, npt, generator=g) - 0.5)
+    fd, xd = feats.to(dev).requires_grad_(True), xyz.to(dev).requires_grad_(True)
+    out = head(sptk.SphericalPointCloud(xd, fd, None))
+    gout = torch.randn(out.shape, generator=g)
+    (out * gout.to(dev)).sum().backward()
+    w64, b64 = head.embed.weight.detach().cpu().double().view(co, c + 3), head.embed.bias.detach().cpu().double()
+    f64, x64 = feats.double().requires_grad_(True), xyz.double().requires_grad_(True)
+    ref = O.pointnet_so3conv(w64, b64, head.anchors.cpu().double(), x64, f64)
+    (ref * gout.double()).sum().backward()
+    assert rel_err(out, ref) < FP32_TOL
+
+    def flipped(got, want):
+        """fraction of elements off by more than the tolerance: only the outputs whose two largest candidates are
+        closer than the fp32 rounding of the embedding may pick the other point (a handful of 61440 maxima)"""
+        return float(((got.detach().cpu().double() - want).abs() > FP32_TOL * float(want.abs().max())).double().mean())
+    assert flipped(fd.grad, f64.grad) < 1e-3 and flipped(xd.grad, x64.grad) < 2e-2

@@ -242,3 +242,21 @@ def test_anchor_orbit_chamfer_oracle_vs_fp64_bruteforce():
     assert torch.equal(r['orbit'], total.argmin(-1))
     single = O.anchor_orbit_chamfer(canon, q.contiguous(), tr, ori, glb_single_cd=1)
     assert torch.equal(single['orbit'], D.min(2)[0].mean(-1).argmin(-1))
+
+
+def test_pointnet_head_oracle_vs_reference_fixture(golden_dir):
+    """oracle.so3.pointnet_so3conv against the reference's own PointnetSO3Conv (tests/golden/make_golden.py pointnet)."""
+    g = np.load(os.path.join(golden_dir, "ref_pointnet_small.npz"))
+    anchors = torch.from_numpy(np.ascontiguousarray(C.get_anchors(60)))
+    for na in (60, 1):
+        t = {k[len(f'a{na}_'):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(f'a{na}_')}
+        feats = t['feats'].clone().requires_grad_(True)
+        w, b = t['weight'].clone().requires_grad_(True), t['bias'].clone().requires_grad_(True)
+        anc = anchors if na == 60 else anchors[29:30]
+        pooled = O.pointnet_so3conv(w, b, anc, t['xyz'], feats)
+        raw = O.pointnet_so3conv(w, b, anc, t['xyz'], feats, return_raw=True)
+        assert torch.allclose(pooled, t['pooled'], atol=2e-6) and torch.allclose(raw, t['raw'], atol=2e-6)
+        (pooled * t['grad_out']).sum().backward()
+        assert torch.allclose(feats.grad, t['grad_feats'], atol=1e-5)
+        assert torch.allclose(w.grad.view_as(t['grad_weight']), t['grad_weight'], atol=1e-5)
+        assert torch.allclose(b.grad, t['grad_bias'], atol=1e-5)
