@@ -7,7 +7,7 @@
 
 #include "../../include/vgtkb.h"
 
-#define VGTKB_ABI_VERSION 7
+#define VGTKB_ABI_VERSION 8
 
 namespace vgtkb {
 

@@ -169,6 +169,288 @@ inter_group_fwd_kernel(int n, int p, int nn, int a, int k, int ci, const float* 
     }
 }
 
+// ---------------------------------------------------------------------------------- forward on the tensor cores
+// bf16x3 variant of the forward grouping (the default contraction arithmetic, mode 3): per (point, anchor) the small
+// product  G[c, kp] = sum_n F[c, n] W[n, kp]  (F = gathered neighbour rows, W = kernel-point correlation weights) runs
+// as warp-level mma.sync.m16n8k16 bf16 MMAs with fp32 accumulation, both operands split hi/lo exactly like the
+// tcgen05 contraction that consumes G (lo*hi + hi*lo + hi*hi: ~1e-5 of max|G|).  Everything stays in registers:
+//   * B fragments (weights) are COMPUTED straight into their fragment slots -- lane (gid, tig) owns kernel points
+//     8t + gid and neighbours 2tig, 2tig+1, 2tig+8, 2tig+9 of every 16-neighbour step -- no shared-memory weight table;
+//   * A fragments come from one 16-byte load per neighbour row and 32-channel chunk: lane gid reads channels
+//     4gid..4gid+3 (8 lanes = one 128-byte line) and the MMA rows are PERMUTED so that those four channels are rows
+//     (gid, gid+8) of two M tiles; the same permutation turns the accumulator fragments into 16-byte stores.
+// The FFMA kernel above issues 12*CPL FFMA per neighbour and lane (45 % of all issued instructions, 70 % issue
+// utilisation: instruction-bound); this one needs about a third of the instructions and leaves the HBM write of G
+// as the bound.  K <= 24 kernel points (3 N tiles), nn <= 32 (KS = 1 or 2 k-steps), Ci % 32 == 0.
+__device__ __forceinline__ uint32_t ig_pack_bf16x2(float lo_elem, float hi_elem) {   // lo_elem -> low half
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+__device__ __forceinline__ void ig_split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    hi = ig_pack_bf16x2(x0, x1);
+    lo = ig_pack_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xFFFF0000u));
+}
+__device__ __forceinline__ void ig_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int KS>
+__global__ void __launch_bounds__(IG_WARPS * 32, 2)
+inter_group_fwd_mma_kernel(int n, int p, int nn, int a, int k, int ci, const float* __restrict__ xyz,
+                           const float* __restrict__ sxyz, const int32_t* __restrict__ idx,
+                           const float* __restrict__ rk, float inv_sigma, const float* __restrict__ feats,
+                           float* __restrict__ grouped) {
+    __shared__ float s_g[16 * KS * 3];
+    __shared__ uint32_t s_off[16 * KS];
+    const int pi = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    {   // neighbour offsets (centre-relative) and row offsets; slots >= nn: weight 0 (offset 1e18 -> relu 0), row 0
+        const float* X = xyz + (size_t)b * 3 * n;
+        const float* S = sxyz + (size_t)b * 3 * p;
+        for (int i = threadIdx.x; i < 16 * KS; i += blockDim.x) {
+            if (i < nn) {
+                const int j = idx[((size_t)b * p + pi) * nn + i];
+                s_off[i] = (uint32_t)j * (uint32_t)(a * ci);
+                s_g[i * 3 + 0] = X[j] - S[pi];
+                s_g[i * 3 + 1] = X[n + j] - S[p + pi];
+                s_g[i * 3 + 2] = X[2 * n + j] - S[2 * p + pi];
+            } else {
+                s_off[i] = 0;
+                s_g[i * 3 + 0] = s_g[i * 3 + 1] = s_g[i * 3 + 2] = 1e18f;
+            }
+        }
+    }
+    __syncthreads();
+    // this lane's four neighbours per k-step: n0 = 16s + 2tig, n0+1, n0+8, n0+9
+    float gx[KS][4], gy[KS][4], gz[KS][4];
+    uint32_t off[KS][4];
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ni = 16 * s + 2 * tig + (j & 1) + 8 * (j >> 1);
+            gx[s][j] = s_g[ni * 3];
+            gy[s][j] = s_g[ni * 3 + 1];
+            gz[s][j] = s_g[ni * 3 + 2];
+            off[s][j] = s_off[ni];
+        }
+    const float* fb = feats + (size_t)b * n * a * ci + 4 * gid;
+    for (int ai = warp; ai < a; ai += IG_WARPS) {
+        // ---- B fragments: weights of kernel points 8t + gid against the lane's neighbours, hi / lo
+        uint32_t bh[KS][3][2], bl[KS][3][2];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int kp = 8 * t + gid;
+            const bool live = kp < k;
+            float kx = 0.f, ky = 0.f, kz = 0.f;
+            if (live) {
+                const float* q = rk + (ai * k + kp) * 3;
+                kx = __ldg(q);
+                ky = __ldg(q + 1);
+                kz = __ldg(q + 2);
+            }
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                float w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float dx = gx[s][j] - kx, dy = gy[s][j] - ky, dz = gz[s][j] - kz;
+                    const float v = fmaxf(0.f, 1.f - (dx * dx + dy * dy + dz * dz) * inv_sigma);
+                    w[j] = live ? v : 0.f;
+                }
+                ig_split2(w[0], w[1], bh[s][t][0], bl[s][t][0]);
+                ig_split2(w[2], w[3], bh[s][t][1], bl[s][t][1]);
+            }
+        }
+        float* out = grouped + (((size_t)b * p + pi) * a + ai) * (size_t)k * ci + 4 * gid;
+        const float* fa = fb + (size_t)ai * ci;
+        for (int c0 = 0; c0 < ci; c0 += 32) {
+            float4 v[KS][4];
+#pragma unroll
+            for (int s = 0; s < KS; ++s)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[s][j] = __ldg(reinterpret_cast<const float4*>(fa + off[s][j] + c0));
+            float d[2][3][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) d[m][t][e] = 0.f;
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                // M tile 0: rows (gid, gid+8) = channels (.x, .y); M tile 1: (.z, .w)
+                uint32_t ah[2][4], al[2][4];
+                ig_split2(v[s][0].x, v[s][1].x, ah[0][0], al[0][0]);
+                ig_split2(v[s][0].y, v[s][1].y, ah[0][1], al[0][1]);
+                ig_split2(v[s][2].x, v[s][3].x, ah[0][2], al[0][2]);
+                ig_split2(v[s][2].y, v[s][3].y, ah[0][3], al[0][3]);
+                ig_split2(v[s][0].z, v[s][1].z, ah[1][0], al[1][0]);
+                ig_split2(v[s][0].w, v[s][1].w, ah[1][1], al[1][1]);
+                ig_split2(v[s][2].z, v[s][3].z, ah[1][2], al[1][2]);
+                ig_split2(v[s][2].w, v[s][3].w, ah[1][3], al[1][3]);
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        ig_mma(d[m][t], al[m], bh[s][t][0], bh[s][t][1]);
+                        ig_mma(d[m][t], ah[m], bl[s][t][0], bl[s][t][1]);
+                        ig_mma(d[m][t], ah[m], bh[s][t][0], bh[s][t][1]);
+                    }
+            }
+            // accumulator (row gid | gid+8, col 2tig | 2tig+1) -> channels 4gid.. of kernel points 8t + 2tig (+1)
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int kp = 8 * t + 2 * tig;
+                if (kp < k)
+                    __stcs(reinterpret_cast<float4*>(out + (size_t)kp * ci + c0),
+                           make_float4(d[0][t][0], d[0][t][2], d[1][t][0], d[1][t][2]));
+                if (kp + 1 < k)
+                    __stcs(reinterpret_cast<float4*>(out + (size_t)(kp + 1) * ci + c0),
+                           make_float4(d[0][t][1], d[0][t][3], d[1][t][1], d[1][t][3]));
+            }
+        }
+    }
+}
+
+// backward on the tensor cores (mode 3): dF[c, n] = sum_kp dG[kp, c] W[n, kp] per (point, anchor), same scheme as the
+// forward kernel with the roles turned: M = channels (permuted rows, 16-byte loads of dG rows), N = neighbours (tiles
+// of 8), K = kernel points = one k16 step + one k8 step (24 exactly).  The accumulator fragments are four adjacent
+// channels of one neighbour: one 16-byte red.global.add per fragment pair.  (The FFMA kernel below is instruction
+// bound -- 70 % issue utilisation, L2 at 30 % -- not atomics bound.)
+__device__ __forceinline__ void ig_mma_k8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+}
+
+template <int KS>
+__global__ void __launch_bounds__(IG_WARPS * 32, 2)
+inter_group_bwd_mma_kernel(int n, int p, int nn, int a, int k, int ci, const float* __restrict__ xyz,
+                           const float* __restrict__ sxyz, const int32_t* __restrict__ idx,
+                           const float* __restrict__ rk, float inv_sigma, const float* __restrict__ ggrouped,
+                           float* __restrict__ gfeats) {
+    constexpr int NT = 2 * KS;                       // neighbour tiles of 8
+    __shared__ float s_g[16 * KS * 3];
+    __shared__ uint32_t s_off[16 * KS];
+    const int pi = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    {
+        const float* X = xyz + (size_t)b * 3 * n;
+        const float* S = sxyz + (size_t)b * 3 * p;
+        for (int i = threadIdx.x; i < 16 * KS; i += blockDim.x) {
+            if (i < nn) {
+                const int j = idx[((size_t)b * p + pi) * nn + i];
+                s_off[i] = (uint32_t)j * (uint32_t)(a * ci);
+                s_g[i * 3 + 0] = X[j] - S[pi];
+                s_g[i * 3 + 1] = X[n + j] - S[p + pi];
+                s_g[i * 3 + 2] = X[2 * n + j] - S[2 * p + pi];
+            } else {
+                s_off[i] = 0;
+                s_g[i * 3 + 0] = s_g[i * 3 + 1] = s_g[i * 3 + 2] = 1e18f;
+            }
+        }
+    }
+    __syncthreads();
+    // B side: this lane's neighbour of tile t is 8t + gid; D side: neighbours 8t + 2tig, 8t + 2tig + 1
+    float gx[NT], gy[NT], gz[NT];
+    uint32_t off[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        gx[t] = s_g[(8 * t + gid) * 3];
+        gy[t] = s_g[(8 * t + gid) * 3 + 1];
+        gz[t] = s_g[(8 * t + gid) * 3 + 2];
+        off[t][0] = s_off[8 * t + 2 * tig];
+        off[t][1] = s_off[8 * t + 2 * tig + 1];
+    }
+    // this lane's kernel points: k16 step 2tig, 2tig+1, 2tig+8, 2tig+9; k8 step 16+2tig, 17+2tig
+    int kps[6];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) kps[j] = 2 * tig + (j & 1) + 8 * (j >> 1);
+    kps[4] = 16 + 2 * tig;
+    kps[5] = 17 + 2 * tig;
+    float* gb = gfeats + (size_t)b * n * a * ci + 4 * gid;
+    for (int ai = warp; ai < a; ai += IG_WARPS) {
+        uint32_t bh[NT][3], bl[NT][3];
+        {
+            float kx[6], ky[6], kz[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                kx[j] = ky[j] = kz[j] = 1e18f;                      // kp >= k: weight 0
+                if (kps[j] < k) {
+                    const float* q = rk + (ai * k + kps[j]) * 3;
+                    kx[j] = __ldg(q);
+                    ky[j] = __ldg(q + 1);
+                    kz[j] = __ldg(q + 2);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                float w[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const float dx = gx[t] - kx[j], dy = gy[t] - ky[j], dz = gz[t] - kz[j];
+                    const float v = fmaxf(0.f, 1.f - (dx * dx + dy * dy + dz * dz) * inv_sigma);
+                    w[j] = (kps[j] < k && 8 * t + gid < nn) ? v : 0.f;
+                }
+                ig_split2(w[0], w[1], bh[t][0], bl[t][0]);
+                ig_split2(w[2], w[3], bh[t][1], bl[t][1]);
+                ig_split2(w[4], w[5], bh[t][2], bl[t][2]);
+            }
+        }
+        const float* gin = ggrouped + (((size_t)b * p + pi) * a + ai) * (size_t)k * ci + 4 * gid;
+        float* ga = gb + (size_t)ai * ci;
+        for (int c0 = 0; c0 < ci; c0 += 32) {
+            float4 v[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                v[j] = kps[j] < k ? __ldcs(reinterpret_cast<const float4*>(gin + (size_t)kps[j] * ci + c0))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t ah[2][6], al[2][6];            // per M tile: k16 a0..a3, k8 a0, a1
+            ig_split2(v[0].x, v[1].x, ah[0][0], al[0][0]);
+            ig_split2(v[0].y, v[1].y, ah[0][1], al[0][1]);
+            ig_split2(v[2].x, v[3].x, ah[0][2], al[0][2]);
+            ig_split2(v[2].y, v[3].y, ah[0][3], al[0][3]);
+            ig_split2(v[4].x, v[5].x, ah[0][4], al[0][4]);
+            ig_split2(v[4].y, v[5].y, ah[0][5], al[0][5]);
+            ig_split2(v[0].z, v[1].z, ah[1][0], al[1][0]);
+            ig_split2(v[0].w, v[1].w, ah[1][1], al[1][1]);
+            ig_split2(v[2].z, v[3].z, ah[1][2], al[1][2]);
+            ig_split2(v[2].w, v[3].w, ah[1][3], al[1][3]);
+            ig_split2(v[4].z, v[5].z, ah[1][4], al[1][4]);
+            ig_split2(v[4].w, v[5].w, ah[1][5], al[1][5]);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                float d[2][4];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) d[m][e] = 0.f;
+                    const uint32_t (&h)[6] = ah[m];
+                    const uint32_t (&l)[6] = al[m];
+                    const uint32_t h16[4] = {h[0], h[1], h[2], h[3]}, l16[4] = {l[0], l[1], l[2], l[3]};
+                    ig_mma(d[m], l16, bh[t][0], bh[t][1]);
+                    ig_mma(d[m], h16, bl[t][0], bl[t][1]);
+                    ig_mma(d[m], h16, bh[t][0], bh[t][1]);
+                    ig_mma_k8(d[m], l[4], l[5], bh[t][2]);
+                    ig_mma_k8(d[m], h[4], h[5], bl[t][2]);
+                    ig_mma_k8(d[m], h[4], h[5], bh[t][2]);
+                }
+                const int n0 = 8 * t + 2 * tig;
+                if (n0 < nn)
+                    atomicAdd(reinterpret_cast<float4*>(ga + off[t][0] + c0), make_float4(d[0][0], d[0][2], d[1][0], d[1][2]));
+                if (n0 + 1 < nn)
+                    atomicAdd(reinterpret_cast<float4*>(ga + off[t][1] + c0), make_float4(d[0][1], d[0][3], d[1][1], d[1][3]));
+            }
+        }
+    }
+}
+
 // backward of the fast path: dX[b, j_n, a, c] += sum_k w[n][k] dG[b,p,a,k,c]
 // (bound by the red.global.add traffic: the 16-byte vector atomics of CPL = 4 beat higher occupancy with
 // CPL = 2 -- measured 2.9 ms vs 3.4 ms per step)
@@ -434,12 +716,21 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 extern "C" int vgtkb_inter_group_forward(int b, int n, int p, int nn, int a, int k, int ci, const float* xyz,
                                          const float* sample_xyz, const int32_t* idx, const float* rot_kernels,
-                                         float sigma, const float* feats, float* grouped, void* stream) {
+                                         float sigma, const float* feats, float* grouped, int mode, void* stream) {
     int rc = check_inter_args(b, n, p, nn, a, k, ci);
     if (rc) return rc;
     if (b == 0 || p == 0) return VGTKB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool al = aligned16(feats) && aligned16(grouped);
+    if (mode == 3 && k <= 24 && nn <= 32 && ci % 32 == 0 && al && (int64_t)n * a * ci < ((int64_t)1 << 32)) {
+        if (nn <= 16)
+            inter_group_fwd_mma_kernel<1><<<dim3(p, b), IG_WARPS * 32, 0, st>>>(n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels,
+                                                                                1.0f / sigma, feats, grouped);
+        else
+            inter_group_fwd_mma_kernel<2><<<dim3(p, b), IG_WARPS * 32, 0, st>>>(n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels,
+                                                                                1.0f / sigma, feats, grouped);
+        return check_launch("inter_group_forward(mma)");
+    }
     if (k <= IG_KP && ci % 128 == 0 && al)
         return launch_inter<4>(true, b, n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels, sigma, feats, grouped, st);
     if (k <= IG_KP && ci % 64 == 0 && al)
@@ -456,12 +747,21 @@ extern "C" int vgtkb_inter_group_forward(int b, int n, int p, int nn, int a, int
 
 extern "C" int vgtkb_inter_group_backward(int b, int n, int p, int nn, int a, int k, int ci, const float* xyz,
                                           const float* sample_xyz, const int32_t* idx, const float* rot_kernels,
-                                          float sigma, const float* grad_grouped, float* grad_feats, void* stream) {
+                                          float sigma, const float* grad_grouped, float* grad_feats, int mode, void* stream) {
     int rc = check_inter_args(b, n, p, nn, a, k, ci);
     if (rc) return rc;
     if (b == 0 || p == 0) return VGTKB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool al = aligned16(grad_feats) && aligned16(grad_grouped);
+    if (mode == 3 && k <= 24 && nn <= 32 && ci % 32 == 0 && al && (int64_t)n * a * ci < ((int64_t)1 << 32)) {
+        if (nn <= 16)
+            inter_group_bwd_mma_kernel<1><<<dim3(p, b), IG_WARPS * 32, 0, st>>>(n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels,
+                                                                                1.0f / sigma, grad_grouped, grad_feats);
+        else
+            inter_group_bwd_mma_kernel<2><<<dim3(p, b), IG_WARPS * 32, 0, st>>>(n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels,
+                                                                                1.0f / sigma, grad_grouped, grad_feats);
+        return check_launch("inter_group_backward(mma)");
+    }
     if (k <= IG_KP && ci % 128 == 0 && al)
         return launch_inter<4>(false, b, n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels, sigma, grad_grouped, grad_feats, st);
     if (k <= IG_KP && ci % 64 == 0 && al)

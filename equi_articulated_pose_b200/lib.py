@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgtkb200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _lib = None
 _device_ok = set()
@@ -29,8 +29,8 @@ SIGNATURES = {
     "vgtkb_anchor_chamfer_forward": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_anchor_chamfer_backward": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_inter_weights": [c_int] * 6 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp],
-    "vgtkb_inter_group_forward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
-    "vgtkb_inter_group_backward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
+    "vgtkb_inter_group_forward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_int, c_vp],
+    "vgtkb_inter_group_backward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_int, c_vp],
     "vgtkb_intra_group_forward": [c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_intra_group_backward": [c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_pose_neighbourhood": [c_int] * 4 + [c_vp] * 7,
@@ -132,6 +132,8 @@ def ptr(t):
 def call(name, device, *args):
     """Invoke an entry point on `device`'s current stream; raise on a non-zero status."""
     lib = load()
+    if len(args) + 1 != len(SIGNATURES[name]):       # ctypes would pass surplus arguments through silently
+        raise VgtkbError(f"{name}: {len(args)} arguments given, {len(SIGNATURES[name]) - 1} expected (+ stream)")
     _ensure_device(device.index if device.index is not None else torch.cuda.current_device())
     with torch.cuda.device(device):
         cur = torch.cuda.current_stream()

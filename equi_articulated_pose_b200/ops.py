@@ -170,7 +170,7 @@ class InterGroupFn(torch.autograd.Function):
         k = rot_kernels.shape[1]
         g = torch.empty((b, p, a, k * ci), dtype=torch.float32, device=feats.device)
         call("vgtkb_inter_group_forward", feats.device, b, n, p, nn, a, k, ci, ptr(xyz), ptr(sample_xyz), ptr(idx),
-             ptr(rot_kernels), float(sigma), ptr(feats), ptr(g))
+             ptr(rot_kernels), float(sigma), ptr(feats), ptr(g), 3 if _GEMM_MODE == 3 else 0)
         ctx.save_for_backward(xyz, sample_xyz, idx, rot_kernels)
         ctx.meta = (b, n, p, nn, a, k, ci, float(sigma))
         return g
@@ -184,7 +184,7 @@ class InterGroupFn(torch.autograd.Function):
         grad_g = _f32(grad_g)
         gx = torch.zeros((b, n, a, ci), dtype=torch.float32, device=grad_g.device)
         call("vgtkb_inter_group_backward", grad_g.device, b, n, p, nn, a, k, ci, ptr(xyz), ptr(sample_xyz), ptr(idx),
-             ptr(rot_kernels), sigma, ptr(grad_g), ptr(gx))
+             ptr(rot_kernels), sigma, ptr(grad_g), ptr(gx), 3 if _GEMM_MODE == 3 else 0)
         return gx, None, None, None, None, None
 
 

@@ -102,17 +102,20 @@ int vgtkb_inter_weights(int b, int n, int p, int nn, int a, int k, const float* 
  *   feats X [b,n,a,ci] (channels-last) -> G [b,p,a,k,ci]   (row (b,p,a), column k*ci + c)
  *   G[b,p,a,k,c] = sum_j relu(1 - |xyz[b,:,idx[b,p,j]] - sample_xyz[b,:,p] - R_a kappa_k|^2 / sigma)
  *                        * X[b, idx[b,p,j], a, c]
- * The weights are recomputed on the fly, never stored. */
+ * The weights are recomputed on the fly, never stored.
+ * mode: arithmetic of the small per-(point, anchor) product, matching the contraction that consumes G:
+ *   0 = fp32 FFMA (exact fp32 accumulation)   3 = bf16x3 on the tensor cores (warp-level MMA, ~1e-5 of max|G|);
+ *   any other value selects the FFMA kernel. */
 int vgtkb_inter_group_forward(int b, int n, int p, int nn, int a, int k, int ci,
                               const float* xyz, const float* sample_xyz, const int32_t* idx,
                               const float* rot_kernels, float sigma,
-                              const float* feats, float* grouped, void* stream);
+                              const float* feats, float* grouped, int mode, void* stream);
 /* inter_zpconv_backward slot: grad_feats [b,n,a,ci] += scatter of grad_grouped (grad_feats is
  * accumulated into; the caller zeroes it when needed). */
 int vgtkb_inter_group_backward(int b, int n, int p, int nn, int a, int k, int ci,
                                const float* xyz, const float* sample_xyz, const int32_t* idx,
                                const float* rot_kernels, float sigma,
-                               const float* grad_grouped, float* grad_feats, void* stream);
+                               const float* grad_grouped, float* grad_feats, int mode, void* stream);
 
 /* Intra-anchor grouping = intra_zpconv_forward slot with the semantics of
  * intra_so3conv_grouping (so3conv/functional.py:2553-2567):
