@@ -1213,6 +1213,11 @@ static int make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t
     return VGTKB_OK;
 }
 
+int tc::make_rows_map(TmaMap* out, const void* base, int64_t rows, int64_t cols, int box_rows) {
+    static_assert(sizeof(CUtensorMap) == sizeof(TmaMap) && alignof(CUtensorMap) <= alignof(TmaMap), "CUtensorMap layout");
+    return make_map_2d(reinterpret_cast<CUtensorMap*>(out), base, rows, cols, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 // X [points, anchors, c] fp32 (or bf16) as a 3-D tensor; box = [box_rows points, 1 anchor, 128 bytes of channels]
 static int make_map_3d(CUtensorMap* map, const void* base, int64_t points, int anchors, int c, int box_rows,
                        CUtensorMapSwizzle swz, bool bf16 = false) {

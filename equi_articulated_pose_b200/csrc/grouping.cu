@@ -7,9 +7,12 @@
 // one CTA owns an output point, a warp owns an anchor, computes its [nn x K] weight tile and
 // streams the neighbour rows (channels-last, one coalesced 256/512-byte row segment per load)
 // through K*CPL register accumulators.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "tc_common.cuh"
 
 namespace vgtkb {
+using namespace tc;
 
 constexpr int IG_WARPS = 8;
 constexpr int IG_MAXNN = 128;
@@ -220,7 +223,7 @@ inter_group_fwd_mma_kernel(int n, int p, int nn, int a, int k, int ci, const flo
                 s_g[i * 3 + 2] = X[2 * n + j] - S[2 * p + pi];
             } else {
                 s_off[i] = 0;
-                s_g[i * 3 + 0] = s_g[i * 3 + 1] = s_g[i * 3 + 2] = 1e18f;
+                s_g[i * 3 + 0] = s_g[i * 3 + 1] = s_g[i * 3 + 2] = 1e12f;
             }
         }
     }
@@ -352,7 +355,7 @@ inter_group_bwd_mma_kernel(int n, int p, int nn, int a, int k, int ci, const flo
                 s_g[i * 3 + 2] = X[2 * n + j] - S[2 * p + pi];
             } else {
                 s_off[i] = 0;
-                s_g[i * 3 + 0] = s_g[i * 3 + 1] = s_g[i * 3 + 2] = 1e18f;
+                s_g[i * 3 + 0] = s_g[i * 3 + 1] = s_g[i * 3 + 2] = 1e12f;
             }
         }
     }
@@ -381,7 +384,7 @@ inter_group_bwd_mma_kernel(int n, int p, int nn, int a, int k, int ci, const flo
             float kx[6], ky[6], kz[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                kx[j] = ky[j] = kz[j] = 1e18f;                      // kp >= k: weight 0
+                kx[j] = ky[j] = kz[j] = 1e12f;                      // kp >= k: weight 0
                 if (kps[j] < k) {
                     const float* q = rk + (ai * k + kps[j]) * 3;
                     kx[j] = __ldg(q);
@@ -447,6 +450,589 @@ inter_group_bwd_mma_kernel(int n, int p, int nn, int a, int k, int ci, const flo
                 if (n0 + 1 < nn)
                     atomicAdd(reinterpret_cast<float4*>(ga + off[t][1] + c0), make_float4(d[0][1], d[0][3], d[1][1], d[1][3]));
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- bulk-copy (TMA) variants
+// ncu on the two kernels above: l1tex__data_pipe_lsu_wavefronts at 80-90 % with one 32-byte sector per wavefront --
+// a quad's four lanes own four different neighbours / kernel points, so every 16-byte gather or scatter instruction
+// is split into 16 wavefronts -- while issue slots, the tensor pipe, L2 and HBM idle.  These variants take the global
+// traffic off the LSU: a warp's neighbour rows (256 B = 64 channels each) arrive in shared memory through
+// cp.async.bulk (completion on a per-warp mbarrier, double buffered over the warp's (anchor, channel-block) items),
+// the fragments are read from / written to padded shared rows with conflict-free 16-byte accesses (4 wavefronts per
+// instruction), and the results leave through cp.async.bulk stores (forward: 24 rows of G) or cp.reduce.async.bulk
+// .add.f32 (backward: one row per neighbour -- the scatter-add runs in the L2, no per-lane atomics).
+constexpr int IGT_WARPS = 4;           // 60 anchors = 15 per warp
+constexpr int IGT_CB = 64;             // channels per item
+constexpr int IGT_LD = IGT_CB + 4;     // padded row (floats): fragment accesses of a quarter warp hit 32 distinct banks
+
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_add_f32(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float4 lds128(const float* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ void sts128(float* p, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// shared prologue of the two kernels: neighbour offsets / row offsets of point (b, pi) for the whole CTA
+template <int KS>
+__device__ __forceinline__ void igt_neighbourhood(int b, int pi, int n, int p, int nn, int a, int ci, const float* xyz,
+                                                  const float* sxyz, const int32_t* idx, float* s_g, uint32_t* s_off) {
+    const float* X = xyz + (size_t)b * 3 * n;
+    const float* S = sxyz + (size_t)b * 3 * p;
+    for (int i = threadIdx.x; i < 16 * KS; i += blockDim.x) {
+        if (i < nn) {
+            const int j = idx[((size_t)b * p + pi) * nn + i];
+            s_off[i] = (uint32_t)j * (uint32_t)(a * ci);
+            s_g[i * 3 + 0] = X[j] - S[pi];
+            s_g[i * 3 + 1] = X[n + j] - S[p + pi];
+            s_g[i * 3 + 2] = X[2 * n + j] - S[2 * p + pi];
+        } else {
+            s_off[i] = 0;
+            s_g[i * 3 + 0] = s_g[i * 3 + 1] = s_g[i * 3 + 2] = 1e12f;
+        }
+    }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(IGT_WARPS * 32)
+inter_group_fwd_tma_kernel(int n, int p, int nn, int a, int k, int ci, const float* __restrict__ xyz,
+                           const float* __restrict__ sxyz, const int32_t* __restrict__ idx,
+                           const float* __restrict__ rk, float inv_sigma, const float* __restrict__ feats,
+                           float* __restrict__ grouped) {
+    constexpr int NNP = 16 * KS;
+    constexpr int IN_FLOATS = NNP * IGT_LD, OUT_FLOATS = 24 * IGT_LD, WARP_FLOATS = 2 * IN_FLOATS + OUT_FLOATS;
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float s_g[NNP * 3];
+    __shared__ uint32_t s_off[NNP];
+    __shared__ __align__(8) uint64_t s_bar[IGT_WARPS][2];
+    const int pi = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    float* inb = smem + warp * WARP_FLOATS;             // [2][NNP][IGT_LD]
+    float* outb = inb + 2 * IN_FLOATS;                  // [24][IGT_LD]
+    igt_neighbourhood<KS>(b, pi, n, p, nn, a, ci, xyz, sxyz, idx, s_g, s_off);
+    for (int i = lane; i < 2 * IN_FLOATS; i += 32) inb[i] = 0.f;      // rows >= nn are never loaded: 0 * weight 0
+    if (lane == 0) {
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
+        fence_barrier_init();
+    }
+    fence_proxy_async();
+    __syncthreads();
+    float gx[KS][4], gy[KS][4], gz[KS][4];
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ni = 16 * s + 2 * tig + (j & 1) + 8 * (j >> 1);
+            gx[s][j] = s_g[ni * 3];
+            gy[s][j] = s_g[ni * 3 + 1];
+            gz[s][j] = s_g[ni * 3 + 2];
+        }
+    const uint32_t my_off = lane < nn ? s_off[lane] : 0u;              // lane <-> neighbour row it fetches
+    const float* fb = feats + (size_t)b * n * a * ci;
+    const int cbs = ci / IGT_CB;
+    const int my_anchors = (a - warp + IGT_WARPS - 1) / IGT_WARPS;      // anchors warp, warp + 4, ...
+    const int items = my_anchors * cbs;                                // item -> (anchor slot, channel block)
+    auto issue = [&](int item) {
+        const int ai = warp + (item / cbs) * IGT_WARPS, cb = item % cbs, buf = item & 1;
+        if (lane == 0) mbar_arrive_expect_tx(&s_bar[warp][buf], (uint32_t)nn * IGT_CB * 4u);
+        __syncwarp();
+        if (lane < nn)
+            bulk_g2s(inb + buf * IN_FLOATS + lane * IGT_LD, fb + my_off + (size_t)ai * ci + cb * IGT_CB, IGT_CB * 4, &s_bar[warp][buf]);
+    };
+    if (items > 0) issue(0);
+    uint32_t bh[KS][3][2], bl[KS][3][2];
+    for (int item = 0; item < items; ++item) {
+        const int ai = warp + (item / cbs) * IGT_WARPS, cb = item % cbs, buf = item & 1;
+        if (item + 1 < items) issue(item + 1);          // its buffer was read two items ago (program order + __syncwarp)
+        if (cb == 0) {
+            // ---- B fragments of this anchor (weights), computed in registers, hi / lo
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int kp = 8 * t + gid;
+                const bool live = kp < k;
+                float kx = 0.f, ky = 0.f, kz = 0.f;
+                if (live) {
+                    const float* q = rk + (ai * k + kp) * 3;
+                    kx = __ldg(q);
+                    ky = __ldg(q + 1);
+                    kz = __ldg(q + 2);
+                }
+#pragma unroll
+                for (int s = 0; s < KS; ++s) {
+                    float w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float dx = gx[s][j] - kx, dy = gy[s][j] - ky, dz = gz[s][j] - kz;
+                        const float v = fmaxf(0.f, 1.f - (dx * dx + dy * dy + dz * dz) * inv_sigma);
+                        w[j] = live ? v : 0.f;
+                    }
+                    ig_split2(w[0], w[1], bh[s][t][0], bl[s][t][0]);
+                    ig_split2(w[2], w[3], bh[s][t][1], bl[s][t][1]);
+                }
+            }
+        }
+        mbar_wait(&s_bar[warp][buf], (uint32_t)(item >> 1) & 1u);
+        const float* in = inb + buf * IN_FLOATS;
+        // the previous item's bulk stores must have finished READING the staging rows before they are rewritten
+        if (lane < 24) bulk_wait_read_all();
+        __syncwarp();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int c0 = half * 32 + 4 * gid;
+            float d[2][3][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) d[m][t][e] = 0.f;
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                float4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = lds128(in + (16 * s + 2 * tig + (j & 1) + 8 * (j >> 1)) * IGT_LD + c0);
+                uint32_t ah[2][4], al[2][4];
+                ig_split2(v[0].x, v[1].x, ah[0][0], al[0][0]);
+                ig_split2(v[0].y, v[1].y, ah[0][1], al[0][1]);
+                ig_split2(v[2].x, v[3].x, ah[0][2], al[0][2]);
+                ig_split2(v[2].y, v[3].y, ah[0][3], al[0][3]);
+                ig_split2(v[0].z, v[1].z, ah[1][0], al[1][0]);
+                ig_split2(v[0].w, v[1].w, ah[1][1], al[1][1]);
+                ig_split2(v[2].z, v[3].z, ah[1][2], al[1][2]);
+                ig_split2(v[2].w, v[3].w, ah[1][3], al[1][3]);
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        ig_mma(d[m][t], al[m], bh[s][t][0], bh[s][t][1]);
+                        ig_mma(d[m][t], ah[m], bl[s][t][0], bl[s][t][1]);
+                        ig_mma(d[m][t], ah[m], bh[s][t][0], bh[s][t][1]);
+                    }
+            }
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int kp = 8 * t + 2 * tig;
+                sts128(outb + kp * IGT_LD + c0, d[0][t][0], d[0][t][2], d[1][t][0], d[1][t][2]);
+                sts128(outb + (kp + 1) * IGT_LD + c0, d[0][t][1], d[0][t][3], d[1][t][1], d[1][t][3]);
+            }
+        }
+        fence_proxy_async();                             // staging rows -> visible to the bulk-copy engine
+        __syncwarp();
+        if (lane < k) {                                  // one 256-byte row of G per kernel point
+            float* out = grouped + ((((size_t)b * p + pi) * a + ai) * (size_t)k + lane) * ci + cb * IGT_CB;
+            bulk_s2g(out, outb + lane * IGT_LD, IGT_CB * 4);
+        }
+        bulk_commit();
+    }
+    bulk_wait_all();                                     // smem must outlive the last stores
+}
+
+template <int KS>
+__global__ void __launch_bounds__(IGT_WARPS * 32)
+inter_group_bwd_tma_kernel(int n, int p, int nn, int a, int k, int ci, const float* __restrict__ xyz,
+                           const float* __restrict__ sxyz, const int32_t* __restrict__ idx,
+                           const float* __restrict__ rk, float inv_sigma, const float* __restrict__ ggrouped,
+                           float* __restrict__ gfeats) {
+    constexpr int NNP = 16 * KS, NT = 2 * KS;
+    constexpr int IN_FLOATS = 24 * IGT_LD, OUT_FLOATS = NNP * IGT_LD, WARP_FLOATS = 2 * IN_FLOATS + OUT_FLOATS;
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float s_g[NNP * 3];
+    __shared__ uint32_t s_off[NNP];
+    __shared__ __align__(8) uint64_t s_bar[IGT_WARPS][2];
+    const int pi = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    float* inb = smem + warp * WARP_FLOATS;             // [2][24][IGT_LD]  dG rows
+    float* outb = inb + 2 * IN_FLOATS;                  // [NNP][IGT_LD]    dF rows, one per neighbour
+    igt_neighbourhood<KS>(b, pi, n, p, nn, a, ci, xyz, sxyz, idx, s_g, s_off);
+    for (int i = lane; i < 2 * IN_FLOATS; i += 32) inb[i] = 0.f;      // kernel-point rows >= k stay zero
+    if (lane == 0) {
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
+        fence_barrier_init();
+    }
+    fence_proxy_async();
+    __syncthreads();
+    float gx[NT], gy[NT], gz[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        gx[t] = s_g[(8 * t + gid) * 3];
+        gy[t] = s_g[(8 * t + gid) * 3 + 1];
+        gz[t] = s_g[(8 * t + gid) * 3 + 2];
+    }
+    const uint32_t my_off = lane < nn ? s_off[lane] : 0u;              // lane <-> neighbour row it scatters
+    int kps[6];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) kps[j] = 2 * tig + (j & 1) + 8 * (j >> 1);
+    kps[4] = 16 + 2 * tig;
+    kps[5] = 17 + 2 * tig;
+    float* gb = gfeats + (size_t)b * n * a * ci;
+    const int cbs = ci / IGT_CB;
+    const int my_anchors = (a - warp + IGT_WARPS - 1) / IGT_WARPS;
+    const int items = my_anchors * cbs;
+    auto issue = [&](int item) {
+        const int ai = warp + (item / cbs) * IGT_WARPS, cb = item % cbs, buf = item & 1;
+        if (lane == 0) mbar_arrive_expect_tx(&s_bar[warp][buf], (uint32_t)k * IGT_CB * 4u);
+        __syncwarp();
+        if (lane < k)
+            bulk_g2s(inb + buf * IN_FLOATS + lane * IGT_LD,
+                     ggrouped + ((((size_t)b * p + pi) * a + ai) * (size_t)k + lane) * ci + cb * IGT_CB, IGT_CB * 4,
+                     &s_bar[warp][buf]);
+    };
+    if (items > 0) issue(0);
+    uint32_t bh[NT][3], bl[NT][3];
+    for (int item = 0; item < items; ++item) {
+        const int ai = warp + (item / cbs) * IGT_WARPS, cb = item % cbs, buf = item & 1;
+        if (item + 1 < items) issue(item + 1);
+        if (cb == 0) {
+            float kx[6], ky[6], kz[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                kx[j] = ky[j] = kz[j] = 1e12f;
+                if (kps[j] < k) {
+                    const float* q = rk + (ai * k + kps[j]) * 3;
+                    kx[j] = __ldg(q);
+                    ky[j] = __ldg(q + 1);
+                    kz[j] = __ldg(q + 2);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                float w[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const float dx = gx[t] - kx[j], dy = gy[t] - ky[j], dz = gz[t] - kz[j];
+                    const float v = fmaxf(0.f, 1.f - (dx * dx + dy * dy + dz * dz) * inv_sigma);
+                    w[j] = (kps[j] < k && 8 * t + gid < nn) ? v : 0.f;
+                }
+                ig_split2(w[0], w[1], bh[t][0], bl[t][0]);
+                ig_split2(w[2], w[3], bh[t][1], bl[t][1]);
+                ig_split2(w[4], w[5], bh[t][2], bl[t][2]);
+            }
+        }
+        mbar_wait(&s_bar[warp][buf], (uint32_t)(item >> 1) & 1u);
+        const float* in = inb + buf * IN_FLOATS;
+        if (lane < nn) bulk_wait_read_all();            // previous item's reduce-adds have read the staging rows
+        __syncwarp();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int c0 = half * 32 + 4 * gid;
+            float4 v[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) v[j] = lds128(in + kps[j] * IGT_LD + c0);
+            uint32_t ah[2][6], al[2][6];
+            ig_split2(v[0].x, v[1].x, ah[0][0], al[0][0]);
+            ig_split2(v[0].y, v[1].y, ah[0][1], al[0][1]);
+            ig_split2(v[2].x, v[3].x, ah[0][2], al[0][2]);
+            ig_split2(v[2].y, v[3].y, ah[0][3], al[0][3]);
+            ig_split2(v[4].x, v[5].x, ah[0][4], al[0][4]);
+            ig_split2(v[4].y, v[5].y, ah[0][5], al[0][5]);
+            ig_split2(v[0].z, v[1].z, ah[1][0], al[1][0]);
+            ig_split2(v[0].w, v[1].w, ah[1][1], al[1][1]);
+            ig_split2(v[2].z, v[3].z, ah[1][2], al[1][2]);
+            ig_split2(v[2].w, v[3].w, ah[1][3], al[1][3]);
+            ig_split2(v[4].z, v[5].z, ah[1][4], al[1][4]);
+            ig_split2(v[4].w, v[5].w, ah[1][5], al[1][5]);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                float d[2][4];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) d[m][e] = 0.f;
+                    const uint32_t h16[4] = {ah[m][0], ah[m][1], ah[m][2], ah[m][3]};
+                    const uint32_t l16[4] = {al[m][0], al[m][1], al[m][2], al[m][3]};
+                    ig_mma(d[m], l16, bh[t][0], bh[t][1]);
+                    ig_mma(d[m], h16, bl[t][0], bl[t][1]);
+                    ig_mma(d[m], h16, bh[t][0], bh[t][1]);
+                    ig_mma_k8(d[m], al[m][4], al[m][5], bh[t][2]);
+                    ig_mma_k8(d[m], ah[m][4], ah[m][5], bl[t][2]);
+                    ig_mma_k8(d[m], ah[m][4], ah[m][5], bh[t][2]);
+                }
+                const int n0 = 8 * t + 2 * tig;
+                sts128(outb + n0 * IGT_LD + c0, d[0][0], d[0][2], d[1][0], d[1][2]);
+                sts128(outb + (n0 + 1) * IGT_LD + c0, d[0][1], d[0][3], d[1][1], d[1][3]);
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane < nn)                                   // dF row of neighbour `lane`: reduce-add in the L2
+            bulk_s2g_add_f32(gb + my_off + (size_t)ai * ci + cb * IGT_CB, outb + lane * IGT_LD, IGT_CB * 4);
+        bulk_commit();
+    }
+    bulk_wait_all();
+}
+
+// ---------------------------------------------------------------------------------- tensor-map variants (default)
+// Measured: 256-byte cp.async.bulk copies cost ~15 cycles each in the copy engine, so the all-bulk kernels above are
+// slower than the register gathers.  These keep the register path for the scattered side (neighbour rows forward,
+// red.global.add backward) and move only the CONTIGUOUS side -- the G / dG block of one (point, anchor, 32 channels):
+// k rows of 128 bytes -- through ONE 2-D tensor-map copy (3 KB) into / out of a 128B-swizzled staging tile, which the
+// fragment accesses hit conflict free (chunk = gid ^ (row & 7)).  LSU wavefronts per step drop by ~45 %.
+template <int KS>
+__global__ void __launch_bounds__(IG_WARPS * 32, 2)
+inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p, int nn, int a, int k, int ci,
+                              const float* __restrict__ xyz, const float* __restrict__ sxyz, const int32_t* __restrict__ idx,
+                              const float* __restrict__ rk, float inv_sigma, const float* __restrict__ feats) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ float s_g[16 * KS * 3];
+    __shared__ uint32_t s_off[16 * KS];
+    const int pi = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    // per warp: two staging tiles [24 rows][128 B], 1024-byte aligned (swizzle atom = 8 rows x 128 B)
+    float* stage = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)) + warp * (2 * 24 * 32);
+    igt_neighbourhood<KS>(b, pi, n, p, nn, a, ci, xyz, sxyz, idx, s_g, s_off);
+    if (threadIdx.x == 0) tma_prefetch_desc(&map_g);
+    __syncthreads();
+    float gx[KS][4], gy[KS][4], gz[KS][4];
+    uint32_t off[KS][4];
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ni = 16 * s + 2 * tig + (j & 1) + 8 * (j >> 1);
+            gx[s][j] = s_g[ni * 3];
+            gy[s][j] = s_g[ni * 3 + 1];
+            gz[s][j] = s_g[ni * 3 + 2];
+            off[s][j] = s_off[ni];
+        }
+    const float* fb = feats + (size_t)b * n * a * ci + 4 * gid;
+    int sb = 0;                                                    // staging tile of the next chunk
+    float4 v[KS][4];                                               // gathered neighbour rows of the chunk in flight
+    for (int ai = warp; ai < a; ai += IG_WARPS) {
+        uint32_t bh[KS][3][2], bl[KS][3][2];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int kp = 8 * t + gid;
+            const bool live = kp < k;
+            float kx = 0.f, ky = 0.f, kz = 0.f;
+            if (live) {
+                const float* q = rk + (ai * k + kp) * 3;
+                kx = __ldg(q);
+                ky = __ldg(q + 1);
+                kz = __ldg(q + 2);
+            }
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                float w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float dx = gx[s][j] - kx, dy = gy[s][j] - ky, dz = gz[s][j] - kz;
+                    const float v = fmaxf(0.f, 1.f - (dx * dx + dy * dy + dz * dz) * inv_sigma);
+                    w[j] = live ? v : 0.f;
+                }
+                ig_split2(w[0], w[1], bh[s][t][0], bl[s][t][0]);
+                ig_split2(w[2], w[3], bh[s][t][1], bl[s][t][1]);
+            }
+        }
+        const int row0 = (((b * p + pi) * a) + ai) * k;            // first row of this (point, anchor) in G [rows, ci]
+        const float* fa = fb + (size_t)ai * ci;
+        if (ai == warp) {                                          // first chunk of the warp; later ones are prefetched
+#pragma unroll
+            for (int s = 0; s < KS; ++s)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[s][j] = __ldg(reinterpret_cast<const float4*>(fa + off[s][j]));
+        }
+        for (int c0 = 0; c0 < ci; c0 += 32, sb ^= 1) {
+            uint32_t ah[KS][2][4], al[KS][2][4];
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                ig_split2(v[s][0].x, v[s][1].x, ah[s][0][0], al[s][0][0]);
+                ig_split2(v[s][0].y, v[s][1].y, ah[s][0][1], al[s][0][1]);
+                ig_split2(v[s][2].x, v[s][3].x, ah[s][0][2], al[s][0][2]);
+                ig_split2(v[s][2].y, v[s][3].y, ah[s][0][3], al[s][0][3]);
+                ig_split2(v[s][0].z, v[s][1].z, ah[s][1][0], al[s][1][0]);
+                ig_split2(v[s][0].w, v[s][1].w, ah[s][1][1], al[s][1][1]);
+                ig_split2(v[s][2].z, v[s][3].z, ah[s][1][2], al[s][1][2]);
+                ig_split2(v[s][2].w, v[s][3].w, ah[s][1][3], al[s][1][3]);
+            }
+            {   // prefetch the next chunk (same anchor, or the first chunk of the warp's next anchor): the barriers of the
+                // store sequence below would otherwise keep these loads from overlapping it
+                const bool more_c = c0 + 32 < ci;
+                const float* nf = more_c ? fa + c0 + 32 : fa + (size_t)IG_WARPS * ci;
+                if (more_c || ai + IG_WARPS < a) {
+#pragma unroll
+                    for (int s = 0; s < KS; ++s)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[s][j] = __ldg(reinterpret_cast<const float4*>(nf + off[s][j]));
+                }
+            }
+            float d[2][3][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) d[m][t][e] = 0.f;
+#pragma unroll
+            for (int s = 0; s < KS; ++s)
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        ig_mma(d[m][t], al[s][m], bh[s][t][0], bh[s][t][1]);
+                        ig_mma(d[m][t], ah[s][m], bl[s][t][0], bl[s][t][1]);
+                        ig_mma(d[m][t], ah[s][m], bh[s][t][0], bh[s][t][1]);
+                    }
+            // the store that used this staging tile two chunks ago must have read it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+            float* st = stage + sb * (24 * 32);
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int kp = 8 * t + 2 * tig;
+                sts128(st + kp * 32 + ((gid ^ (kp & 7)) << 2), d[0][t][0], d[0][t][2], d[1][t][0], d[1][t][2]);
+                sts128(st + (kp + 1) * 32 + ((gid ^ ((kp + 1) & 7)) << 2), d[0][t][1], d[0][t][3], d[1][t][1], d[1][t][3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&map_g, st, c0, row0);                // k rows x 128 B (box rows = k)
+                bulk_commit();
+            }
+        }
+    }
+    if (lane == 0) bulk_wait_all();
+}
+
+template <int KS>
+__global__ void __launch_bounds__(IG_WARPS * 32, 2)
+inter_group_bwd_mma_tl_kernel(const __grid_constant__ TmaMap map_dg, int n, int p, int nn, int a, int k, int ci,
+                              const float* __restrict__ xyz, const float* __restrict__ sxyz, const int32_t* __restrict__ idx,
+                              const float* __restrict__ rk, float inv_sigma, float* __restrict__ gfeats) {
+    constexpr int NT = 2 * KS;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ float s_g[16 * KS * 3];
+    __shared__ uint32_t s_off[16 * KS];
+    __shared__ __align__(8) uint64_t s_bar[IG_WARPS][2];
+    const int pi = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    float* stage = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)) + warp * (2 * 24 * 32);
+    igt_neighbourhood<KS>(b, pi, n, p, nn, a, ci, xyz, sxyz, idx, s_g, s_off);
+    for (int i = lane; i < 2 * 24 * 32; i += 32) stage[i] = 0.f;    // rows >= k are never loaded
+    if (lane == 0) {
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
+        fence_barrier_init();
+    }
+    if (threadIdx.x == 0) tma_prefetch_desc(&map_dg);
+    fence_proxy_async();
+    __syncthreads();
+    float gx[NT], gy[NT], gz[NT];
+    uint32_t off[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        gx[t] = s_g[(8 * t + gid) * 3];
+        gy[t] = s_g[(8 * t + gid) * 3 + 1];
+        gz[t] = s_g[(8 * t + gid) * 3 + 2];
+        off[t][0] = s_off[8 * t + 2 * tig];
+        off[t][1] = s_off[8 * t + 2 * tig + 1];
+    }
+    int kps[6];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) kps[j] = 2 * tig + (j & 1) + 8 * (j >> 1);
+    kps[4] = 16 + 2 * tig;
+    kps[5] = 17 + 2 * tig;
+    float* gb = gfeats + (size_t)b * n * a * ci + 4 * gid;
+    const int chunks = ci / 32;
+    const int my_anchors = (a - warp + IG_WARPS - 1) / IG_WARPS;
+    const int items = my_anchors * chunks;                          // item -> (anchor slot, 32-channel chunk)
+    auto issue = [&](int item) {
+        if (lane == 0) {
+            const int ai = warp + (item / chunks) * IG_WARPS, c0 = (item % chunks) * 32, buf = item & 1;
+            mbar_arrive_expect_tx(&s_bar[warp][buf], (uint32_t)k * 128u);
+            tma_load_2d(stage + buf * (24 * 32), &map_dg, c0, (((b * p + pi) * a) + ai) * k, &s_bar[warp][buf]);
+        }
+    };
+    if (items > 0) issue(0);
+    uint32_t bh[NT][3], bl[NT][3];
+    for (int item = 0; item < items; ++item) {
+        const int ai = warp + (item / chunks) * IG_WARPS, c0 = (item % chunks) * 32, buf = item & 1;
+        __syncwarp();                                   // every lane is done reading the tile the next load overwrites
+        if (item + 1 < items) issue(item + 1);
+        if (c0 == 0) {
+            float kx[6], ky[6], kz[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                kx[j] = ky[j] = kz[j] = 1e12f;
+                if (kps[j] < k) {
+                    const float* q = rk + (ai * k + kps[j]) * 3;
+                    kx[j] = __ldg(q);
+                    ky[j] = __ldg(q + 1);
+                    kz[j] = __ldg(q + 2);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                float w[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const float dx = gx[t] - kx[j], dy = gy[t] - ky[j], dz = gz[t] - kz[j];
+                    const float v = fmaxf(0.f, 1.f - (dx * dx + dy * dy + dz * dz) * inv_sigma);
+                    w[j] = (kps[j] < k && 8 * t + gid < nn) ? v : 0.f;
+                }
+                ig_split2(w[0], w[1], bh[t][0], bl[t][0]);
+                ig_split2(w[2], w[3], bh[t][1], bl[t][1]);
+                ig_split2(w[4], w[5], bh[t][2], bl[t][2]);
+            }
+        }
+        mbar_wait(&s_bar[warp][buf], (uint32_t)(item >> 1) & 1u);
+        const float* in = stage + buf * (24 * 32);
+        float4 v[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v[j] = lds128(in + kps[j] * 32 + ((gid ^ (kps[j] & 7)) << 2));
+        uint32_t ah[2][6], al[2][6];
+        ig_split2(v[0].x, v[1].x, ah[0][0], al[0][0]);
+        ig_split2(v[0].y, v[1].y, ah[0][1], al[0][1]);
+        ig_split2(v[2].x, v[3].x, ah[0][2], al[0][2]);
+        ig_split2(v[2].y, v[3].y, ah[0][3], al[0][3]);
+        ig_split2(v[4].x, v[5].x, ah[0][4], al[0][4]);
+        ig_split2(v[4].y, v[5].y, ah[0][5], al[0][5]);
+        ig_split2(v[0].z, v[1].z, ah[1][0], al[1][0]);
+        ig_split2(v[0].w, v[1].w, ah[1][1], al[1][1]);
+        ig_split2(v[2].z, v[3].z, ah[1][2], al[1][2]);
+        ig_split2(v[2].w, v[3].w, ah[1][3], al[1][3]);
+        ig_split2(v[4].z, v[5].z, ah[1][4], al[1][4]);
+        ig_split2(v[4].w, v[5].w, ah[1][5], al[1][5]);
+        float* ga = gb + (size_t)ai * ci + c0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            float d[2][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) d[m][e] = 0.f;
+                const uint32_t h16[4] = {ah[m][0], ah[m][1], ah[m][2], ah[m][3]};
+                const uint32_t l16[4] = {al[m][0], al[m][1], al[m][2], al[m][3]};
+                ig_mma(d[m], l16, bh[t][0], bh[t][1]);
+                ig_mma(d[m], h16, bl[t][0], bl[t][1]);
+                ig_mma(d[m], h16, bh[t][0], bh[t][1]);
+                ig_mma_k8(d[m], al[m][4], al[m][5], bh[t][2]);
+                ig_mma_k8(d[m], ah[m][4], ah[m][5], bl[t][2]);
+                ig_mma_k8(d[m], ah[m][4], ah[m][5], bh[t][2]);
+            }
+            const int n0 = 8 * t + 2 * tig;
+            if (n0 < nn) atomicAdd(reinterpret_cast<float4*>(ga + off[t][0]), make_float4(d[0][0], d[0][2], d[1][0], d[1][2]));
+            if (n0 + 1 < nn) atomicAdd(reinterpret_cast<float4*>(ga + off[t][1]), make_float4(d[0][1], d[0][3], d[1][1], d[1][3]));
         }
     }
 }
@@ -722,6 +1308,40 @@ extern "C" int vgtkb_inter_group_forward(int b, int n, int p, int nn, int a, int
     if (b == 0 || p == 0) return VGTKB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool al = aligned16(feats) && aligned16(grouped);
+    // VGTKB_GROUP_TMA: 2 (default) = register gathers + tensor-map store of G, 1 = all-bulk variant, 0 = registers only
+    static const int use_tma = getenv("VGTKB_GROUP_TMA") ? atoi(getenv("VGTKB_GROUP_TMA")) : 2;
+    const int64_t g_rows = (int64_t)b * p * a * k;
+    if (use_tma == 2 && mode == 3 && k <= 24 && nn <= 32 && ci % 32 == 0 && al && (int64_t)n * a * ci < ((int64_t)1 << 32) &&
+        g_rows < ((int64_t)1 << 31)) {
+        TmaMap map;
+        if (make_rows_map(&map, grouped, g_rows, ci, k) == VGTKB_OK) {
+            const size_t smem = (size_t)IG_WARPS * 2 * 24 * 128 + 1024;
+            if (nn <= 16) {
+                VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_mma_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                inter_group_fwd_mma_ts_kernel<1><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(map, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
+                                                                                          rot_kernels, 1.0f / sigma, feats);
+            } else {
+                VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_mma_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                inter_group_fwd_mma_ts_kernel<2><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(map, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
+                                                                                          rot_kernels, 1.0f / sigma, feats);
+            }
+            return check_launch("inter_group_forward(mma, tensor-map store)");
+        }
+    }
+    if (use_tma == 1 && mode == 3 && k <= 24 && nn <= 32 && ci % IGT_CB == 0 && al && (int64_t)n * a * ci < ((int64_t)1 << 32)) {
+        const int ks = nn <= 16 ? 1 : 2;
+        const size_t smem = (size_t)IGT_WARPS * (2 * 16 * ks + 24) * IGT_LD * sizeof(float);
+        if (ks == 1) {
+            VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            inter_group_fwd_tma_kernel<1><<<dim3(p, b), IGT_WARPS * 32, smem, st>>>(n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels,
+                                                                                    1.0f / sigma, feats, grouped);
+        } else {
+            VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            inter_group_fwd_tma_kernel<2><<<dim3(p, b), IGT_WARPS * 32, smem, st>>>(n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels,
+                                                                                    1.0f / sigma, feats, grouped);
+        }
+        return check_launch("inter_group_forward(mma+tma)");
+    }
     if (mode == 3 && k <= 24 && nn <= 32 && ci % 32 == 0 && al && (int64_t)n * a * ci < ((int64_t)1 << 32)) {
         if (nn <= 16)
             inter_group_fwd_mma_kernel<1><<<dim3(p, b), IG_WARPS * 32, 0, st>>>(n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels,
@@ -753,6 +1373,39 @@ extern "C" int vgtkb_inter_group_backward(int b, int n, int p, int nn, int a, in
     if (b == 0 || p == 0) return VGTKB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool al = aligned16(grad_feats) && aligned16(grad_grouped);
+    static const int use_tma = getenv("VGTKB_GROUP_TMA") ? atoi(getenv("VGTKB_GROUP_TMA")) : 2;
+    const int64_t g_rows = (int64_t)b * p * a * k;
+    if (use_tma == 2 && mode == 3 && k <= 24 && nn <= 32 && ci % 32 == 0 && al && (int64_t)n * a * ci < ((int64_t)1 << 32) &&
+        g_rows < ((int64_t)1 << 31)) {
+        TmaMap map;
+        if (make_rows_map(&map, grad_grouped, g_rows, ci, k) == VGTKB_OK) {
+            const size_t smem = (size_t)IG_WARPS * 2 * 24 * 128 + 1024;
+            if (nn <= 16) {
+                VGTKB_CUDA(cudaFuncSetAttribute(inter_group_bwd_mma_tl_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                inter_group_bwd_mma_tl_kernel<1><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(map, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
+                                                                                          rot_kernels, 1.0f / sigma, grad_feats);
+            } else {
+                VGTKB_CUDA(cudaFuncSetAttribute(inter_group_bwd_mma_tl_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                inter_group_bwd_mma_tl_kernel<2><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(map, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
+                                                                                          rot_kernels, 1.0f / sigma, grad_feats);
+            }
+            return check_launch("inter_group_backward(mma, tensor-map load)");
+        }
+    }
+    if (use_tma == 1 && mode == 3 && k <= 24 && nn <= 32 && ci % IGT_CB == 0 && al && (int64_t)n * a * ci < ((int64_t)1 << 32)) {
+        const int ks = nn <= 16 ? 1 : 2;
+        const size_t smem = (size_t)IGT_WARPS * (2 * 24 + 16 * ks) * IGT_LD * sizeof(float);
+        if (ks == 1) {
+            VGTKB_CUDA(cudaFuncSetAttribute(inter_group_bwd_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            inter_group_bwd_tma_kernel<1><<<dim3(p, b), IGT_WARPS * 32, smem, st>>>(n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels,
+                                                                                    1.0f / sigma, grad_grouped, grad_feats);
+        } else {
+            VGTKB_CUDA(cudaFuncSetAttribute(inter_group_bwd_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            inter_group_bwd_tma_kernel<2><<<dim3(p, b), IGT_WARPS * 32, smem, st>>>(n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels,
+                                                                                    1.0f / sigma, grad_grouped, grad_feats);
+        }
+        return check_launch("inter_group_backward(mma+tma)");
+    }
     if (mode == 3 && k <= 24 && nn <= 32 && ci % 32 == 0 && al && (int64_t)n * a * ci < ((int64_t)1 << 32)) {
         if (nn <= 16)
             inter_group_bwd_mma_kernel<1><<<dim3(p, b), IG_WARPS * 32, 0, st>>>(n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels,

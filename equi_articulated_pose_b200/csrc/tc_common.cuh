@@ -162,6 +162,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// opaque CUtensorMap (128 bytes, 64-byte aligned) for translation units that do not include <cuda.h>; passed to kernels
+// as `const __grid_constant__ TmaMap`.  make_rows_map (gemm_tc.cu): row-major fp32 matrix [rows, cols], box = [box_rows, 32
+// floats = 128 bytes], 128-byte swizzle.
+struct alignas(64) TmaMap {
+    unsigned char bytes[128];
+};
+int make_rows_map(TmaMap* out, const void* base, int64_t rows, int64_t cols, int box_rows);
+
 // ---- TMA 2-D tile load (tensor map in kernel parameter space) ----------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int crd_inner, int crd_outer, uint64_t* bar) {
     asm volatile(
@@ -176,6 +184,12 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, in
             smem_u32(smem_dst)),
         "l"(tmap), "r"(smem_u32(bar)), "r"(crd0), "r"(crd1), "r"(crd2)
         : "memory");
+}
+// 2-D tile store shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int crd_inner, int crd_outer) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
+                 "r"(smem_u32(smem_src)), "r"(crd_inner), "r"(crd_outer)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
