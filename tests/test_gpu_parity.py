@@ -717,3 +717,49 @@ def test_pointnet_head_backbone_size_vs_oracle(dev):
         closer than the fp32 rounding of the embedding may pick the other point (a handful of 61440 maxima)"""
         return float(((got.detach().cpu().double() - want).abs() > FP32_TOL * float(want.abs().max())).double().mean())
     assert flipped(fd.grad, f64.grad) < 1e-3 and flipped(xd.grad, x64.grad) < 2e-2
+
+
+# ------------------------------------------------------------------------------ grouping: tensor-core variants
+@pytest.mark.parametrize("b,n,p,nn,ci,k", [
+    (2, 128, 128, 16, 64, 24),      # stride-1 layer shape, one k-step
+    (2, 200, 100, 32, 128, 24),     # stride-2 layer shape, two k-steps
+    (1, 90, 90, 7, 32, 24),         # fewer neighbours than one k-step: padded slots carry weight 0
+    (2, 150, 75, 17, 96, 24),       # nn just above one k-step, Ci = 3 chunks
+    (1, 64, 64, 12, 160, 13),       # fewer kernel points than 24: tensor-map box of 13 rows
+    (3, 256, 128, 32, 256, 24),
+])
+def test_inter_group_mma_variants_match_fp32_kernel(dev, b, n, p, nn, ci, k):
+    """mode 3 (warp-level bf16x3 MMAs, tensor-map store / load) against mode 0 (exact fp32 FFMA kernel), forward and
+    backward, through the C ABI; and against the oracle's torch restatement on the smallest case."""
+    from equi_articulated_pose_b200 import ops, so3_constants as C
+    from equi_articulated_pose_b200.lib import call, ptr
+    from oracle import so3 as O
+    g = torch.Generator().manual_seed(100 + nn + ci)
+    anchors = torch.from_numpy(np.ascontiguousarray(C.get_anchors(60))).float()
+    xyz = O.synthetic_cloud(b, n, 5 + n).permute(0, 2, 1).contiguous().to(dev)
+    sxyz = xyz[:, :, :p].contiguous()
+    radius, sigma = 0.45, 0.1
+    idx = ops.ball_query(sxyz, xyz, radius, nn)
+    base = torch.randn(k, 3, generator=g)
+    base = base / base.norm(dim=1, keepdim=True) * torch.rand(k, 1, generator=g) * 0.7 * radius
+    rk = torch.einsum('aij,kj->aki', anchors, base).contiguous().to(dev)
+    feats = torch.randn(b, n, 60, ci, generator=g).to(dev)
+    dg = torch.randn(b, p, 60, k * ci, generator=g).to(dev)
+    out, gin = {}, {}
+    for mode in (0, 3):
+        gg = torch.full((b, p, 60, k * ci), float('nan'), device=dev)
+        call("vgtkb_inter_group_forward", dev, b, n, p, nn, 60, k, ci, ptr(xyz), ptr(sxyz), ptr(idx), ptr(rk), sigma, ptr(feats),
+             ptr(gg), mode)
+        gx = torch.zeros(b, n, 60, ci, device=dev)
+        call("vgtkb_inter_group_backward", dev, b, n, p, nn, 60, k, ci, ptr(xyz), ptr(sxyz), ptr(idx), ptr(rk), sigma, ptr(dg),
+             ptr(gx), mode)
+        out[mode], gin[mode] = gg, gx
+    assert torch.isfinite(out[3]).all()
+    assert rel_err(out[3], out[0]) < 3e-5 and rel_err(gin[3], gin[0]) < 3e-5
+    if nn == 7:     # tie the fp32 kernel itself to the oracle's restatement of the reference einsum
+        gxyz = torch.gather(xyz.cpu(), 2, idx.cpu().long().view(b, 1, p * nn).expand(b, 3, p * nn)).view(b, 3, p, nn) \
+            - sxyz.cpu().unsqueeze(-1)
+        w = torch.relu(1.0 - ((gxyz[:, :, :, None, None, :] - rk.cpu().permute(2, 0, 1)[None, :, None, :, :, None]) ** 2).sum(1) / sigma)
+        f = feats.cpu()[torch.arange(b)[:, None, None], idx.cpu().long()]            # [b,p,nn,a,c]
+        ref = torch.einsum('bpakn,bpnac->bpakc', w, f).reshape(b, p, 60, k * ci)
+        assert rel_err(out[0], ref) < 1e-5

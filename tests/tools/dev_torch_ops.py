@@ -27,13 +27,23 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=False) as prof:
     step()
     torch.cuda.synchronize()
+from torch.autograd import DeviceType
 rows = []
-for e in prof.key_averages(group_by_input_shape=True):
-    t = getattr(e, "device_time_total", 0) or getattr(e, "cuda_time_total", 0)
-    if t > 0 and not e.key.startswith("vgtkb"):
-        rows.append((t, e.count, e.key, str(e.input_shapes)[:110]))
+for e in prof.key_averages():
+    if e.device_type == DeviceType.CUDA:
+        rows.append((e.device_time_total, e.count, e.key))
 rows.sort(reverse=True)
-tot = 0
-for t, c, k, s in rows[:45]:
-    print(f"{t:9.1f} us  n={c:3d}  {k[:60]:60s} {s}")
-print("total listed us:", sum(r[0] for r in rows))
+mine = sum(t for t, c, k in rows if "vgtkb" in k)
+other = [(t, c, k) for t, c, k in rows if "vgtkb" not in k]
+print(f"vgtkb kernels {mine:.0f} us, other kernels {sum(t for t, c, k in other):.0f} us")
+for t, c, k in other[:25]:
+    print(f"{t:9.1f} us  n={c:3d}  {k[:150]}")
+# which autograd / aten ops launch them
+ops = []
+for e in prof.key_averages(group_by_input_shape=True):
+    if e.device_type == DeviceType.CPU and e.self_device_time_total > 0 and not e.key.startswith("vgtkb"):
+        ops.append((e.self_device_time_total, e.count, e.key, str(e.input_shapes)[:100]))
+ops.sort(reverse=True)
+print("---- aten ops by self device time")
+for t, c, k, sh in ops[:30]:
+    print(f"{t:9.1f} us  n={c:3d}  {k[:40]:40s} {sh}")
