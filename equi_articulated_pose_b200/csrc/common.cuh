@@ -7,7 +7,7 @@
 
 #include "../../include/vgtkb.h"
 
-#define VGTKB_ABI_VERSION 8
+#define VGTKB_ABI_VERSION 9
 
 namespace vgtkb {
 

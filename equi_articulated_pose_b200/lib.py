@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgtkb200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _lib = None
 _device_ok = set()
@@ -57,6 +57,14 @@ SIGNATURES = {
     "vgtkb_pointnet_pool_forward": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_pointnet_embed_xyz": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_pointnet_pool_backward": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_knn_query": [c_int] * 4 + [c_vp] * 5,
+    "vgtkb_sa_group_forward": [c_int] * 6 + [c_vp] * 6,
+    "vgtkb_sa_group_backward": [c_int] * 6 + [c_vp] * 4,
+    "vgtkb_sa_maxpool_forward": [c_i64, c_int, c_int, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
+    "vgtkb_sa_maxpool_backward": [c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_three_nn": [c_int] * 3 + [c_vp] * 5,
+    "vgtkb_three_interpolate_forward": [c_int] * 4 + [c_vp] * 5,
+    "vgtkb_three_interpolate_backward": [c_int] * 4 + [c_vp] * 5,
     "vgtkb_peer_allreduce_f64": [c_int, c_vp, c_int, c_int, c_vp, ctypes.c_uint64, c_vp],
     "vgtkb_norm_finalize_peer": [c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_int, c_vp, ctypes.c_uint64, c_vp],
 }

@@ -315,11 +315,12 @@ class LinearFn(torch.autograd.Function):
     """y[M,N] = x[M,K] @ w[N,K]^T + bias  (the BasicSO3Conv contraction / 1x1 skip conv)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias):
+    def forward(ctx, x, w, bias, mode=None):
         x, w = _f32(x), _f32(w)
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
-        return gemm_nt(x, w, bias)
+        ctx.mode = mode
+        return gemm_nt(x, w, bias, mode)
 
     @staticmethod
     def backward(ctx, gy):
@@ -327,12 +328,12 @@ class LinearFn(torch.autograd.Function):
         gy = _f32(gy)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = gemm_nt(gy, w.t().contiguous())
+            gx = gemm_nt(gy, w.t().contiguous(), None, ctx.mode)
         if ctx.needs_input_grad[1]:
-            gw = gemm_tn(gy, x)
+            gw = gemm_tn(gy, x, ctx.mode)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = col_sum(gy)
-        return gx, gw, gb
+        return gx, gw, gb, None
 
 
 class PointnetPoolFn(torch.autograd.Function):
@@ -564,3 +565,131 @@ class ChamferFn(torch.autograd.Function):
         xyz1, xyz2, i1, i2 = ctx.saved_tensors
         gx1, gx2 = chamfer_backward(xyz1, xyz2, i1, i2, g1.contiguous(), g2.contiguous())
         return gx1, gx2
+
+
+# ----------------------------------------------------------------------------- PointNet++ set abstraction
+def knn_query(pos, centers, k):
+    """SPConvNets/models/PointNet2.py:85-87: pos [B,N,3], centers [B,S,3] -> idx int32 [B,S,k], dist [B,S,k]
+    (ascending; dist = sqrt of the squared distance in torch's evaluation order)."""
+    pos, centers = _f32(pos), _f32(centers)
+    b, n, d = pos.shape
+    if d != 3 or centers.shape[2] != 3:
+        raise _lib.VgtkbError("knn_query: 3-D coordinates expected")
+    s = centers.shape[1]
+    idx = torch.empty((b, s, k), dtype=torch.int32, device=pos.device)
+    dist = torch.empty((b, s, k), dtype=torch.float32, device=pos.device)
+    call("vgtkb_knn_query", pos.device, b, n, s, int(k), ptr(pos), ptr(centers), ptr(idx), ptr(dist))
+    return idx, dist
+
+
+def _pad8(c):
+    return (c + 7) // 8 * 8
+
+
+class SaGroupFn(torch.autograd.Function):
+    """rows [B,S,k,cpad] = [pos[idx] - centre | feat[idx] | 0]  (PointNet2.py:92-100; idx None: the identity
+    neighbourhood of the global level :151-156).  Differentiable in feat; coordinates are data."""
+
+    @staticmethod
+    def forward(ctx, feat, pos, centers, idx, cpad):
+        pos = _f32(pos)
+        b, n, _ = pos.shape
+        c = 0 if feat is None else feat.shape[2]
+        feat = _f32(feat) if feat is not None else None
+        if idx is None:
+            s, k = 1, n
+        else:
+            s, k = idx.shape[1], idx.shape[2]
+        out = torch.empty((b, s, k, cpad), dtype=torch.float32, device=pos.device)
+        cen = _f32(centers) if centers is not None else None
+        call("vgtkb_sa_group_forward", pos.device, b, n, s, k, c, int(cpad), ptr(pos), ptr(feat), ptr(cen), ptr(idx), ptr(out))
+        ctx.idx = idx
+        ctx.meta = (b, n, s, k, c, int(cpad))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        b, n, s, k, c, cpad = ctx.meta
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise NotImplementedError("sa_group: gradients with respect to the coordinates are not part of this path")
+        gfeat = None
+        if c > 0 and ctx.needs_input_grad[0]:
+            gout = _f32(gout)
+            gfeat = torch.empty((b, n, c), dtype=torch.float32, device=gout.device)
+            call("vgtkb_sa_group_backward", gout.device, b, n, s, k, c, cpad, ptr(gout), ptr(ctx.idx), ptr(gfeat))
+        return gfeat, None, None, None, None
+
+
+def sa_group(feat, pos, centers, idx, cpad=None):
+    c = 0 if feat is None else feat.shape[2]
+    return SaGroupFn.apply(feat, pos, centers, idx, _pad8(3 + c) if cpad is None else cpad)
+
+
+class SaMaxPoolFn(torch.autograd.Function):
+    """PointNet2.py:102-112: y [G,k,C], dist [G,k] or None, r -> [G,C]; entries beyond the radius count as -1e8."""
+
+    @staticmethod
+    def forward(ctx, y, dist, radius):
+        y = _f32(y)
+        g, k, c = y.shape
+        out = torch.empty((g, c), dtype=torch.float32, device=y.device)
+        arg = torch.empty((g, c), dtype=torch.int32, device=y.device)
+        d = _f32(dist) if (dist is not None and radius is not None) else None
+        call("vgtkb_sa_maxpool_forward", y.device, g, k, c, ptr(y), ptr(d), float(radius) if radius is not None else 0.0,
+             ptr(out), ptr(arg))
+        ctx.save_for_backward(arg)
+        ctx.meta = (g, k, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (arg,) = ctx.saved_tensors
+        g, k, c = ctx.meta
+        gout = _f32(gout)
+        gy = torch.empty((g, k, c), dtype=torch.float32, device=gout.device)
+        call("vgtkb_sa_maxpool_backward", gout.device, g, k, c, ptr(gout), ptr(arg), ptr(gy))
+        return gy, None, None
+
+
+def sa_maxpool(y, dist=None, radius=None):
+    return SaMaxPoolFn.apply(y, dist, radius)
+
+
+def three_nn(p1, p2):
+    """PointNet2.py:114-123: for every point of p2 [B,n2,3] the min(3,n1) nearest points of p1 [B,n1,3] and their
+    normalised inverse-distance weights -> idx int32 [B,n2,3], w [B,n2,3]."""
+    p1, p2 = _f32(p1), _f32(p2)
+    b, n1, _ = p1.shape
+    n2 = p2.shape[1]
+    idx = torch.empty((b, n2, 3), dtype=torch.int32, device=p1.device)
+    w = torch.empty((b, n2, 3), dtype=torch.float32, device=p1.device)
+    call("vgtkb_three_nn", p1.device, b, n1, n2, ptr(p1), ptr(p2), ptr(idx), ptr(w))
+    return idx, w
+
+
+class ThreeInterpolateFn(torch.autograd.Function):
+    """PointNet2.py:126-128: out [B,n2,C] = sum_j feat[b, idx[b,q,j], :] * w[b,q,j]."""
+
+    @staticmethod
+    def forward(ctx, feat, idx, w):
+        feat, w = _f32(feat), _f32(w)
+        b, n1, c = feat.shape
+        n2 = idx.shape[1]
+        out = torch.empty((b, n2, c), dtype=torch.float32, device=feat.device)
+        call("vgtkb_three_interpolate_forward", feat.device, b, n1, n2, c, ptr(feat), ptr(idx), ptr(w), ptr(out))
+        ctx.save_for_backward(idx, w)
+        ctx.meta = (b, n1, n2, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        idx, w = ctx.saved_tensors
+        b, n1, n2, c = ctx.meta
+        gout = _f32(gout)
+        gfeat = torch.empty((b, n1, c), dtype=torch.float32, device=gout.device)
+        call("vgtkb_three_interpolate_backward", gout.device, b, n1, n2, c, ptr(gout), ptr(idx), ptr(w), ptr(gfeat))
+        return gfeat, None, None
+
+
+def three_interpolate(feat, idx, w):
+    return ThreeInterpolateFn.apply(feat, idx, w)

@@ -1,0 +1,165 @@
+"""PointNet++ encoder-decoder `PointnetPP` on the sm_100a kernels -- drop-in for
+SPConvNets/models/PointNet2.py:8-196 (same constructor, attributes, method names, returned tuples and
+state-dict keys `mlp_layers.L.J.{0,1}.*` / `up_mlp_layers.L.J.{0,1}.*`).
+
+What runs where (csrc/pointnet2.cu):
+  * sampling: `vgtkb_fps_plain` (torch_cluster.fps(random_start=False) semantics, model_util.py:183-200)
+  * neighbourhoods: `vgtkb_knn_query` -- the [B,S,N] distance matrix + torch.topk of the reference (:85-87) never exist
+  * gather / centre / concat: `vgtkb_sa_group_forward` writes the operand rows of the first contraction once
+  * the 1x1-conv MLPs (model_util.py:93-118): tcgen05 contraction `vgtkb_gemm_nt` + fused BatchNorm/ReLU passes
+  * `max_pooling_with_r` (:102-112): `vgtkb_sa_maxpool_forward`, radius mask folded in
+  * `interpolate_features` (:114-129): `vgtkb_three_nn` + `vgtkb_three_interpolate_forward`
+There is no CPU path: tensors must live on the GPU.
+
+Gradient note: the reference masks the MLP output IN PLACE before the max (:109), which its own autograd rejects in
+backward (recorded in tests/golden/ref_pointnet2_small.npz).  Here the mask is part of the pooling kernel; masked and
+non-maximal rows receive zero gradient.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops as _ops
+from .blocks import FusedBatchNorm2d
+
+# Contraction arithmetic of the MLPs: 1 = tcgen05 3xTF32 (operands split into a 19-bit head + exact remainder, ~1e-6 per
+# GEMM).  The decoder's first layers see a large per-cloud constant (the interpolated global feature) that BatchNorm then
+# removes, which amplifies operand rounding ~100x: with the backbone's default bf16x3 split (16 significand bits) the
+# output sits at 1e-4..4e-4 of the reference instead of the 3e-5 two fp32 evaluations differ by (measured).
+GEMM_MODE = 1
+
+
+def construct_conv_modules(mlp_dims, n_in, last_act=True, bn=True):
+    """model_util.py:93-118: a ModuleList of Sequential(Conv2d 1x1 [, BatchNorm2d [, ReLU]]) (parameter containers with the
+    reference's names; `_apply_mlp` runs them on the fused kernels)."""
+    blocks = nn.ModuleList()
+    for i, dim in enumerate(mlp_dims):
+        inc, ouc = (n_in if i == 0 else mlp_dims[i - 1]), dim
+        conv = nn.Conv2d(inc, ouc, kernel_size=(1, 1), stride=(1, 1), bias=True)
+        if i < len(mlp_dims) - 1 or last_act:
+            blocks.append(nn.Sequential(conv, FusedBatchNorm2d(ouc, eps=1e-5, momentum=0.1), nn.ReLU()))
+        elif bn:
+            blocks.append(nn.Sequential(conv, FusedBatchNorm2d(ouc, eps=1e-5, momentum=0.1)))
+        else:
+            blocks.append(nn.Sequential(conv))
+    return blocks
+
+
+def _apply_mlp(rows, blocks):
+    """rows [M, C] channels-last -> [M, C'] through Conv2d 1x1 + BatchNorm2d + ReLU blocks (apply_module_with_conv2d_bn,
+    model_util.py:148-156).  Operand rows narrower than the weight are zero padded to the tensor-core granule (8)."""
+    for blk in blocks:
+        conv = blk[0]
+        w = conv.weight.view(conv.out_channels, conv.in_channels)
+        kpad = rows.shape[1]
+        if kpad < conv.in_channels:
+            raise ValueError(f"MLP input has {kpad} channels, the layer expects {conv.in_channels}")
+        if kpad % 8 != 0:
+            extra = (-kpad) % 8
+            rows = F.pad(rows, (0, extra))
+            kpad += extra
+        if kpad > conv.in_channels:
+            w = F.pad(w, (0, kpad - conv.in_channels))
+        rows = _ops.LinearFn.apply(rows, w, conv.bias, GEMM_MODE)
+        if len(blk) > 1:                       # BatchNorm2d (+ ReLU as the slope-0 activation of the same pass)
+            rows = blk[1].forward_rows(rows, 0.0 if len(blk) > 2 else 1.0)
+    return rows
+
+
+class PointnetPP(nn.Module):
+    def __init__(self, in_feat_dim: int, args=None):
+        super().__init__()
+        self.skip_global = False
+        self.n_samples = [512, 128, 1]
+        mlps = [[64, 64, 128], [128, 128, 256], [256, 512, 1024]]
+        mlps_in = [[in_feat_dim, 64, 64], [128 + 3, 128, 128], [256 + 3, 256, 512]]
+        up_mlps = [[256, 256], [256, 128], [128, 128, 128]]
+        up_mlps_in = [1024 + 256, 256 + 128, 128 + in_feat_dim]
+        self.in_feat_dim = in_feat_dim
+        self.radius = [0.2, 0.4, None]
+        if args is not None:
+            n_layers = args.pnpp_n_layers
+            self.n_samples = self.n_samples[:n_layers]
+            mlps, mlps_in = mlps[:n_layers], mlps_in[:n_layers]
+            self.radius = self.radius[:n_layers]
+            up_mlps = up_mlps[-n_layers:]
+            up_mlps_in = up_mlps_in[-n_layers:]
+        self.mlp_layers = nn.ModuleList(
+            construct_conv_modules(dims_out, dims_in[0], last_act=True, bn=True) for dims_in, dims_out in zip(mlps_in, mlps))
+        self.up_mlp_layers = nn.ModuleList(
+            construct_conv_modules(dims_out, dim_in, last_act=True, bn=True) for dim_in, dims_out in zip(up_mlps_in, up_mlps))
+
+    # ---- reference helpers (PointNet2.py:66-76) --------------------------------------------------------------------
+    def set_bn_no_training(self):
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+
+    def set_grad_to_none(self):
+        for p in self.parameters():
+            p.grad = None
+
+    # ---- building blocks ---------------------------------------------------------------------------------------------
+    def _sample_and_group_rows(self, feat, pos, n_samples, k=64):
+        """-> operand rows [B,S,k,cpad] (zero padded), sorted neighbour distances [B,S,k], centres [B,S,3]."""
+        if pos.shape[-1] != 3:
+            raise NotImplementedError("PointnetPP: 3-D coordinates expected")
+        bz = pos.size(0)
+        fps_idx = _ops.fps_plain(pos.detach().permute(0, 2, 1).contiguous(), n_samples).long()        # [B,S]
+        sampled_pos = torch.gather(pos, 1, fps_idx.unsqueeze(-1).expand(bz, n_samples, 3)).contiguous()
+        topk_idx, topk_dist = _ops.knn_query(pos.detach(), sampled_pos.detach(), k)
+        rows = _ops.sa_group(feat, pos, sampled_pos, topk_idx)
+        return rows, topk_dist, sampled_pos
+
+    def sample_and_group(self, feat, pos, n_samples, use_pos=True, k=64):
+        """PointNet2.py:78-100: -> grouped_feat [B,S,k,3+C] (or [B,S,k,C] without use_pos), topk_dist, sampled_pos."""
+        rows, topk_dist, sampled_pos = self._sample_and_group_rows(feat, pos, n_samples, k)
+        c = 0 if feat is None else feat.shape[-1]
+        grouped = rows[..., :3 + c] if (use_pos or feat is None) else rows[..., 3:3 + c]
+        return grouped, topk_dist, sampled_pos
+
+    def max_pooling_with_r(self, grouped_feat, ppdist, r=None):
+        """PointNet2.py:102-112: grouped_feat [B,S,k,C], ppdist [B,S,k] -> [B,S,C]."""
+        b, s, k, c = grouped_feat.shape
+        res = _ops.sa_maxpool(grouped_feat.reshape(b * s, k, c), None if r is None else ppdist.reshape(b * s, k), r)
+        return res.view(b, s, c)
+
+    def interpolate_features(self, feat, p1, p2):
+        """PointNet2.py:114-129: features of p1 [B,n1,3] carried to p2 [B,n2,3] by inverse-distance 3-NN weights."""
+        idx, w = _ops.three_nn(p1.detach(), p2.detach())
+        return _ops.three_interpolate(feat, idx, w)
+
+    # ---- PointNet2.py:131-196 -------------------------------------------------------------------------------------------
+    def forward(self, x, pos, return_global=False):
+        bz = pos.size(0)
+        cache = [(x, pos)]
+        for i, n_samples in enumerate(self.n_samples):
+            layers = self.mlp_layers[i]
+            if n_samples == 1:
+                rows = _ops.sa_group(x, pos, None, None)                       # [B,1,N,cpad] = [pos | x | 0]
+                n = rows.shape[2]
+                y = _apply_mlp(rows.view(bz * n, rows.shape[-1]), layers)
+                x = _ops.sa_maxpool(y.view(bz, n, y.shape[-1])).view(bz, 1, -1)
+                pos = torch.zeros((bz, 1, 3), dtype=torch.float32, device=pos.device)
+            else:
+                rows, topk_dist, pos = self._sample_and_group_rows(x, pos, n_samples, k=64)
+                k = rows.shape[2]
+                y = _apply_mlp(rows.view(bz * n_samples * k, rows.shape[-1]), layers)
+                x = self.max_pooling_with_r(y.view(bz, n_samples, k, y.shape[-1]), topk_dist, r=self.radius[i])
+            cache.append((x, pos))
+
+        global_x = x
+        for i, up_conv_layers in enumerate(self.up_mlp_layers):
+            prev_x, prev_pos = cache[-i - 2]
+            interpolated = self.interpolate_features(x, pos, prev_pos)
+            if prev_x is None:
+                prev_x = prev_pos
+            elif i == len(self.up_mlp_layers) - 1:
+                prev_x = torch.cat([prev_x, prev_pos], dim=-1)
+            cur = torch.cat([interpolated, prev_x], dim=-1)
+            n_prev = cur.shape[1]
+            x = _apply_mlp(cur.reshape(bz * n_prev, cur.shape[-1]), up_conv_layers).view(bz, n_prev, -1)
+            pos = prev_pos
+        if return_global:
+            return x, global_x, pos
+        return x, pos

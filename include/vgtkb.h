@@ -257,6 +257,36 @@ int vgtkb_pointnet_embed_xyz(int b, int n, int a, int co, float* e, const float*
 int vgtkb_pointnet_pool_backward(int b, int n, int a, int co, const float* grad_out, const int32_t* arg, float* grad_e,
                                  void* stream);
 
+/* PointNet++ set abstraction / feature propagation (SPConvNets/models/PointNet2.py:78-129, `PointnetPP`; csrc/pointnet2.cu).
+ * Clouds are [b, n, 3] rows here (the layout PointnetPP works in), features [b, n, c] rows.
+ *   knn_query (sample_and_group :85-87: sqrt(sum((centre - pos)^2)) + torch.topk(k, largest=False)):
+ *       idx int32 [b, s, k] / dist [b, s, k] = the k nearest points of every centre, ascending distance, ties to the
+ *       smaller index; squared distance evaluated as (dx*dx + dy*dy) + dz*dz (torch's CPU order), dist = sqrt of it
+ *   sa_group_forward (:92-100): out [b, s, k, cpad] rows = [pos[idx] - centre | feat[idx] | zero padding to cpad];
+ *       idx == NULL: identity neighbourhood (s = 1, k = n: the global level :151-156), centers == NULL: origin;
+ *       feat == NULL with c = 0: coordinates only
+ *   sa_group_backward: grad_feat [b, n, c] = scatter-add of grad_out[..., 3:3+c]
+ *   sa_maxpool_forward (max_pooling_with_r :102-112): out [groups, c] = max_j (dist[g,j] <= radius ? y[g,j,:] : -1e8),
+ *       arg int32 = first arg-max; dist == NULL: plain max
+ *   sa_maxpool_backward: grad_y [groups, k, c] = grad_out at the arg-max row, zero elsewhere (written in one pass)
+ *   three_nn (interpolate_features :114-123): for every p2 point the min(3, n1) nearest p1 points (torch.norm order:
+ *       fma(dz,dz,fma(dy,dy,dx*dx))), weights (1/(d+1e-8)) / sum; unused slots have weight 0
+ *   three_interpolate_forward/backward (:126-128): out [b, n2, c] = sum_j feat[b, idx_j, :] * w_j and its scatter-add */
+int vgtkb_knn_query(int b, int n, int s, int k, const float* pos, const float* centers, int32_t* idx, float* dist, void* stream);
+int vgtkb_sa_group_forward(int b, int n, int s, int k, int c, int cpad, const float* pos, const float* feat,
+                           const float* centers, const int32_t* idx, float* out, void* stream);
+int vgtkb_sa_group_backward(int b, int n, int s, int k, int c, int cpad, const float* grad_out, const int32_t* idx,
+                            float* grad_feat, void* stream);
+int vgtkb_sa_maxpool_forward(int64_t groups, int k, int c, const float* y, const float* dist, float radius, float* out,
+                             int32_t* arg, void* stream);
+int vgtkb_sa_maxpool_backward(int64_t groups, int k, int c, const float* grad_out, const int32_t* arg, float* grad_y,
+                              void* stream);
+int vgtkb_three_nn(int b, int n1, int n2, const float* p1, const float* p2, int32_t* idx, float* w, void* stream);
+int vgtkb_three_interpolate_forward(int b, int n1, int n2, int c, const float* feat, const int32_t* idx, const float* w,
+                                    float* out, void* stream);
+int vgtkb_three_interpolate_backward(int b, int n1, int n2, int c, const float* grad_out, const int32_t* idx, const float* w,
+                                     float* grad_feat, void* stream);
+
 /* column sums of a row-major [rows, c] matrix (bias gradient of the skip conv) */
 int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream);
 

@@ -11,6 +11,7 @@ Writes (all small):
   tests/golden/ref_intra_small.npz    one IntraSO3Conv (BASELINE config 1a, reduced size)
   tests/golden/ref_weights_small.npz  inter_so3conv_grouping_anchor + grouping einsum
   tests/golden/ref_intrazp_small.npz, ref_pose_group_small.npz, ref_pointnet_small.npz (`make_golden.py pointnet`)
+  tests/golden/ref_pointnet2_small.npz  PointnetPP encoder-decoder (SPConvNets/models/PointNet2.py), fwd (`make_golden.py pointnet2`)
 """
 import contextlib
 import io
@@ -65,8 +66,65 @@ def make_pointnet():
     print("pointnet", out['a60_pooled'].shape, out['a1_pooled'].shape)
 
 
+def make_pointnet2():
+    """PointnetPP (SPConvNets/models/PointNet2.py:8-196), train-mode forward with return_global=True on two clouds of 600
+    points, in_feat_dim = 6 (x = 3 extra channels).  Weights come from oracle.pointnet2.make_state (numpy RandomState, so the
+    tests rebuild them); torch_cluster.fps is a stub over the oracle's plain FPS (dependency not vendored)."""
+    import math
+    import types
+    from oracle import cops
+    from oracle import pointnet2 as OP
+    tc = types.ModuleType("torch_cluster")
+
+    def fps(src, batch=None, ratio=0.5, random_start=True):
+        assert not random_start
+        nb = int(batch[-1]) + 1
+        n = src.shape[0] // nb
+        m = int(math.ceil(ratio * n))
+        xyz = src[:, :3].float().reshape(nb, n, 3).permute(0, 2, 1).contiguous().numpy()
+        idx = torch.from_numpy(cops.fps_plain(xyz, m)).long()
+        return (idx + torch.arange(nb).view(nb, 1) * n).reshape(-1)
+    tc.fps = fps
+    sys.modules["torch_cluster"] = tc
+    H.import_blocks()
+    import importlib
+    P = importlib.import_module("SPConvNets.models.PointNet2")
+    net = P.PointnetPP(in_feat_dim=6)
+    net.load_state_dict(OP.make_state(6, seed=7))
+    net.train()
+    g = torch.Generator().manual_seed(6001)
+    pos = torch.rand(2, 600, 3, generator=g) - 0.5
+    x = torch.randn(2, 600, 3, generator=g)
+    taps = {}
+    orig = net.sample_and_group
+
+    def tapped(feat, p, n_samples, use_pos=True, k=64):
+        r = orig(feat, p, n_samples, use_pos=use_pos, k=k)
+        taps[f"topk_dist_{n_samples}"] = r[1].detach().numpy().copy()
+        taps[f"pos_{n_samples}"] = r[2].detach().numpy().copy()
+        return r
+    net.sample_and_group = tapped
+    out, glb, p_out = net(x.clone(), pos.clone(), return_global=True)
+    res = {"pos": pos.numpy(), "x": x.numpy(), "out": out.detach().numpy(), "global_x": glb.detach().numpy(),
+           "pos_out": p_out.numpy(), "seed": np.int64(7)}
+    res.update(taps)
+    for name in ("mlp_layers.0.2.1", "mlp_layers.2.2.1", "up_mlp_layers.2.2.1"):
+        sd = net.state_dict()
+        res["rm:" + name] = sd[name + ".running_mean"].numpy()
+        res["rv:" + name] = sd[name + ".running_var"].numpy()
+    try:                        # the reference masks the MLP output in place (:109): its own backward rejects that
+        out.square().mean().backward()
+        res["reference_backward"] = np.array("ok")
+    except RuntimeError as e:
+        res["reference_backward"] = np.array("RuntimeError: " + str(e).splitlines()[0][:160])
+    np.savez_compressed(os.path.join(GOLD, "ref_pointnet2_small.npz"), **res)
+    print("pointnet2", out.shape, glb.shape, str(res["reference_backward"]))
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1 and sys.argv[1] == "pointnet2":
+        return make_pointnet2()
     if len(sys.argv) > 1 and sys.argv[1] == "pointnet":      # only this fixture (the others stay untouched)
         return make_pointnet()
     M = H.import_blocks()
