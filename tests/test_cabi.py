@@ -63,3 +63,19 @@ def test_sass_has_blackwell_paths(libpath):
     out = subprocess.run(["cuobjdump", "-sass", libpath], capture_output=True, text=True).stdout
     assert "sm_100a" in out or "SM100" in out.upper()
     assert "UBLKCP" in out
+
+
+def test_product_synthetic_generators_match_the_checkers():
+    """bench.py's CUDA arm builds its clouds / weights from the product package (nothing under oracle/ on that arm); the CPU
+    baseline arm uses the oracle's generators: both must see identical tensors."""
+    import torch
+    from equi_articulated_pose_b200 import blocks, synthetic
+    from oracle import so3 as O
+    for n in (1024, 4096):
+        assert blocks.backbone_params(input_num=n) == O.backbone_params(input_num=n) or \
+            all(a['args'][k] == b['args'][k] for pa, pb in zip(blocks.backbone_params(input_num=n), O.backbone_params(input_num=n))
+                for a, b in zip(pa, pb) for k in b['args'])
+    p = blocks.backbone_params(input_num=1024)
+    s1, s2 = synthetic.init_backbone_state(p, seed=0), O.init_backbone_state(O.backbone_params(input_num=1024), seed=0)
+    assert s1.keys() == s2.keys() and all(torch.equal(s1[k], s2[k]) for k in s1)
+    assert torch.equal(synthetic.synthetic_cloud(3, 1024, 2000), O.synthetic_cloud(3, 1024, 2000))
