@@ -165,7 +165,7 @@ col_reduce4_kernel(int64_t rows, int c, int rows_per_cta, const float* __restric
 // issues U independent 16-byte loads per array before touching any of them (the kernel is latency-bound otherwise:
 // 30% of the HBM rate with one load in flight per thread), and folds them into its fp64 sums.
 template <int MODE, int U>
-__global__ void __launch_bounds__(NT, MODE == 1 ? 3 : 4)
+__global__ void __launch_bounds__(NT, 2)
 col_reduce4b_kernel(int64_t rows, int c, int rows_per_cta, const float* __restrict__ x, OpBwd bw, double* __restrict__ scratch) {
     const int g = blockIdx.y;
     const int c4 = c >> 2;
@@ -188,8 +188,10 @@ col_reduce4b_kernel(int64_t rows, int c, int rows_per_cta, const float* __restri
             if (bw.beta) be[i] = bw.beta[ch + i];
         }
     }
-    for (int64_t r = r0 + ly; r < r1; r += (int64_t)ty * U) {
-        float4 v4[U], g4[MODE == 1 ? U : 1];
+    // two register buffers: the loads of batch i+1 are in flight while batch i is folded into the fp64 sums (ncu on the
+    // one-buffer version: long-scoreboard stalls 9-13 per issue, 44 % of the DRAM rate)
+    constexpr int UG = MODE == 1 ? U : 1;
+    auto load = [&](float4 (&v4)[U], float4 (&g4)[UG], int64_t r) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t rr = r + (int64_t)u * ty;
@@ -197,6 +199,8 @@ col_reduce4b_kernel(int64_t rows, int c, int rows_per_cta, const float* __restri
             v4[u] = ok ? __ldg(xg + rr * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (MODE == 1) g4[u] = ok ? __ldg(gyg + rr * c4) : make_float4(0.f, 0.f, 0.f, 0.f);   // gy = 0: no contribution
         }
+    };
+    auto fold = [&](const float4 (&v4)[U], const float4 (&g4)[UG]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const float v[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
@@ -214,13 +218,28 @@ col_reduce4b_kernel(int64_t rows, int c, int rows_per_cta, const float* __restri
                     const float xh = (v[i] - mean[i]) * inv[i];
                     const float pre = xh * ga[i] + be[i];
                     const float d = pre > 0.f ? gv[i] : gv[i] * bw.slope;
-                    s1[i] += (double)d;
+                    s1[i] += (double)d;                              // padded rows: gy = 0, so d = 0
                     s2[i] += (double)d * (double)xh;
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) s1[i] += (double)v[i];
             }
+        }
+    };
+    {
+        const int64_t step = (int64_t)ty * U;
+        int64_t r = r0 + ly;
+        float4 va[U], ga4[UG], vb[U], gb4[UG];
+        if (r < r1) load(va, ga4, r);
+        while (r < r1) {
+            const int64_t rb = r + step;
+            if (rb < r1) load(vb, gb4, rb);
+            fold(va, ga4);
+            if (rb >= r1) break;
+            r = rb + step;
+            if (r < r1) load(va, ga4, r);
+            fold(vb, gb4);
         }
     }
     if (ty > 1) {
@@ -467,9 +486,10 @@ __global__ void col_sum_finalize_kernel(int c, const double* __restrict__ scratc
     if (ch < c) out[ch] = (float)scratch[ch];
 }
 
-static int reduce_geometry(int64_t rows, int c, int groups, int& rows_per_cta, unsigned& gx) {
-    // aim at ~4 CTAs per SM overall, at least 64 rows per CTA
-    int64_t want = (int64_t)kNumSMs * 4 / (groups > 0 ? groups : 1);
+static int reduce_geometry(int64_t rows, int c, int groups, int& rows_per_cta, unsigned& gx, int ctas_per_sm = 4) {
+    // exactly one wave of resident CTAs overall (ncu: 591 CTAs on 444 slots = 1.33 waves left the second wave a third full),
+    // at least 64 rows per CTA
+    int64_t want = (int64_t)kNumSMs * ctas_per_sm / (groups > 0 ? groups : 1);
     if (want < 1) want = 1;
     int64_t rpc = ceil_div64(rows, want);
     if (rpc < 64) rpc = 64;
@@ -490,7 +510,7 @@ extern "C" int vgtkb_norm_sums(int groups, int64_t rows, int c, const float* x, 
     VGTKB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (size_t)groups * 2 * c, st));
     int rpc;
     unsigned gx;
-    reduce_geometry(rows, c, groups, rpc, gx);
+    reduce_geometry(rows, c, groups, rpc, gx, 2);
     OpBwd dummy{};
     launch_col_reduce<0>(groups, rows, c, rpc, gx, x, dummy, scratch, st);
     return check_launch("norm_sums");
@@ -551,7 +571,7 @@ extern "C" int vgtkb_norm_bwd_sums(int groups, int64_t rows, int c, const float*
     OpBwd bw{grad_y, stats, gamma, beta, slope, c};
     int rpc;
     unsigned gx;
-    reduce_geometry(rows, c, groups, rpc, gx);
+    reduce_geometry(rows, c, groups, rpc, gx, 2);
     launch_col_reduce<1>(groups, rows, c, rpc, gx, x, bw, scratch, st);
     if (grad_gamma || grad_beta)
         affine_grad_kernel<<<ceil_div(c, 128), 128, 0, st>>>(groups, c, scratch, grad_gamma, grad_beta);
@@ -601,7 +621,7 @@ extern "C" int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratc
     VGTKB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (size_t)2 * c, st));
     int rpc;
     unsigned gx;
-    reduce_geometry(rows, c, 1, rpc, gx);
+    reduce_geometry(rows, c, 1, rpc, gx, 2);
     OpBwd dummy{};
     launch_col_reduce<2>(1, rows, c, rpc, gx, x, dummy, scratch, st);
     col_sum_finalize_kernel<<<ceil_div(c, 128), 128, 0, st>>>(c, scratch, out);
