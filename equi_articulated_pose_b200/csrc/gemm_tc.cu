@@ -384,8 +384,8 @@ struct PairCfg {
 template <int BN_>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-                       const __grid_constant__ CUtensorMap map_blo, const float* __restrict__ bias, float* __restrict__ C,
-                       int64_t M, int N, int K, int chunk_kb, TcGather ga) {
+                       const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c, int tma_out,
+                       const float* __restrict__ bias, float* __restrict__ C, int64_t M, int N, int K, int chunk_kb, TcGather ga) {
     using Cfg = PairCfg<BN_>;
     constexpr int STAGES = Cfg::STAGES, BN = Cfg::BN, KBE = 64, UK = 16;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -450,6 +450,38 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             const uint32_t stg = smem_base + (uint32_t)(STAGES * Cfg::STAGE_BYTES) + (uint32_t)warp * 4096u;
             const int64_t row0 = (int64_t)mt * TC_BM + q * 32;
             const int c_base = nt * BN + h * Cfg::HALF;
+            if (tma_out) {
+                // tensor-map store: the 32x32 block goes registers -> 128B-swizzled staging tile -> ONE bulk tensor copy, instead
+                // of being read back and stored by every lane (ncu on the wide-output launches dG = gy W: l1tex 90 %, LSU
+                // wavefronts 87 %, tensor pipe 62 % -- the epilogue's shared-memory transposes were the bound)
+#pragma unroll
+                for (int j = 0; j < Cfg::HALF / 32; ++j) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile read out
+                    __syncwarp();
+                    const int colj = c_base + j * 32;
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        float4 o = make_float4(acc[j * 32 + c4 * 4], acc[j * 32 + c4 * 4 + 1], acc[j * 32 + c4 * 4 + 2],
+                                               acc[j * 32 + c4 * 4 + 3]);
+                        if (bias != nullptr) {
+                            const int col = colj + c4 * 4;
+                            if (col < N) o.x += __ldg(bias + col);
+                            if (col + 1 < N) o.y += __ldg(bias + col + 1);
+                            if (col + 2 < N) o.z += __ldg(bias + col + 2);
+                            if (col + 3 < N) o.w += __ldg(bias + col + 3);
+                        }
+                        st_shared_v4(stg + (uint32_t)(lane * 128 + ((c4 ^ (lane & 7)) << 4)), o);
+                    }
+                    fence_proxy_async();                      // generic-proxy writes -> visible to the bulk-copy engine
+                    __syncwarp();
+                    if (lane == 0 && colj < N && row0 < M) {  // rows / columns beyond M / N are clipped by the tensor map
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_c),
+                                     "r"(stg), "r"(colj), "r"((int)row0)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else
 #pragma unroll
             for (int j = 0; j < Cfg::HALF / 32; ++j) {
 #pragma unroll
@@ -489,6 +521,7 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 #pragma unroll
             for (int i = 0; i < Cfg::HALF; ++i) acc[i] = 0.f;
         }
+        if (tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all tile stores landed
     } else if (warp != TC_MMA_WARP && warp != TC_TMA_WARP) {
         // ============================ converters ============================
         reg_dec_other();
@@ -1291,7 +1324,7 @@ template <int BN_>
 static int launch_nt_pair(int64_t M, int N, int K, const float* A, const void* Bhi, const void* Blo, const float* bias, float* C,
                           cudaStream_t st, TcGather ga) {
     using Cfg = PairCfg<BN_>;
-    CUtensorMap ma, mhi, mlo;
+    CUtensorMap ma, mhi, mlo, mc;
     int rc = ga.anchors > 0 ? make_map_3d(&ma, A, M, ga.anchors, ga.c, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B)
                             : make_map_2d(&ma, A, M, K, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -1299,6 +1332,15 @@ static int launch_nt_pair(int64_t M, int N, int K, const float* A, const void* B
     if (rc) return rc;
     rc = make_map_2d(&mlo, Blo, N, K, Cfg::BN / 2, CU_TENSOR_MAP_SWIZZLE_128B, true);
     if (rc) return rc;
+    // output through 32x32 tensor-map stores: plain (non-gather) GEMMs whose rows are 16-byte multiples; VGTKB_TMA_EPILOGUE=0
+    // keeps the per-lane stores (comparison / fallback)
+    static const bool tma_epi = []() { const char* e = getenv("VGTKB_TMA_EPILOGUE"); return e == nullptr || e[0] != '0'; }();
+    const int tma_out = tma_epi && ga.anchors == 0 && N % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+    mc = ma;
+    if (tma_out) {
+        rc = make_map_2d(&mc, C, M, N, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
     const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024 + TC_EPI_WARPS * 4096;
     auto kern = tc_gemm_nt_pair_kernel<BN_>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1317,7 +1359,7 @@ static int launch_nt_pair(int64_t M, int N, int K, const float* A, const void* B
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VGTKB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mhi, mlo, bias, C, M, N, K, default_chunk(3, true), ga));
+    VGTKB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mhi, mlo, mc, tma_out, bias, C, M, N, K, default_chunk(3, true), ga));
     return check_launch("gemm_nt(tcgen05, cta pairs)");
 }
 
