@@ -10,7 +10,8 @@ the only collective is the gradient all-reduce (NCCL).  Rank 0 prints ONE JSON l
   value     whole-job points/sec, inputs resident in HBM, K steps between barrier+sync, CUDA events
   e2e       same metric with the input clouds in pinned HOST memory (H2D inside the timed region)
             and the loss read back (D2H) every step
-  roofline  the dominant kernel of the step (largest summed CUDA-event time over the timed region)
+  roofline  the dominant kernel of the step (largest summed CUDA-event time); the per-call CUDA events are recorded
+            in a repeat of the same K steps right after the headline region (they cost ~0.9 ms of a 19 ms step)
   cpu_baseline  the oracle port of the reference on the host cores, bounded sample (rank 0, N=1 only)
 
 --impl reference times the reference's algorithm on the host CPU (oracle/so3.py + oracle_ops.c,
@@ -300,7 +301,6 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    lib.PROFILE = []
     k0, c0 = lib.COUNTERS["kernels"], lib.COUNTERS["launch_calls"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -312,8 +312,22 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.COUNTERS["kernels"] - k0
-    records, lib.PROFILE = lib.PROFILE, None
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region 1b: the same K steps with a CUDA-event pair around every C-ABI call (roofline bookkeeping).
+    # ~600 event records per step cost ~0.9 ms of a 19 ms step (measured), so they stay out of the headline region;
+    # the per-kernel durations they deliver are the ones `roofline` / `kernel_table` report.
+    lib.PROFILE = []
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    p0.record()
+    for _ in range(args.steps):
+        step(clouds_dev)
+        flush.zero_()
+    p1.record()
+    barrier()
+    ms_profiled = p0.elapsed_time(p1)
+    records, lib.PROFILE = lib.PROFILE, None
 
     # ---- timed region 2: end to end (pinned host input -> device, loss -> host, every step) -----
     barrier()
@@ -348,7 +362,11 @@ def run_ours(args):
                            "l2": "256 MiB buffer written between steps (L2 flush); per-step activations >> 126 MB L2"},
                 "e2e": {"value": pts_per_step * args.steps / (ms_e2e * 1e-3), "unit": "points/s",
                         "h2d_bytes_per_step": clouds_host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "rooflines_other": other_roofs, "kernel_table": table, "shape_table": shape_table,
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline_region": {"ms_per_step": ms_profiled / args.steps,
+                                    "note": "roofline / kernel_table: the same K steps repeated with a CUDA-event pair around every "
+                                            "C-ABI call on the launching stream; `value` is timed without those events"},
+                "roofline": roof, "rooflines_other": other_roofs, "kernel_table": table, "shape_table": shape_table,
                 "loss": float(loss_host)}
         if world == 1 and not args.no_cpu_baseline:
             r = time_oracle(1, 1)
