@@ -280,6 +280,40 @@ def backbone_params(input_num=1024, kanchor=60, mlps=((64, 64), (128, 128), (256
     return out
 
 
+def model38_backbone_params(input_num=512, kanchor=60, init_radius=0.2, mlps=((64,), (128,), (512,)), dropout_rate=0.0):
+    """Per-layer argument dictionaries of the equivariant backbone model 38 (`--use-equi=38`) builds for `kanchor=60`
+    (SPConvNets/models/unsup_seg_so3_pose_conv_pn_38_multi_stage.py:2084-2225): three stride-1 separable blocks
+    64 / 128 / 512, 64 neighbours each, input radius 0.4, radii and sigmas taken from the stride ladder [1, 2, 4, 8]."""
+    input_radius, sampling_density, sigma_ratio = 0.4, 0.5, 0.5
+    strides = [2, 2, 2, 2]
+    n_layer = len(mlps)
+    mult = [1]
+    for i in range(n_layer):
+        mult.append(mult[-1] * strides[i])
+    radius_ratio = [init_radius * m ** sampling_density for m in mult]
+    radii = [r * input_radius for r in radius_ratio]
+    weighted_sigma = [sigma_ratio * radii[0] ** 2]
+    for i, st in enumerate(strides):
+        weighted_sigma.append(weighted_sigma[i] * st)
+    out, dim_in = [], 1
+    for i, block in enumerate(mlps):
+        layers = []
+        for j, dim_out in enumerate(block):
+            neighbor = 32
+            nidx = i + 1
+            if j == 0:
+                nidx = i if i == 0 else i + 1
+                neighbor *= 2
+            layers.append({'type': 'inter_block' if kanchor < 60 else 'separable_block', 'args': {
+                'dim_in': dim_in, 'dim_out': dim_out, 'kernel_size': 1, 'stride': 1,
+                'radius': radii[nidx], 'sigma': weighted_sigma[nidx], 'n_neighbor': neighbor,
+                'lazy_sample': i != 0 or j != 0, 'dropout_rate': dropout_rate, 'multiplier': 2,
+                'activation': 'leaky_relu', 'pooling': None, 'kanchor': kanchor, 'norm': 'BatchNorm2d'}})
+            dim_in = dim_out
+        out.append(layers)
+    return out
+
+
 class SO3Backbone(nn.Module):
     """`ClsSO3ConvModel.backbone` + its forward loop (cls_so3net_pn.py:15-33), without the head."""
 

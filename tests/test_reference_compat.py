@@ -60,6 +60,7 @@ def test_model38_registry_builds_on_dropin():
     """run_unsup_arti_align.py maps --use-equi=38 to this registry entry (run_unsup_arti_align.py:8-17)."""
     out = _run(PRELUDE + """
 import io, contextlib
+from equi_articulated_pose_b200 import blocks          # before the reference's own `extensions` package gets imported
 torch.Tensor.cuda = lambda self, *a, **k: self          # the model constructor calls .cuda() (no GPU here)
 sys.argv = ['run_unsup_arti_align.py', '-d', '/tmp/none', '--use-equi=38', '--kanchor=60', '--kpconv-kanchor=60',
             '--input-num=512', '--bsz=1', '--nmasks=2', '--cur-stage=0']
@@ -76,6 +77,15 @@ n_intra = sum(isinstance(m, sptk.IntraSO3Conv) for m in net.modules())
 assert n_pose >= 3 and n_intra >= 3, (n_pose, n_intra)
 from extensions.chamfer_dist import ChamferDistance
 assert ChamferDistance.__module__.startswith('extensions.chamfer_dist')
-print('OK', sum(p.numel() for p in net.parameters()))
+# the per-layer geometry the reference's builder hands to its convolutions == blocks.model38_backbone_params()
+mine = [l['args'] for blk in blocks.model38_backbone_params(input_num=512) for l in blk]
+theirs = [m for m in net.modules() if isinstance(m, sptk.InterSO3Conv)]
+groups = [theirs[i:i + len(mine)] for i in range(0, len(theirs) - len(mine) + 1, len(mine))]
+assert groups, len(theirs)
+for grp in groups:
+    for a, m in zip(mine, grp):
+        assert (a['dim_in'], a['dim_out'], a['stride'], a['n_neighbor']) == (m.dim_in, m.dim_out, m.stride, m.n_neighbor), (a, m.dim_in, m.dim_out)
+        assert abs(a['radius'] - m.radius) < 1e-12 and abs(a['sigma'] - m.sigma) < 1e-12, (a, m.radius, m.sigma)
+print('OK', sum(p.numel() for p in net.parameters()), len(theirs))
 """)
     assert "OK" in out
