@@ -104,7 +104,10 @@ class PointnetPP(nn.Module):
         """-> operand rows [B,S,k,cpad] (zero padded), sorted neighbour distances [B,S,k], centres [B,S,3]."""
         if pos.shape[-1] != 3:
             raise NotImplementedError("PointnetPP: 3-D coordinates expected")
-        bz = pos.size(0)
+        bz, n = pos.size(0), pos.size(1)
+        if n_samples > n or k > n:
+            # the reference fails here too (torch_cluster.fps with ratio > 1 / torch.topk with k > N), with less helpful messages
+            raise ValueError(f"PointnetPP level needs {n_samples} centres with {k} neighbours each, the cloud has {n} points")
         fps_idx = _ops.fps_plain(pos.detach().permute(0, 2, 1).contiguous(), n_samples).long()        # [B,S]
         sampled_pos = torch.gather(pos, 1, fps_idx.unsqueeze(-1).expand(bz, n_samples, 3)).contiguous()
         topk_idx, topk_dist = _ops.knn_query(pos.detach(), sampled_pos.detach(), k)

@@ -79,3 +79,19 @@ def test_product_synthetic_generators_match_the_checkers():
     s1, s2 = synthetic.init_backbone_state(p, seed=0), O.init_backbone_state(O.backbone_params(input_num=1024), seed=0)
     assert s1.keys() == s2.keys() and all(torch.equal(s1[k], s2[k]) for k in s1)
     assert torch.equal(synthetic.synthetic_cloud(3, 1024, 2000), O.synthetic_cloud(3, 1024, 2000))
+
+
+def test_pointnetpp_constructs_with_reference_keys_and_validates_sizes():
+    """CPU-side checks of the PointnetPP drop-in (no kernel launches): state-dict keys of the reference class
+    (SPConvNets/models/PointNet2.py:22-64) and a clear error for clouds smaller than a level."""
+    import pytest
+    import torch
+    from equi_articulated_pose_b200.pointnet2 import PointnetPP
+    from oracle import pointnet2 as OP
+    net = PointnetPP(6)
+    assert set(net.state_dict().keys()) == set(OP.make_state(6).keys())
+    net.load_state_dict(OP.make_state(6, seed=1))
+    two = PointnetPP(6, type("A", (), {"pnpp_n_layers": 2})())
+    assert set(two.state_dict().keys()) == set(OP.make_state(6, n_layers=2).keys())
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 100, 3), torch.zeros(1, 100, 3))           # 100 points < 512 centres: rejected before any launch
