@@ -3,9 +3,10 @@
 The reference trains with DistributedDataParallel over NCCL, one cloud per rank
 (SPConvNets/trainer_unsup_arti_align.py:52-56,203-208,430-440): the convolution is per-sample,
 so the only exchange step of the path is the gradient all-reduce (7.67 M fp32 = 30.7 MB for the
-classic backbone).  Here the gradients live in ONE flat fp32 bucket that the parameters' .grad
-tensors are views of, so a step needs exactly one NCCL all-reduce (NVLink 5 / NVSwitch, NVLS
-in-switch reduction when available) and no flatten/unflatten copies.
+classic backbone).  Here the gradients are packed into ONE flat fp32 bucket after backward (one
+concatenation kernel; the parameters' .grad tensors become views of it), so a step needs exactly one
+NCCL all-reduce (NVLink 5 / NVSwitch, NVLS in-switch reduction when available) and the optimiser
+works on the flat storage.
 """
 import os
 
@@ -39,46 +40,69 @@ def shard_range(total, rank, world):
 
 
 class FlatGradBucket:
-    """All gradients of `params` as views of one contiguous fp32 buffer."""
+    """All gradients of `params` in one contiguous fp32 buffer, gathered AFTER backward.
+
+    `zero_()` drops the gradients (`p.grad = None`), so autograd hands every parameter its freshly computed gradient tensor
+    instead of launching one `grad += new` kernel per parameter (59 small launches per step on the classic backbone);
+    `collect()` then packs them into the flat buffer with ONE concatenation kernel and re-points every `p.grad` at its
+    slice, so the optimiser and the all-reduce work on the flat storage.  `flat` collects on first access."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         ref = self.params[0]
-        self.flat = torch.zeros(total, dtype=torch.float32, device=ref.device)
-        off = 0
+        self._flat = torch.zeros(total, dtype=torch.float32, device=ref.device)
+        self._views, off = [], 0
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            self._views.append(self._flat[off:off + n].view_as(p))
             off += n
+        for p, v in zip(self.params, self._views):
+            p.grad = v
+        self._collected = True
+
+    @property
+    def flat(self):
+        self.collect()
+        return self._flat
 
     def zero_(self):
-        self.flat.zero_()
-        for p in self.params:           # autograd may have replaced a view (first accumulation): re-attach
-            if p.grad is None or p.grad.untyped_storage().data_ptr() != self.flat.untyped_storage().data_ptr():
-                self._reattach()
-                break
-
-    def _reattach(self):
-        off = 0
+        """Forget the gradients of the previous step (the next backward writes new tensors; nothing is memset)."""
         for p in self.params:
-            n = p.numel()
-            view = self.flat[off:off + n].view_as(p)
-            if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
-                view.copy_(p.grad)
-            p.grad = view
-            off += n
+            p.grad = None
+        self._collected = False
+
+    def collect(self):
+        """Pack the parameters' gradients into the flat buffer (one kernel) and make every `.grad` a view of it."""
+        if self._collected and all(p.grad is v or (p.grad is not None and p.grad.data_ptr() == v.data_ptr())
+                                   for p, v in zip(self.params, self._views)):
+            return
+        base = self._flat.untyped_storage().data_ptr()
+        pieces, aliased = [], False
+        for p, v in zip(self.params, self._views):
+            g = p.grad
+            if g is None:
+                g = torch.zeros_like(v)                          # parameter not reached by this backward
+            elif g.untyped_storage().data_ptr() == base:
+                aliased = True                                   # still one of our views (accumulated in place)
+            pieces.append(g.reshape(-1))
+        if aliased:                                              # mixed state: never concatenate a buffer into itself
+            pieces = [t.clone() for t in pieces]
+        torch.cat(pieces, out=self._flat)
+        for p, v in zip(self.params, self._views):
+            p.grad = v
+        self._collected = True
 
     def all_reduce_mean(self, group=None):
         """One collective for the whole model; averages over ranks like DDP does."""
+        self.collect()
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return
-        self._reattach()
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        self.flat.div_(dist.get_world_size(group))
+        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=group)
+        self._flat.div_(dist.get_world_size(group))
 
     def nbytes(self):
-        return self.flat.numel() * 4
+        return self._flat.numel() * 4
 
 
 class PeerMailbox:

@@ -144,3 +144,33 @@ def test_syncbn_protocol_matches_full_batch_batchnorm():
     assert torch.allclose(gx, x_all.grad, atol=1e-12)
     assert torch.allclose(res[0][5] + res[1][5], gamma.grad, atol=1e-12)      # local sums add up to the global gradient
     assert torch.allclose(res[0][6] + res[1][6], beta.grad, atol=1e-12)
+
+
+def test_flat_grad_bucket_single_process_semantics():
+    """zero_() drops the gradients, backward writes fresh tensors, collect()/flat packs them with one concatenation and makes
+    every .grad a view of the flat buffer; accumulation without zero_() happens in place; unused parameters read as zero."""
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3), torch.nn.Linear(3, 2))
+    bucket = dp.FlatGradBucket(net.parameters())
+    opt = torch.optim.Adam(bucket.params, lr=1e-2)
+    x = torch.randn(8, 5)
+    for _ in range(3):
+        bucket.zero_()
+        assert all(p.grad is None for p in net.parameters())
+        net(x).square().mean().backward()
+        want = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+        bucket.all_reduce_mean()                                  # world size 1: collect only
+        assert torch.equal(want, bucket.flat)
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket._views))
+        opt.step()
+    before = bucket.flat.clone()
+    net(x).square().mean().backward()                             # no zero_(): accumulates into the views in place
+    assert not torch.equal(before, bucket.flat) and all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket._views))
+    bucket.zero_()
+    net[0](x).sum().backward()                                    # only the first layer is reached
+    f = bucket.flat
+    assert float(f[:35].abs().max()) > 0 and float(f[42:].abs().max()) == 0.0
+    bucket.zero_()
+    net(x).square().mean().backward()
+    want = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    assert torch.equal(bucket.flat, want)                         # `flat` collects on first access
