@@ -28,6 +28,34 @@ def _free_port():
     return p
 
 
+def _spawn(target, world=2, attempts=2):
+    """Run `target(rank, world, port, queue)` in `world` spawned processes and return their results; a failed rendezvous
+    (the probed port taken in the meantime, a loaded host) is retried once on a fresh port."""
+    import queue as _queue
+    last = None
+    for _ in range(attempts):
+        port = _free_port()
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=target, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        try:
+            got = [q.get(timeout=180) for _ in range(world)]
+            for p in procs:
+                p.join(timeout=60)
+            if all(p.exitcode == 0 for p in procs):
+                return got
+            last = f"exit codes {[p.exitcode for p in procs]}"
+        except _queue.Empty:
+            last = "no result within 180 s"
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+            p.join(timeout=10)
+    raise AssertionError(f"workers failed on {attempts} attempts: {last}")
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
@@ -56,16 +84,7 @@ def _offsets(params):
 
 
 def test_flat_bucket_allreduce_matches_full_batch():
-    world, port = 2, _free_port()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    got = [q.get(timeout=120) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    got = _spawn(_worker)
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
     data = torch.arange(8 * 5, dtype=torch.float32).view(8, 5) / 40.0
@@ -118,16 +137,7 @@ def _syncbn_worker(rank, world, port, q):
 
 
 def test_syncbn_protocol_matches_full_batch_batchnorm():
-    world, port = 2, _free_port()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_syncbn_worker, args=(r, world, port, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = sorted(_spawn(_syncbn_worker), key=lambda t: t[0])
     g = torch.Generator().manual_seed(7)
     c, slope, eps = 6, 0.01, 1e-5
     x_all = (torch.randn(8, c, generator=g, dtype=torch.float64) * 2 + 0.5).requires_grad_(True)
