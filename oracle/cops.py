@@ -105,3 +105,23 @@ def chamfer_backward(xyz1, xyz2, idx1, idx2, g1, g2):
     gx1, gx2 = np.zeros_like(xyz1), np.zeros_like(xyz2)
     lib().oracle_chamfer_bwd(b, n, _p(xyz1), m, _p(xyz2), _p(idx1), _p(idx2), _p(g1), _p(g2), _p(gx1), _p(gx2))
     return gx1, gx2
+
+
+def knn(pos, centers, k):
+    """PointNet2.py:85-87 -> idx int32 [B,S,k], dist [B,S,k] (ascending, ties to the smaller index)."""
+    pos, centers = _f(pos), _f(centers)
+    b, n, _ = pos.shape
+    s = centers.shape[1]
+    idx, dist = np.zeros((b, s, k), np.int32), np.zeros((b, s, k), np.float32)
+    lib().oracle_knn(b, n, s, int(k), _p(pos), _p(centers), _p(idx), _p(dist))
+    return idx, dist
+
+
+def three_nn(p1, p2):
+    """PointNet2.py:114-123 -> idx int32 [B,n2,3], weights [B,n2,3] (unused slots: index 0, weight 0)."""
+    p1, p2 = _f(p1), _f(p2)
+    b, n1, _ = p1.shape
+    n2 = p2.shape[1]
+    idx, w = np.zeros((b, n2, 3), np.int32), np.zeros((b, n2, 3), np.float32)
+    lib().oracle_three_nn(b, n1, n2, _p(p1), _p(p2), _p(idx), _p(w))
+    return idx, w

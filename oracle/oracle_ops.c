@@ -212,3 +212,78 @@ void oracle_chamfer_bwd(int b, int n, const float* xyz1, int m, const float* xyz
     chamfer_grad_dir(b, n, xyz1, m, xyz2, grad_dist1, idx1, grad_xyz1, grad_xyz2);
     chamfer_grad_dir(b, m, xyz2, n, xyz1, grad_dist2, idx2, grad_xyz2, grad_xyz1);
 }
+
+/* ---- PointNet++ neighbourhoods (SPConvNets/models/PointNet2.py:85-87, 114-123) --------------------------------------
+ * The reference evaluates these in torch: ppdist = sqrt(sum((centre - pos)^2, -1)) followed by topk(k, largest=False), and
+ * dist = norm(p2 - p1) followed by topk(3).  Restated here with the evaluation order torch uses (verified on the host, see
+ * tests/test_oracle_golden.py): sum over three elements = (dx*dx + dy*dy) + dz*dz with every product rounded (this file is
+ * compiled with -ffp-contract=off); torch.norm = sqrt(fma(dz,dz,fma(dy,dy,dx*dx))); square roots correctly rounded (what
+ * CUDA's sqrtf and numpy give; torch.sqrt on AVX-512 hosts is up to one ulp off).  Ties: smaller index first (torch.topk
+ * leaves the order of equal keys unspecified). */
+#include <math.h>
+
+void oracle_knn(int b, int n, int s, int k, const float* pos, const float* centers, int32_t* idx, float* dist) {
+    float* d2 = (float*)malloc(sizeof(float) * (size_t)n);
+    int32_t* best = (int32_t*)malloc(sizeof(int32_t) * (size_t)k);
+    for (int bi = 0; bi < b; ++bi)
+        for (int si = 0; si < s; ++si) {
+            const float* c = centers + ((size_t)bi * s + si) * 3;
+            const float* p = pos + (size_t)bi * n * 3;
+            for (int i = 0; i < n; ++i) {
+                const float dx = c[0] - p[3 * i], dy = c[1] - p[3 * i + 1], dz = c[2] - p[3 * i + 2];
+                const float xx = dx * dx, yy = dy * dy, zz = dz * dz;
+                const float t = xx + yy;
+                d2[i] = t + zz;
+            }
+            int cnt = 0;                                   /* insertion into the sorted list of the k best so far */
+            for (int i = 0; i < n; ++i) {
+                if (cnt == k && !(d2[i] < d2[best[k - 1]])) continue;      /* equal keys: the earlier index stays */
+                int j = cnt < k ? cnt : k - 1;
+                while (j > 0 && d2[i] < d2[best[j - 1]]) {
+                    best[j] = best[j - 1];
+                    --j;
+                }
+                best[j] = i;
+                if (cnt < k) ++cnt;
+            }
+            for (int j = 0; j < k; ++j) {
+                idx[((size_t)bi * s + si) * k + j] = best[j];
+                dist[((size_t)bi * s + si) * k + j] = sqrtf(d2[best[j]]);
+            }
+        }
+    free(d2);
+    free(best);
+}
+
+void oracle_three_nn(int b, int n1, int n2, const float* p1, const float* p2, int32_t* idx, float* w) {
+    const int kk = n1 < 3 ? n1 : 3;
+    for (int bi = 0; bi < b; ++bi)
+        for (int q = 0; q < n2; ++q) {
+            const float* qq = p2 + ((size_t)bi * n2 + q) * 3;
+            float d[3] = {INFINITY, INFINITY, INFINITY};
+            int id[3] = {0, 0, 0};
+            for (int i = 0; i < n1; ++i) {
+                const float* pp = p1 + ((size_t)bi * n1 + i) * 3;
+                const float dx = qq[0] - pp[0], dy = qq[1] - pp[1], dz = qq[2] - pp[2];
+                const float v = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                if (v < d[2]) {
+                    int j = 2;
+                    while (j > 0 && v < d[j - 1]) {
+                        d[j] = d[j - 1];
+                        id[j] = id[j - 1];
+                        --j;
+                    }
+                    d[j] = v;
+                    id[j] = i;
+                }
+            }
+            float r[3] = {0.f, 0.f, 0.f};
+            for (int j = 0; j < kk; ++j) r[j] = 1.0f / (d[j] + 1e-8f);
+            const float t = r[0] + r[1];
+            const float norm = t + r[2];
+            for (int j = 0; j < 3; ++j) {
+                idx[((size_t)bi * n2 + q) * 3 + j] = j < kk ? id[j] : 0;
+                w[((size_t)bi * n2 + q) * 3 + j] = r[j] / norm;
+            }
+        }
+}

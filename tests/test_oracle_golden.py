@@ -295,3 +295,43 @@ def test_pointnet2_oracle_gradient_defined():
     r.sum().backward()
     assert float(y.grad[(d > 0.5)].abs().max()) == 0.0
     assert torch.equal(y.grad.sum(2), torch.ones(2, 5, 4))
+
+
+def test_pointnet2_c_oracle_matches_torch_restatement_and_fixture(golden_dir):
+    """oracle_ops.c::oracle_knn / oracle_three_nn (plain C, explicit evaluation order, correctly rounded sqrt) against the
+    torch evaluation the reference performs: same neighbours, squared-distance order bit-exact, distances equal to
+    numpy's correctly rounded sqrt and within one ulp of torch.sqrt; and against the neighbour distances the reference's
+    own module produced (fixture)."""
+    g = torch.Generator().manual_seed(3)
+    pos = torch.rand(3, 500, 3, generator=g) - 0.5
+    cen = pos[:, torch.randperm(500, generator=g)[:40]].contiguous()
+    idx, dist = cops.knn(pos.numpy(), cen.numpy(), 64)
+    d2 = torch.sum((cen.unsqueeze(2) - pos.unsqueeze(1)) ** 2, dim=-1)                      # PointNet2.py:85
+    ref_d2, ref_i = torch.topk(d2, k=64, dim=2, largest=False)
+    assert np.array_equal(dist, np.sqrt(ref_d2.numpy()))
+    assert np.abs(dist - torch.sqrt(ref_d2).numpy()).max() <= 6e-8
+    uniq = np.ones(ref_d2.shape, bool)
+    same = (ref_d2[..., 1:] == ref_d2[..., :-1]).numpy()
+    uniq[..., 1:] &= ~same
+    uniq[..., :-1] &= ~same
+    uniq[..., -1] = False
+    assert np.array_equal(idx[uniq], ref_i.numpy()[uniq])
+    # ties resolve to the smaller index
+    grid = (torch.randint(-3, 4, (1, 200, 3), generator=g).float() * 0.25).contiguous()
+    gi, _ = cops.knn(grid.numpy(), grid[:, :8].contiguous().numpy(), 32)
+    full = torch.sum((grid[:, :8].unsqueeze(2) - grid.unsqueeze(1)) ** 2, dim=-1).double()
+    assert np.array_equal(gi, (full * 1e6 + torch.arange(200).double() * 1e-3).argsort(dim=2)[..., :32].numpy())
+    # the reference module's own neighbour distances (level 1 of the fixture), to one ulp of its torch.sqrt
+    f = np.load(os.path.join(golden_dir, "ref_pointnet2_small.npz"))
+    _, fd = cops.knn(f["pos"], f["pos_512"], 64)
+    assert np.abs(fd - f["topk_dist_512"]).max() <= 6e-8
+    # three nearest neighbours + inverse-distance weights (interpolate_features :114-123)
+    p1, p2 = torch.rand(2, 90, 3, generator=g) - 0.5, torch.rand(2, 300, 3, generator=g) - 0.5
+    ti, tw = cops.three_nn(p1.numpy(), p2.numpy())
+    dist3 = torch.norm(p2[:, :, None, :] - p1[:, None, :, :], dim=-1, p=2)
+    rd, ri = dist3.topk(3, dim=-1, largest=False)
+    assert np.array_equal(ti, ri.numpy())
+    rec = 1.0 / (rd + 1e-8)
+    assert np.abs(tw - (rec / rec.sum(2, keepdim=True)).numpy()).max() <= 2e-7          # torch.norm's sqrt: one ulp
+    one_i, one_w = cops.three_nn(p1[:, :1].contiguous().numpy(), p2.numpy())
+    assert (one_i == 0).all() and np.array_equal(one_w[..., 0], np.ones((2, 300), np.float32)) and (one_w[..., 1:] == 0).all()
