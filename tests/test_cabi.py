@@ -95,3 +95,24 @@ def test_pointnetpp_constructs_with_reference_keys_and_validates_sizes():
     assert set(two.state_dict().keys()) == set(OP.make_state(6, n_layers=2).keys())
     with pytest.raises(ValueError):
         net(torch.zeros(1, 100, 3), torch.zeros(1, 100, 3))           # 100 points < 512 centres: rejected before any launch
+
+
+def test_articulated_cloud_generators():
+    """synthetic 'oven' / 'laptop' clouds (BASELINE configs 3 / 5): deterministic per seed, unit bounding-box diagonal before
+    the global rotation (so every point within 0.5 of the centre), two parts, distinct poses per sample."""
+    import numpy as np
+    import torch
+    from equi_articulated_pose_b200 import synthetic
+    for kind in ("oven", "laptop"):
+        a = synthetic.articulated_cloud(kind, 3, 192, 11)
+        b = synthetic.articulated_cloud(kind, 3, 192, 11)
+        assert a.dtype == torch.float32 and tuple(a.shape) == (3, 192, 3) and torch.equal(a, b)
+        assert not torch.equal(a, synthetic.articulated_cloud(kind, 3, 192, 12))
+        assert float(a.norm(dim=2).max()) <= 0.5 + 1e-6           # inside the sphere circumscribing the unit-diagonal box
+        assert float(torch.cdist(a[0], a[0]).max()) > 0.6          # and spanning most of it
+        assert not torch.allclose(a[0], a[1])
+        d = torch.cdist(a[0], a[0]) + torch.eye(192) * 10
+        assert float(d.min()) > 1e-4                                # farthest-point sampled: no duplicate points
+    import pytest
+    with pytest.raises(ValueError):
+        synthetic.articulated_cloud("chair", 1, 16, 0)
