@@ -381,11 +381,16 @@ struct PairCfg {
     static_assert(STAGES >= 3 && BN % 64 == 0, "pair configuration");
 };
 
-template <int BN_>
+// PRE = true (EXPERIMENTAL, round-2 groundwork, not on any default path): the activation operand arrives ALREADY split
+// into bf16 hi / lo planes in global memory (map_a = hi plane, map_a2 = lo plane; same shape as the fp32 operand), so the
+// stage is filled by TMA in its final layout and the converter warps only forward the barrier -- the operand-conversion
+// work that bounds the narrow layers (profiles/r1_ncu_gemm_tn_stall_hotspots.txt) disappears from the kernel.
+template <int BN_, bool PRE = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                        const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c, int tma_out,
-                       const float* __restrict__ bias, float* __restrict__ C, int64_t M, int N, int K, int chunk_kb, TcGather ga) {
+                       const float* __restrict__ bias, float* __restrict__ C, int64_t M, int N, int K, int chunk_kb, TcGather ga,
+                       const __grid_constant__ CUtensorMap map_a2) {
     using Cfg = PairCfg<BN_>;
     constexpr int STAGES = Cfg::STAGES, BN = Cfg::BN, KBE = 64, UK = 16;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -531,8 +536,10 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
-                convert_rows_bf16(smem_base + s * Cfg::STAGE_BYTES, ct >> 5, lane);
-                fence_proxy_async();
+                if (!PRE) {
+                    convert_rows_bf16(smem_base + s * Cfg::STAGE_BYTES, ct >> 5, lane);
+                    fence_proxy_async();
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_remote(&bars.full[s], 0);
             }
@@ -583,6 +590,7 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         reg_dec_other();
         if (lane == 0) {
             tma_prefetch_desc(&map_a);
+            if (PRE) tma_prefetch_desc(&map_a2);
             tma_prefetch_desc(&map_bhi);
             tma_prefetch_desc(&map_blo);
             const uint32_t tx = 2u * (uint32_t)Cfg::A_BYTES + 2u * (uint32_t)Cfg::BH_BYTES;
@@ -595,7 +603,17 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
                     unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&bars.raw_full[s], tx);
-                    if (ga.anchors > 0) {
+                    if (PRE) {          // bf16 planes: one box of 64 columns per plane, already the MMA's layout
+                        if (ga.anchors > 0) {
+                            const int kcol = kb * KBE, kk = kcol / ga.c, c0 = kcol - kk * ga.c;
+                            const int mid = __ldg(ga.table + an * ga.kk_n + kk);
+                            tma_load_3d(st, &map_a, c0, mid, mt * TC_BM, &bars.raw_full[s]);
+                            tma_load_3d(st + Cfg::A_BYTES, &map_a2, c0, mid, mt * TC_BM, &bars.raw_full[s]);
+                        } else {
+                            tma_load_2d(st, &map_a, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
+                            tma_load_2d(st + Cfg::A_BYTES, &map_a2, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
+                        }
+                    } else if (ga.anchors > 0) {
                         const int kcol = kb * KBE, kk = kcol / ga.c, c0 = kcol - kk * ga.c;
                         const int mid = __ldg(ga.table + an * ga.kk_n + kk);
                         tma_load_3d(st, &map_a, c0, mid, mt * TC_BM, &bars.raw_full[s]);
@@ -1320,14 +1338,20 @@ static int tc_gemm_nt_impl(int64_t M, int N, int K, const float* A, const float*
                            float* workspace, cudaStream_t st, TcGather ga);
 
 // CTA-pair launch (bf16x3, N > 128): clusters of two CTAs, one pair per two SMs
-template <int BN_>
-static int launch_nt_pair(int64_t M, int N, int K, const float* A, const void* Bhi, const void* Blo, const float* bias, float* C,
-                          cudaStream_t st, TcGather ga) {
+template <int BN_, bool PRE = false>
+static int launch_nt_pair(int64_t M, int N, int K, const void* A, const void* Bhi, const void* Blo, const float* bias, float* C,
+                          cudaStream_t st, TcGather ga, const void* A_lo = nullptr) {
     using Cfg = PairCfg<BN_>;
-    CUtensorMap ma, mhi, mlo, mc;
-    int rc = ga.anchors > 0 ? make_map_3d(&ma, A, M, ga.anchors, ga.c, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B)
-                            : make_map_2d(&ma, A, M, K, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap ma, mhi, mlo, mc, ma2;
+    int rc = ga.anchors > 0 ? make_map_3d(&ma, A, M, ga.anchors, ga.c, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B, PRE)
+                            : make_map_2d(&ma, A, M, K, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B, PRE);
     if (rc) return rc;
+    ma2 = ma;
+    if (PRE) {
+        rc = ga.anchors > 0 ? make_map_3d(&ma2, A_lo, M, ga.anchors, ga.c, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B, true)
+                            : make_map_2d(&ma2, A_lo, M, K, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B, true);
+        if (rc) return rc;
+    }
     rc = make_map_2d(&mhi, Bhi, N, K, Cfg::BN / 2, CU_TENSOR_MAP_SWIZZLE_128B, true);
     if (rc) return rc;
     rc = make_map_2d(&mlo, Blo, N, K, Cfg::BN / 2, CU_TENSOR_MAP_SWIZZLE_128B, true);
@@ -1342,7 +1366,7 @@ static int launch_nt_pair(int64_t M, int N, int K, const float* A, const void* B
         if (rc) return rc;
     }
     const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024 + TC_EPI_WARPS * 4096;
-    auto kern = tc_gemm_nt_pair_kernel<BN_>;
+    auto kern = tc_gemm_nt_pair_kernel<BN_, PRE>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t pair_tiles = ceil_div64(ceil_div64(M, TC_BM), 2) * ceil_div(N, Cfg::BN) * (ga.anchors > 0 ? ga.anchors : 1);
     const int max_pairs = num_sms() / 2;
@@ -1359,7 +1383,7 @@ static int launch_nt_pair(int64_t M, int N, int K, const float* A, const void* B
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VGTKB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mhi, mlo, mc, tma_out, bias, C, M, N, K, default_chunk(3, true), ga));
+    VGTKB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mhi, mlo, mc, tma_out, bias, C, M, N, K, default_chunk(3, true), ga, ma2));
     return check_launch("gemm_nt(tcgen05, cta pairs)");
 }
 
@@ -1590,3 +1614,37 @@ int tc_gemm_tn_gather(int64_t points, int anchors, int kk_n, int c_n, int M, con
 }
 
 }  // namespace vgtkb
+
+// ---------------------------------------------------------------------------------- EXPERIMENTAL (round-2 groundwork)
+// Pre-split activation operand: C[M,N] = (A_hi + A_lo)[M,K] * B[N,K]^T (+ bias) with A given as two bf16 planes
+// (hi = bf16_rn(a), lo = bf16_rn(a - hi): vgtkb_split_bf16) -- the same bf16x3 arithmetic as mode 3 of vgtkb_gemm_nt,
+// without the in-kernel operand conversion.  Not called by any default path; parity test gated on VGTKB_EXPERIMENTAL=1.
+
+extern "C" int vgtkb_split_bf16(int64_t n, const float* x, void* hi, void* lo, void* stream) {
+    using namespace vgtkb;
+    VGTKB_REQUIRE(n >= 0, "split_bf16: bad size");
+    if (n == 0) return VGTKB_OK;
+    const int blocks = (int)(ceil_div64(n, 256) < 1184 ? ceil_div64(n, 256) : 1184);
+    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, x, reinterpret_cast<uint16_t*>(hi), reinterpret_cast<uint16_t*>(lo));
+    return check_launch("split_bf16");
+}
+
+extern "C" int vgtkb_gemm_nt_presplit(int64_t M, int N, int K, const void* a_hi, const void* a_lo, const float* B,
+                                      const float* bias, float* C, float* workspace, void* stream) {
+    using namespace vgtkb;
+    VGTKB_REQUIRE(M >= 1 && N >= 1 && K >= 64, "gemm_nt_presplit: bad size");
+    VGTKB_REQUIRE(K % 8 == 0 && M < ((int64_t)1 << 31), "gemm_nt_presplit: K must be a multiple of 8, M < 2^31");
+    VGTKB_REQUIRE(((reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) | reinterpret_cast<uintptr_t>(B) |
+                    reinterpret_cast<uintptr_t>(workspace)) & 15) == 0 && workspace != nullptr,
+                  "gemm_nt_presplit: operands and workspace (N*K floats) must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nb = (int64_t)N * K;
+    const int blocks = (int)(ceil_div64(nb, 256) < 1184 ? ceil_div64(nb, 256) : 1184);
+    uint16_t* bhi = reinterpret_cast<uint16_t*>(workspace);
+    uint16_t* blo = bhi + nb;
+    split_bf16_kernel<<<blocks, 256, 0, st>>>(nb, B, bhi, blo);
+    const TcGather none{0, 0, 0, nullptr};
+    if (N <= 64) return launch_nt_pair<64, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo);
+    if (N <= 128) return launch_nt_pair<128, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo);
+    return launch_nt_pair<256, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo);
+}

@@ -693,3 +693,29 @@ class ThreeInterpolateFn(torch.autograd.Function):
 
 def three_interpolate(feat, idx, w):
     return ThreeInterpolateFn.apply(feat, idx, w)
+
+
+# ----------------------------------------------------------------------------- experimental (round-2 groundwork)
+def split_bf16(x):
+    """fp32 tensor -> (hi, lo) bf16 planes with hi = bf16_rn(x), lo = bf16_rn(x - hi) (the operand split of gemm mode 3)."""
+    x = _f32(x)
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    call("vgtkb_split_bf16", x.device, x.numel(), ptr(x), ptr(hi), ptr(lo))
+    return hi, lo
+
+
+def gemm_nt_presplit(a_hi, a_lo, b, bias=None):
+    """C[M,N] = (a_hi + a_lo)[M,K] @ b[N,K]^T (+ bias): the bf16x3 contraction with its activation operand already stored
+    as bf16 planes (no in-kernel conversion).  EXPERIMENTAL: not used by any module; see include/vgtkb.h."""
+    if a_hi.dtype != torch.bfloat16 or a_lo.dtype != torch.bfloat16 or a_hi.shape != a_lo.shape:
+        raise _lib.VgtkbError("gemm_nt_presplit: two bf16 planes of the same shape expected")
+    b = _f32(b)
+    m, k = a_hi.shape
+    n = b.shape[0]
+    assert b.shape[1] == k
+    c = torch.empty((m, n), dtype=torch.float32, device=b.device)
+    ws = torch.empty(n * k, dtype=torch.float32, device=b.device)
+    call("vgtkb_gemm_nt_presplit", b.device, m, n, k, ptr(a_hi.contiguous()), ptr(a_lo.contiguous()), ptr(b),
+         ptr(bias.contiguous()) if bias is not None else None, ptr(c), ptr(ws))
+    return c

@@ -287,6 +287,16 @@ int vgtkb_three_interpolate_forward(int b, int n1, int n2, int c, const float* f
 int vgtkb_three_interpolate_backward(int b, int n1, int n2, int c, const float* grad_out, const int32_t* idx, const float* w,
                                      float* grad_feat, void* stream);
 
+/* EXPERIMENTAL (round-2 groundwork; no default path calls these, csrc/gemm_tc.cu): activation operand stored once as two
+ * bf16 planes (hi = bf16_rn(x), lo = bf16_rn(x - hi)) by its producer, consumed by the contraction without the in-kernel
+ * operand conversion that bounds the narrow layers.
+ *   split_bf16:        hi / lo planes (uint16 bf16 bit patterns, n elements each) of an fp32 array
+ *   gemm_nt_presplit:  C [M, N] = (a_hi + a_lo) [M, K] * B [N, K]^T (+ bias), bf16x3 arithmetic of vgtkb_gemm_nt mode 3;
+ *                      K % 8 == 0, K >= 64; workspace: N*K floats (hi / lo planes of B), 16-byte aligned */
+int vgtkb_split_bf16(int64_t n, const float* x, void* hi, void* lo, void* stream);
+int vgtkb_gemm_nt_presplit(int64_t M, int N, int K, const void* a_hi, const void* a_lo, const float* B, const float* bias,
+                           float* C, float* workspace, void* stream);
+
 /* column sums of a row-major [rows, c] matrix (bias gradient of the skip conv) */
 int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream);
 

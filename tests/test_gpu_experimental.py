@@ -1,0 +1,30 @@
+"""Round-2 groundwork, NOT part of the default suite: parity of the pre-split-operand contraction
+(vgtkb_split_bf16 + vgtkb_gemm_nt_presplit, csrc/gemm_tc.cu template PRE) against mode 3 of vgtkb_gemm_nt, whose arithmetic it
+reproduces (bit-identical results expected: same operand split, same MMA order, same chunked accumulation).
+The path was written after the GPU budget of round 1 was spent; run with VGTKB_EXPERIMENTAL=1 on a B200."""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("VGTKB_EXPERIMENTAL", "0") != "1", reason="experimental path: set VGTKB_EXPERIMENTAL=1")]
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 64, 1536), (1000, 128, 3072), (61440, 256, 6144), (300, 256, 64), (129, 72, 128)])
+def test_presplit_contraction_matches_mode3(M, N, K):
+    from equi_articulated_pose_b200 import lib, ops
+    lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(dev)
+    b = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    hi, lo = ops.split_bf16(a)
+    assert torch.equal(hi.float(), a.to(torch.bfloat16).float())                       # round to nearest even
+    assert torch.equal(lo.float(), (a - hi.float()).to(torch.bfloat16).float())
+    ref = ops.gemm_nt(a, b, bias, mode=3)
+    out = ops.gemm_nt_presplit(hi, lo, b, bias)
+    assert torch.equal(out, ref)
+    truth = (a.double() @ b.double().t() + bias.double()).float()
+    assert float((out - truth).abs().max() / truth.abs().max()) < 2e-5
