@@ -736,12 +736,14 @@ __device__ __forceinline__ void convert_tn_rows4_bf16(uint32_t region, int k0, i
 // BF = false: kind::tf32 (k-block = 32 rows of R).  BF = true: bf16x3, kind::f16, k-block = 64 rows of R,
 // operands in the canonical 128B-swizzled MN-major bf16 layout: stage = [mn-atom of 64 columns][64 k-rows x 128 B],
 // LBO (next MN atom) = 8192 B, SBO (next 8 k-rows) = 1024 B, one MMA (K = 16) starts 2048 B after the previous.
-template <int BN, bool BF>
+// PRE = true (EXPERIMENTAL, with BF; round-2 groundwork, not on any default path): the wide operand P arrives as two
+// bf16 planes (map_p = hi, map_p2 = lo) and is loaded by TMA in the MMA's layout, like Q; the converters only forward the barrier.
+template <int BN, bool BF, bool PRE = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
                   const __grid_constant__ CUtensorMap map_q2, int Pw, int Qw,
                   float* __restrict__ C, int ldc, int64_t R, int64_t rows_per_split, int splits, int passes, int chunk_kb,
-                  TcGather ga, int anchors_per_item) {
+                  TcGather ga, int anchors_per_item, const __grid_constant__ CUtensorMap map_p2) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr uint32_t MN_LBO = BF ? 8192 : 4096, K_SBO = BF ? 1024 : 512, L32 = BF ? 2 : 1;
@@ -833,7 +835,9 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
             for (int kb = 0; kb < nblk; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
-                if (BF) {
+                if (BF && PRE) {
+                    // both operands arrived in their final layout
+                } else if (BF) {
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
                     // only P is converted here: Q (the narrow operand every P tile re-reads) was split to bf16
                     // hi/lo once in global memory and arrives in its final layout through TMA
@@ -932,6 +936,17 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
                     if (ga.anchors > 0) {
                         // gathered P: column (kk, c) of anchor `an` lives at X[point, table[an, kk], c]
                         const int an = a0 + kb / nkb;
+                        if (PRE) {
+#pragma unroll
+                            for (int a = 0; a < TC_BM / 64; ++a) {       // bf16 planes: atoms of 64 columns, final layout
+                                const int cc = p0 + a * 64;
+                                const int kk = cc < Pw ? cc / ga.c : 0;
+                                const int c0 = cc < Pw ? cc - kk * ga.c : ga.c;                 // out of bounds: zeros
+                                const int mid = cc < Pw ? __ldg(ga.table + an * ga.kk_n + kk) : 0;
+                                tma_load_3d(st + a * 8192, &map_p, c0, mid, row, &bars.raw_full[s]);
+                                tma_load_3d(st + Cfg::A_BYTES + a * 8192, &map_p2, c0, mid, row, &bars.raw_full[s]);
+                            }
+                        } else
 #pragma unroll
                         for (int a = 0; a < TC_BM / 32; ++a) {
                             const int cc = p0 + a * 32;
@@ -955,6 +970,13 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
                         }
                         continue;
                     }
+                    if (PRE) {
+#pragma unroll
+                        for (int a = 0; a < TC_BM / 64; ++a) {
+                            tma_load_2d(st + a * 8192, &map_p, p0 + a * 64, row, &bars.raw_full[s]);
+                            tma_load_2d(st + Cfg::A_BYTES + a * 8192, &map_p2, p0 + a * 64, row, &bars.raw_full[s]);
+                        }
+                    } else
 #pragma unroll
                     for (int a = 0; a < TC_BM / 32; ++a)
                         tma_load_2d(st + a * BOX_BYTES, &map_p, p0 + a * 32, row, &bars.raw_full[s]);
@@ -1000,11 +1022,12 @@ struct TnPairCfg {
     static_assert(STAGES >= 3 && BN % 128 == 0, "pair configuration");
 };
 
-template <int BN_>
+template <int BN_, bool PRE = false>       // PRE: see tc_gemm_tn_kernel (experimental pre-split P operand)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
                        const __grid_constant__ CUtensorMap map_q2, int Pw, int Qw, float* __restrict__ C, int ldc, int64_t R,
-                       int64_t rows_per_split, int splits, int chunk_kb, TcGather ga, int anchors_per_item) {
+                       int64_t rows_per_split, int splits, int chunk_kb, TcGather ga, int anchors_per_item,
+                       const __grid_constant__ CUtensorMap map_p2) {
     using Cfg = TnPairCfg<BN_>;
     constexpr int STAGES = Cfg::STAGES, BN = Cfg::BN, KR = 64, UK = 16;
     constexpr uint32_t MN_LBO = 8192, K_SBO = 1024, KSTEP_BYTES = 2048;
@@ -1104,9 +1127,11 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
             for (int kb = 0; kb < nblk; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
-                const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
-                for (int task = ct >> 5; task < KR / 4; task += TC_CONV_WARPS) convert_tn_rows4_bf16(st, task * 4, lane);
-                fence_proxy_async();
+                if (!PRE) {
+                    const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+                    for (int task = ct >> 5; task < KR / 4; task += TC_CONV_WARPS) convert_tn_rows4_bf16(st, task * 4, lane);
+                    fence_proxy_async();
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_remote(&bars.full[s], 0);
             }
@@ -1183,6 +1208,17 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
                     mbar_arrive_expect_tx(&bars.raw_full[s], tx);
                     if (ga.anchors > 0) {
                         const int an = a0 + kb / nkb;
+                        if (PRE) {
+#pragma unroll
+                            for (int a = 0; a < TC_BM / 64; ++a) {
+                                const int cc = p0 + a * 64;
+                                const int kk = cc < Pw ? cc / ga.c : 0;
+                                const int c0 = cc < Pw ? cc - kk * ga.c : ga.c;                 // out of bounds: zeros
+                                const int mid = cc < Pw ? __ldg(ga.table + an * ga.kk_n + kk) : 0;
+                                tma_load_3d(st + a * 8192, &map_p, c0, mid, row, &bars.raw_full[s]);
+                                tma_load_3d(st + Cfg::A_BYTES + a * 8192, &map_p2, c0, mid, row, &bars.raw_full[s]);
+                            }
+                        } else
 #pragma unroll
                         for (int a = 0; a < TC_BM / 32; ++a) {
                             const int cc = p0 + a * 32;
@@ -1200,6 +1236,13 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
                         }
                         continue;
                     }
+                    if (PRE) {
+#pragma unroll
+                        for (int a = 0; a < TC_BM / 64; ++a) {
+                            tma_load_2d(st + a * 8192, &map_p, p0 + a * 64, row, &bars.raw_full[s]);
+                            tma_load_2d(st + Cfg::A_BYTES + a * 8192, &map_p2, p0 + a * 64, row, &bars.raw_full[s]);
+                        }
+                    } else
 #pragma unroll
                     for (int a = 0; a < TC_BM / 32; ++a)
                         tma_load_2d(st + a * 8192, &map_p, p0 + a * 32, row, &bars.raw_full[s]);
@@ -1443,24 +1486,32 @@ static int tc_gemm_nt_impl(int64_t M, int N, int K, const float* A, const float*
     return rc;
 }
 
-template <int BN, bool BF>
-static int launch_tn(const float* P, int Pw, const void* Q, const void* Q2, int Qw, float* C, int ldc, int64_t R, int passes,
-                     cudaStream_t st, TcGather ga = TcGather{0, 0, 0, nullptr}) {
+template <int BN, bool BF, bool PRE = false>
+static int launch_tn(const void* P, int Pw, const void* Q, const void* Q2, int Qw, float* C, int ldc, int64_t R, int passes,
+                     cudaStream_t st, TcGather ga = TcGather{0, 0, 0, nullptr}, const void* P_lo = nullptr) {
     using Cfg = TcCfg<BN>;
     constexpr int KR = BF ? 64 : TC_BK;
-    CUtensorMap mp, mq, mq2;
+    CUtensorMap mp, mq, mq2, mp2;
     const CUtensorMapSwizzle swz = BF ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     int rc;
     if (ga.anchors > 0) {   // R = points; P = X [points, anchors, c]; Q = Y [points, anchors, Qw]
-        rc = make_map_3d(&mp, P, R, ga.anchors, ga.c, KR, swz);
+        rc = make_map_3d(&mp, P, R, ga.anchors, ga.c, KR, swz, PRE);
         if (rc) return rc;
+        if (PRE) {
+            rc = make_map_3d(&mp2, P_lo, R, ga.anchors, ga.c, KR, swz, true);
+            if (rc) return rc;
+        }
         rc = make_map_3d(&mq, Q, R, ga.anchors, Qw, KR, swz, BF);
         if (rc) return rc;
         rc = make_map_3d(&mq2, Q2, R, ga.anchors, Qw, KR, swz, BF);
         if (rc) return rc;
     } else {
-        rc = make_map_2d(&mp, P, R, Pw, KR, swz);
+        rc = make_map_2d(&mp, P, R, Pw, KR, swz, PRE);
         if (rc) return rc;
+        if (PRE) {
+            rc = make_map_2d(&mp2, P_lo, R, Pw, KR, swz, true);
+            if (rc) return rc;
+        }
         rc = make_map_2d(&mq, Q, R, Qw, KR, swz, BF);      // BF: bf16 hi, box = 64 columns x 64 rows
         if (rc) return rc;
         rc = make_map_2d(&mq2, Q2, R, Qw, KR, swz, BF);    // BF: bf16 lo (tf32 path: unused duplicate)
@@ -1482,33 +1533,42 @@ static int launch_tn(const float* P, int Pw, const void* Q, const void* Q2, int 
     splits = ceil_div64(R, rps);
     const int64_t items = splits * tiles * n_groups;
     const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024;
-    auto kern = tc_gemm_tn_kernel<BN, BF>;
+    if (!PRE) mp2 = mp;
+    auto kern = tc_gemm_tn_kernel<BN, BF, PRE>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)(items < num_sms() ? items : num_sms());
     kern<<<grid, TC_THREADS, smem, st>>>(mp, mq, mq2, Pw, Qw, C, ldc, R, rps, (int)splits, passes, default_chunk(passes, BF),
-                                         ga, ag);
+                                         ga, ag, mp2);
     return check_launch("gemm_tn(tcgen05)");
 }
 
 // CTA-pair launch of the bf16x3 weight-gradient kernel (Q tile 128 or 256)
-template <int BN_>
-static int launch_tn_pair(const float* P, int Pw, const void* Q, const void* Q2, int Qw, float* C, int ldc, int64_t R,
-                          cudaStream_t st, TcGather ga = TcGather{0, 0, 0, nullptr}) {
+template <int BN_, bool PRE = false>
+static int launch_tn_pair(const void* P, int Pw, const void* Q, const void* Q2, int Qw, float* C, int ldc, int64_t R,
+                          cudaStream_t st, TcGather ga = TcGather{0, 0, 0, nullptr}, const void* P_lo = nullptr) {
     using Cfg = TnPairCfg<BN_>;
     constexpr int KR = 64;
-    CUtensorMap mp, mq, mq2;
+    CUtensorMap mp, mq, mq2, mp2;
     const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;
     int rc;
     if (ga.anchors > 0) {
-        rc = make_map_3d(&mp, P, R, ga.anchors, ga.c, KR, swz);
+        rc = make_map_3d(&mp, P, R, ga.anchors, ga.c, KR, swz, PRE);
         if (rc) return rc;
+        if (PRE) {
+            rc = make_map_3d(&mp2, P_lo, R, ga.anchors, ga.c, KR, swz, true);
+            if (rc) return rc;
+        }
         rc = make_map_3d(&mq, Q, R, ga.anchors, Qw, KR, swz, true);
         if (rc) return rc;
         rc = make_map_3d(&mq2, Q2, R, ga.anchors, Qw, KR, swz, true);
         if (rc) return rc;
     } else {
-        rc = make_map_2d(&mp, P, R, Pw, KR, swz);
+        rc = make_map_2d(&mp, P, R, Pw, KR, swz, PRE);
         if (rc) return rc;
+        if (PRE) {
+            rc = make_map_2d(&mp2, P_lo, R, Pw, KR, swz, true);
+            if (rc) return rc;
+        }
         rc = make_map_2d(&mq, Q, R, Qw, KR, swz, true);
         if (rc) return rc;
         rc = make_map_2d(&mq2, Q2, R, Qw, KR, swz, true);
@@ -1531,7 +1591,8 @@ static int launch_tn_pair(const float* P, int Pw, const void* Q, const void* Q2,
     splits = ceil_div64(R, rps);
     const int64_t items = splits * tiles * n_groups;
     const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024;
-    auto kern = tc_gemm_tn_pair_kernel<BN_>;
+    if (!PRE) mp2 = mp;
+    auto kern = tc_gemm_tn_pair_kernel<BN_, PRE>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int pairs = (int)(items < max_pairs ? items : max_pairs);
     cudaLaunchConfig_t cfg = {};
@@ -1546,7 +1607,7 @@ static int launch_tn_pair(const float* P, int Pw, const void* Q, const void* Q2,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VGTKB_CUDA(cudaLaunchKernelEx(&cfg, kern, mp, mq, mq2, Pw, Qw, C, ldc, R, rps, (int)splits, default_chunk(3, true), ga, ag));
+    VGTKB_CUDA(cudaLaunchKernelEx(&cfg, kern, mp, mq, mq2, Pw, Qw, C, ldc, R, rps, (int)splits, default_chunk(3, true), ga, ag, mp2));
     return check_launch("gemm_tn(tcgen05, cta pairs)");
 }
 
@@ -1647,4 +1708,30 @@ extern "C" int vgtkb_gemm_nt_presplit(int64_t M, int N, int K, const void* a_hi,
     if (N <= 64) return launch_nt_pair<64, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo);
     if (N <= 128) return launch_nt_pair<128, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo);
     return launch_nt_pair<256, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo);
+}
+
+// weight-gradient counterpart: C [M, N] (+)= A [R, M]^T * (b_hi + b_lo) [R, N]; A (narrow, fp32) is split here as in
+// vgtkb_gemm_tn, the wide operand arrives as bf16 planes.  workspace: R*M floats.
+extern "C" int vgtkb_gemm_tn_presplit(int M, int N, int64_t R, const float* A, const void* b_hi, const void* b_lo, float* C,
+                                      int accumulate, float* workspace, void* stream) {
+    using namespace vgtkb;
+    VGTKB_REQUIRE(M >= 8 && M % 8 == 0 && M <= 256 && N >= 64 && N % 8 == 0 && R >= 64 && R < ((int64_t)1 << 31),
+                  "gemm_tn_presplit: needs M % 8 == 0, M <= 256, N % 8 == 0, R >= 64");
+    VGTKB_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo) |
+                    reinterpret_cast<uintptr_t>(workspace)) & 15) == 0 && workspace != nullptr,
+                  "gemm_tn_presplit: operands and workspace (R*M floats) must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+    const int64_t na = R * (int64_t)M;
+    uint16_t* hi = reinterpret_cast<uint16_t*>(workspace);
+    uint16_t* lo = hi + na;
+    const int blocks = (int)(ceil_div64(na, 256) < 2368 ? ceil_div64(na, 256) : 2368);
+    split_bf16_kernel<<<blocks, 256, 0, st>>>(na, A, hi, lo);
+    const TcGather none{0, 0, 0, nullptr};
+    if (M <= 64) return launch_tn<64, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
+    if (N > TC_BM)
+        return M <= 128 ? launch_tn_pair<128, true>(b_hi, N, hi, lo, M, C, N, R, st, none, b_lo)
+                        : launch_tn_pair<256, true>(b_hi, N, hi, lo, M, C, N, R, st, none, b_lo);
+    if (M <= 128) return launch_tn<128, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
+    return launch_tn<256, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
 }

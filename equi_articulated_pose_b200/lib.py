@@ -59,6 +59,7 @@ SIGNATURES = {
     "vgtkb_pointnet_pool_backward": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_split_bf16": [c_i64, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_gemm_nt_presplit": [c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_gemm_tn_presplit": [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp],
     "vgtkb_knn_query": [c_int] * 4 + [c_vp] * 5,
     "vgtkb_sa_group_forward": [c_int] * 6 + [c_vp] * 6,
     "vgtkb_sa_group_backward": [c_int] * 6 + [c_vp] * 4,

@@ -719,3 +719,18 @@ def gemm_nt_presplit(a_hi, a_lo, b, bias=None):
     call("vgtkb_gemm_nt_presplit", b.device, m, n, k, ptr(a_hi.contiguous()), ptr(a_lo.contiguous()), ptr(b),
          ptr(bias.contiguous()) if bias is not None else None, ptr(c), ptr(ws))
     return c
+
+
+def gemm_tn_presplit(a, b_hi, b_lo):
+    """C[M,N] = a[R,M]^T @ (b_hi + b_lo)[R,N]: the bf16x3 weight-gradient contraction with its wide operand stored as bf16
+    planes.  EXPERIMENTAL: not used by any module; see include/vgtkb.h."""
+    if b_hi.dtype != torch.bfloat16 or b_lo.dtype != torch.bfloat16 or b_hi.shape != b_lo.shape:
+        raise _lib.VgtkbError("gemm_tn_presplit: two bf16 planes of the same shape expected")
+    a = _f32(a)
+    r, m = a.shape
+    n = b_hi.shape[1]
+    assert b_hi.shape[0] == r
+    c = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    ws = torch.empty(r * m, dtype=torch.float32, device=a.device)
+    call("vgtkb_gemm_tn_presplit", a.device, m, n, r, ptr(a), ptr(b_hi.contiguous()), ptr(b_lo.contiguous()), ptr(c), 0, ptr(ws))
+    return c

@@ -296,6 +296,10 @@ int vgtkb_three_interpolate_backward(int b, int n1, int n2, int c, const float* 
 int vgtkb_split_bf16(int64_t n, const float* x, void* hi, void* lo, void* stream);
 int vgtkb_gemm_nt_presplit(int64_t M, int N, int K, const void* a_hi, const void* a_lo, const float* B, const float* bias,
                            float* C, float* workspace, void* stream);
+/*   gemm_tn_presplit:  C [M, N] (+)= A [R, M]^T * (b_hi + b_lo) [R, N] (weight gradient with the wide operand as planes);
+ *                      M % 8 == 0, M <= 256, N % 8 == 0, R >= 64; workspace: R*M floats (split of the narrow operand) */
+int vgtkb_gemm_tn_presplit(int M, int N, int64_t R, const float* A, const void* b_hi, const void* b_lo, float* C, int accumulate,
+                           float* workspace, void* stream);
 
 /* column sums of a row-major [rows, c] matrix (bias gradient of the skip conv) */
 int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream);

@@ -28,3 +28,22 @@ def test_presplit_contraction_matches_mode3(M, N, K):
     assert torch.equal(out, ref)
     truth = (a.double() @ b.double().t() + bias.double()).float()
     assert float((out - truth).abs().max() / truth.abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,R", [(64, 1536, 24576), (128, 3072, 12288), (256, 6144, 6144), (64, 128, 4096), (256, 192, 1000)])
+def test_presplit_weight_gradient_matches_mode3(M, N, R):
+    """C = a^T (b_hi + b_lo): the wide operand as planes; same arithmetic as mode 3 of vgtkb_gemm_tn up to the order of the
+    red.global.add partial sums over the R splits (so: tight tolerance, not bit equality)."""
+    from equi_articulated_pose_b200 import lib, ops
+    lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + N + R)
+    a = torch.randn(R, M, generator=g).to(dev)
+    b = torch.randn(R, N, generator=g).to(dev)
+    hi, lo = ops.split_bf16(b)
+    ref = ops.gemm_tn(a, b, mode=3)
+    out = ops.gemm_tn_presplit(a, hi, lo)
+    truth = (a.double().t() @ b.double()).float()
+    scale = float(truth.abs().max())
+    assert float((out - ref).abs().max()) < 2e-6 * scale
+    assert float((out - truth).abs().max()) < 2e-5 * scale
