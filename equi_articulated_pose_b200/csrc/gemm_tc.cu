@@ -1312,6 +1312,26 @@ int tc::make_rows_map(TmaMap* out, const void* base, int64_t rows, int64_t cols,
     return make_map_2d(reinterpret_cast<CUtensorMap*>(out), base, rows, cols, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+int tc::make_plane_map(TmaMap* out, const void* base, int64_t rows, int64_t cols, int box_rows) {
+    EncodeTiledFn enc = get_encoder();
+    if (enc == nullptr) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return VGTKB_EUNSUP;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                           gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(plane) failed (%d)", (int)r);
+        return VGTKB_ECUDA;
+    }
+    return VGTKB_OK;
+}
+
 // X [points, anchors, c] fp32 (or bf16) as a 3-D tensor; box = [box_rows points, 1 anchor, 128 bytes of channels]
 static int make_map_3d(CUtensorMap* map, const void* base, int64_t points, int anchors, int c, int box_rows,
                        CUtensorMapSwizzle swz, bool bf16 = false) {
@@ -1676,10 +1696,10 @@ int tc_gemm_tn_gather(int64_t points, int anchors, int kk_n, int c_n, int M, con
 
 }  // namespace vgtkb
 
-// ---------------------------------------------------------------------------------- EXPERIMENTAL (round-2 groundwork)
-// Pre-split activation operand: C[M,N] = (A_hi + A_lo)[M,K] * B[N,K]^T (+ bias) with A given as two bf16 planes
-// (hi = bf16_rn(a), lo = bf16_rn(a - hi): vgtkb_split_bf16) -- the same bf16x3 arithmetic as mode 3 of vgtkb_gemm_nt,
-// without the in-kernel operand conversion.  Not called by any default path; parity test gated on VGTKB_EXPERIMENTAL=1.
+// ---------------------------------------------------------------------------------- pre-split (plane) operands
+// C[M,N] = (A_hi + A_lo)[M,K] * B[N,K]^T (+ bias) with A given as two bf16 planes (hi = bf16_rn(a), lo = bf16_rn(a - hi):
+// vgtkb_split_bf16, or written directly by the producer -- vgtkb_inter_conv_forward's grouping kernel): the same bf16x3
+// arithmetic as mode 3 of vgtkb_gemm_nt (bit-identical results), without the in-kernel operand conversion.
 
 extern "C" int vgtkb_split_bf16(int64_t n, const float* x, void* hi, void* lo, void* stream) {
     using namespace vgtkb;
@@ -1690,15 +1710,15 @@ extern "C" int vgtkb_split_bf16(int64_t n, const float* x, void* hi, void* lo, v
     return check_launch("split_bf16");
 }
 
-extern "C" int vgtkb_gemm_nt_presplit(int64_t M, int N, int K, const void* a_hi, const void* a_lo, const float* B,
-                                      const float* bias, float* C, float* workspace, void* stream) {
-    using namespace vgtkb;
-    VGTKB_REQUIRE(M >= 1 && N >= 1 && K >= 64, "gemm_nt_presplit: bad size");
-    VGTKB_REQUIRE(K % 8 == 0 && M < ((int64_t)1 << 31), "gemm_nt_presplit: K must be a multiple of 8, M < 2^31");
-    VGTKB_REQUIRE(((reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) | reinterpret_cast<uintptr_t>(B) |
-                    reinterpret_cast<uintptr_t>(workspace)) & 15) == 0 && workspace != nullptr,
-                  "gemm_nt_presplit: operands and workspace (N*K floats) must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
+namespace vgtkb {
+// C[M,N] = (a_hi + a_lo)[M,K] * B[N,K]^T (+ bias); workspace: N*K floats (bf16 hi/lo split of B).  VGTKB_EUNSUP for
+// shapes the CTA-pair kernel does not take.
+int tc_gemm_nt_planes(int64_t M, int N, int K, const void* a_hi, const void* a_lo, const float* B, const float* bias, float* C,
+                      float* workspace, cudaStream_t st) {
+    if (M < 1 || N < 1 || K < 64 || K % 8 != 0 || M >= ((int64_t)1 << 31) || workspace == nullptr ||
+        ((reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) | reinterpret_cast<uintptr_t>(B) |
+          reinterpret_cast<uintptr_t>(workspace)) & 15) != 0)
+        return VGTKB_EUNSUP;
     const int64_t nb = (int64_t)N * K;
     const int blocks = (int)(ceil_div64(nb, 256) < 1184 ? ceil_div64(nb, 256) : 1184);
     uint16_t* bhi = reinterpret_cast<uint16_t*>(workspace);
@@ -1710,17 +1730,13 @@ extern "C" int vgtkb_gemm_nt_presplit(int64_t M, int N, int K, const void* a_hi,
     return launch_nt_pair<256, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo);
 }
 
-// weight-gradient counterpart: C [M, N] (+)= A [R, M]^T * (b_hi + b_lo) [R, N]; A (narrow, fp32) is split here as in
-// vgtkb_gemm_tn, the wide operand arrives as bf16 planes.  workspace: R*M floats.
-extern "C" int vgtkb_gemm_tn_presplit(int M, int N, int64_t R, const float* A, const void* b_hi, const void* b_lo, float* C,
-                                      int accumulate, float* workspace, void* stream) {
-    using namespace vgtkb;
-    VGTKB_REQUIRE(M >= 8 && M % 8 == 0 && M <= 256 && N >= 64 && N % 8 == 0 && R >= 64 && R < ((int64_t)1 << 31),
-                  "gemm_tn_presplit: needs M % 8 == 0, M <= 256, N % 8 == 0, R >= 64");
-    VGTKB_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo) |
-                    reinterpret_cast<uintptr_t>(workspace)) & 15) == 0 && workspace != nullptr,
-                  "gemm_tn_presplit: operands and workspace (R*M floats) must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
+// C[M,N] (+)= A[R,M]^T * (b_hi + b_lo)[R,N]; workspace: R*M floats (bf16 hi/lo split of A)
+int tc_gemm_tn_planes(int M, int N, int64_t R, const float* A, const void* b_hi, const void* b_lo, float* C, int accumulate,
+                      float* workspace, cudaStream_t st) {
+    if (M < 8 || M % 8 != 0 || M > 256 || N < 64 || N % 8 != 0 || R < 64 || R >= ((int64_t)1 << 31) || workspace == nullptr ||
+        ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo) |
+          reinterpret_cast<uintptr_t>(workspace)) & 15) != 0)
+        return VGTKB_EUNSUP;
     if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
     const int64_t na = R * (int64_t)M;
     uint16_t* hi = reinterpret_cast<uint16_t*>(workspace);
@@ -1734,4 +1750,27 @@ extern "C" int vgtkb_gemm_tn_presplit(int M, int N, int64_t R, const float* A, c
                         : launch_tn_pair<256, true>(b_hi, N, hi, lo, M, C, N, R, st, none, b_lo);
     if (M <= 128) return launch_tn<128, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
     return launch_tn<256, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
+}
+}  // namespace vgtkb
+
+extern "C" int vgtkb_gemm_nt_presplit(int64_t M, int N, int K, const void* a_hi, const void* a_lo, const float* B,
+                                      const float* bias, float* C, float* workspace, void* stream) {
+    using namespace vgtkb;
+    VGTKB_REQUIRE(M >= 1 && N >= 1 && K >= 64, "gemm_nt_presplit: bad size");
+    const int rc = tc_gemm_nt_planes(M, N, K, a_hi, a_lo, B, bias, C, workspace, (cudaStream_t)stream);
+    if (rc == VGTKB_EUNSUP)
+        set_error("gemm_nt_presplit: needs K %% 8 == 0, M < 2^31, 16-byte aligned operands and a workspace of N*K floats");
+    return rc;
+}
+
+// weight-gradient counterpart: C [M, N] (+)= A [R, M]^T * (b_hi + b_lo) [R, N]; A (narrow, fp32) is split here as in
+// vgtkb_gemm_tn, the wide operand arrives as bf16 planes.  workspace: R*M floats.
+extern "C" int vgtkb_gemm_tn_presplit(int M, int N, int64_t R, const float* A, const void* b_hi, const void* b_lo, float* C,
+                                      int accumulate, float* workspace, void* stream) {
+    using namespace vgtkb;
+    const int rc = tc_gemm_tn_planes(M, N, R, A, b_hi, b_lo, C, accumulate, workspace, (cudaStream_t)stream);
+    if (rc == VGTKB_EUNSUP)
+        set_error("gemm_tn_presplit: needs M %% 8 == 0, 8 <= M <= 256, N %% 8 == 0, N >= 64, R >= 64, 16-byte aligned operands "
+                  "and a workspace of R*M floats");
+    return rc;
 }

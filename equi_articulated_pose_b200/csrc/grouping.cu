@@ -786,11 +786,17 @@ inter_group_bwd_tma_kernel(int n, int p, int nn, int a, int k, int ci, const flo
 // red.global.add backward) and move only the CONTIGUOUS side -- the G / dG block of one (point, anchor, 32 channels):
 // k rows of 128 bytes -- through ONE 2-D tensor-map copy (3 KB) into / out of a 128B-swizzled staging tile, which the
 // fragment accesses hit conflict free (chunk = gid ^ (row & 7)).  LSU wavefronts per step drop by ~45 %.
-template <int KS>
+// PL = true: G leaves as two bf16 planes (hi = bf16_rn(g), lo = bf16_rn(g - hi): the operand split of the bf16x3
+// contraction, done HERE once instead of by the converter warps of every kernel that consumes G); map_g = hi plane,
+// map_lo = lo plane, both [rows*k, ci] bf16 with boxes of k rows x 32 channels (64 bytes, no swizzle).  A staging buffer
+// holds the hi tile (24 x 64 B) followed by the lo tile; the 8-byte fragment stores alternate between the even and the
+// odd kernel-point row across the quad pairs so that one store instruction covers all 32 banks (2 wavefronts).
+template <int KS, bool PL = false>
 __global__ void __launch_bounds__(IG_WARPS * 32, 2)
 inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p, int nn, int a, int k, int ci,
                               const float* __restrict__ xyz, const float* __restrict__ sxyz, const int32_t* __restrict__ idx,
-                              const float* __restrict__ rk, float inv_sigma, const float* __restrict__ feats) {
+                              const float* __restrict__ rk, float inv_sigma, const float* __restrict__ feats,
+                              const __grid_constant__ TmaMap map_lo) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ float s_g[16 * KS * 3];
     __shared__ uint32_t s_off[16 * KS];
@@ -800,7 +806,10 @@ inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p
     // per warp: two staging tiles [24 rows][128 B], 1024-byte aligned (swizzle atom = 8 rows x 128 B)
     float* stage = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)) + warp * (2 * 24 * 32);
     igt_neighbourhood<KS>(b, pi, n, p, nn, a, ci, xyz, sxyz, idx, s_g, s_off);
-    if (threadIdx.x == 0) tma_prefetch_desc(&map_g);
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_g);
+        if (PL) tma_prefetch_desc(&map_lo);
+    }
     __syncthreads();
     float gx[KS][4], gy[KS][4], gz[KS][4];
     uint32_t off[KS][4];
@@ -896,6 +905,26 @@ inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             __syncwarp();
             float* st = stage + sb * (24 * 32);
+            if (PL) {
+                const uint32_t sh = smem_u32(st), sl = sh + 24 * 64;
+                const int flip = tig >> 1;                         // quads 2, 3 store the odd row first
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int kp = 8 * t + 2 * tig;
+                    uint32_t h[2][2], l[2][2];                     // [row parity][channel pair]
+                    ig_split2(d[0][t][0], d[0][t][2], h[0][0], l[0][0]);
+                    ig_split2(d[1][t][0], d[1][t][2], h[0][1], l[0][1]);
+                    ig_split2(d[0][t][1], d[0][t][3], h[1][0], l[1][0]);
+                    ig_split2(d[1][t][1], d[1][t][3], h[1][1], l[1][1]);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int par = q ^ flip;
+                        const uint32_t o = (uint32_t)((kp + par) * 64 + gid * 8);
+                        st_shared_u2(sh + o, par ? h[1][0] : h[0][0], par ? h[1][1] : h[0][1]);
+                        st_shared_u2(sl + o, par ? l[1][0] : l[0][0], par ? l[1][1] : l[0][1]);
+                    }
+                }
+            } else
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
                 const int kp = 8 * t + 2 * tig;
@@ -905,7 +934,8 @@ inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                tma_store_2d(&map_g, st, c0, row0);                // k rows x 128 B (box rows = k)
+                tma_store_2d(&map_g, st, c0, row0);                // k rows x 128 B (box rows = k); PL: k rows x 64 B, hi
+                if (PL) tma_store_2d(&map_lo, reinterpret_cast<unsigned char*>(st) + 24 * 64, c0, row0);
                 bulk_commit();
             }
         }
@@ -1263,6 +1293,8 @@ __global__ void intra_group_bwd_kernel(int64_t rows, int a, int kk, int cv, cons
 
 using namespace vgtkb;
 
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 static int check_inter_args(int b, int n, int p, int nn, int a, int k, int ci) {
     VGTKB_REQUIRE(b >= 0 && n > 0 && p >= 0 && nn > 0 && a > 0 && k > 0 && ci > 0, "inter_group: bad size");
     VGTKB_REQUIRE(nn <= IG_MAXNN, "inter_group: nn=%d > %d", nn, IG_MAXNN);
@@ -1298,7 +1330,34 @@ static int launch_inter(bool fwd, int b, int n, int p, int nn, int a, int k, int
     return check_launch(fwd ? "inter_group_forward" : "inter_group_backward");
 }
 
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+namespace vgtkb {
+// G as two bf16 planes [b*p*a, k*ci] (hi, lo): the forward grouping of vgtkb_inter_conv_forward.  VGTKB_EUNSUP for shapes
+// the warp-MMA kernel does not take (k > 24, nn > 32, ci % 32 != 0, misaligned / too large tensors).
+int inter_group_forward_planes(int b, int n, int p, int nn, int a, int k, int ci, const float* xyz, const float* sample_xyz,
+                               const int32_t* idx, const float* rot_kernels, float sigma, const float* feats, void* g_hi,
+                               void* g_lo, cudaStream_t st) {
+    const int64_t g_rows = (int64_t)b * p * a * k;
+    if (k > 24 || nn > 32 || ci % 32 != 0 || !aligned16(feats) || !aligned16(g_hi) || !aligned16(g_lo) ||
+        (int64_t)n * a * ci >= ((int64_t)1 << 32) || g_rows >= ((int64_t)1 << 31) || b > 65535)
+        return VGTKB_EUNSUP;
+    TmaMap mh, ml;
+    int rc = make_plane_map(&mh, g_hi, g_rows, ci, k);
+    if (rc) return rc;
+    rc = make_plane_map(&ml, g_lo, g_rows, ci, k);
+    if (rc) return rc;
+    const size_t smem = (size_t)IG_WARPS * 2 * 24 * 128 + 1024;
+    if (nn <= 16) {
+        VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_mma_ts_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        inter_group_fwd_mma_ts_kernel<1, true><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(mh, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
+                                                                                        rot_kernels, 1.0f / sigma, feats, ml);
+    } else {
+        VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_mma_ts_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        inter_group_fwd_mma_ts_kernel<2, true><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(mh, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
+                                                                                        rot_kernels, 1.0f / sigma, feats, ml);
+    }
+    return check_launch("inter_group_forward(mma, bf16 planes)");
+}
+}  // namespace vgtkb
 
 extern "C" int vgtkb_inter_group_forward(int b, int n, int p, int nn, int a, int k, int ci, const float* xyz,
                                          const float* sample_xyz, const int32_t* idx, const float* rot_kernels,
@@ -1319,11 +1378,11 @@ extern "C" int vgtkb_inter_group_forward(int b, int n, int p, int nn, int a, int
             if (nn <= 16) {
                 VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_mma_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 inter_group_fwd_mma_ts_kernel<1><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(map, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
-                                                                                          rot_kernels, 1.0f / sigma, feats);
+                                                                                          rot_kernels, 1.0f / sigma, feats, map);
             } else {
                 VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_mma_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 inter_group_fwd_mma_ts_kernel<2><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(map, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
-                                                                                          rot_kernels, 1.0f / sigma, feats);
+                                                                                          rot_kernels, 1.0f / sigma, feats, map);
             }
             return check_launch("inter_group_forward(mma, tensor-map store)");
         }

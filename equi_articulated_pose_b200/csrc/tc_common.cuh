@@ -169,6 +169,9 @@ struct alignas(64) TmaMap {
     unsigned char bytes[128];
 };
 int make_rows_map(TmaMap* out, const void* base, int64_t rows, int64_t cols, int box_rows);
+// make_plane_map: row-major bf16 matrix [rows, cols], box = [box_rows, 32 columns = 64 bytes], no swizzle (the grouping
+// kernel's staging tile of one bf16 plane)
+int make_plane_map(TmaMap* out, const void* base, int64_t rows, int64_t cols, int box_rows);
 
 // ---- TMA 2-D tile load (tensor map in kernel parameter space) ----------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int crd_inner, int crd_outer, uint64_t* bar) {

@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgtkb200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _lib = None
 _device_ok = set()
@@ -60,6 +60,8 @@ SIGNATURES = {
     "vgtkb_split_bf16": [c_i64, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_gemm_nt_presplit": [c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_gemm_tn_presplit": [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp],
+    "vgtkb_inter_conv_forward": [c_int] * 8 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_inter_conv_backward": [c_int] * 8 + [c_vp, c_vp, c_vp, c_vp, c_f32] + [c_vp] * 9,
     "vgtkb_knn_query": [c_int] * 4 + [c_vp] * 5,
     "vgtkb_sa_group_forward": [c_int] * 6 + [c_vp] * 6,
     "vgtkb_sa_group_backward": [c_int] * 6 + [c_vp] * 4,
@@ -80,7 +82,7 @@ SETUP_SIGNATURES = {
     "vgtkb_peer_free": [c_vp],
 }
 NO_STATUS = {"vgtkb_last_error": (ctypes.c_char_p, []), "vgtkb_version": (c_int, []),
-             "vgtkb_device_check": (c_int, [])}
+             "vgtkb_device_check": (c_int, []), "vgtkb_inter_conv_supported": (c_int, [c_int] * 8)}
 
 
 class VgtkbError(RuntimeError):
@@ -168,4 +170,6 @@ PROFILE = None  # set to a list to record (entry point, args, start event, end e
 # device kernels launched per entry point (memsets not counted); used for bench.py's gpu_launches
 KERNELS_PER_CALL = {"vgtkb_gemm_nt": 2, "vgtkb_gemm_tn": 2, "vgtkb_gather_gemm_nt": 2, "vgtkb_gather_gemm_tn": 2,
                     "vgtkb_chamfer_forward": 2, "vgtkb_chamfer_backward": 4, "vgtkb_anchor_chamfer_forward": 2, "vgtkb_anchor_chamfer_backward": 2, "vgtkb_norm_stats": 2,
-                    "vgtkb_norm_act_backward": 3, "vgtkb_norm_bwd_sums": 2, "vgtkb_col_sum": 2}
+                    "vgtkb_norm_act_backward": 3, "vgtkb_norm_bwd_sums": 2, "vgtkb_col_sum": 2,
+                    "vgtkb_inter_conv_forward": 3, "vgtkb_inter_conv_backward": 6, "vgtkb_gemm_nt_presplit": 2,
+                    "vgtkb_gemm_tn_presplit": 2}

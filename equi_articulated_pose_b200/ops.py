@@ -188,6 +188,52 @@ class InterGroupFn(torch.autograd.Function):
         return gx, None, None, None, None, None
 
 
+def inter_conv_supported(b, n, p, nn, a, k, ci, co):
+    """Shapes vgtkb_inter_conv_forward/backward take (mode 3 only; the others run InterGroupFn + LinearFn)."""
+    return _GEMM_MODE == 3 and bool(_lib.load().vgtkb_inter_conv_supported(b, n, p, nn, a, k, ci, co))
+
+
+class InterConvFn(torch.autograd.Function):
+    """InterSO3Conv in one call per direction (vgtkb_inter_conv_forward / _backward): feats X [B,N,A,Ci] channels-last,
+    w_kc [Co, K*Ci] -> out [B*P*A, Co].  The grouped tensor exists only as the two bf16 operand planes the grouping
+    kernel writes (kept for the weight gradient); reference: so3conv/functional.py:144-203, spconv/functional.py:375-406,
+    so3conv/modules.py:48-55."""
+
+    @staticmethod
+    def forward(ctx, feats, w_kc, xyz, sample_xyz, idx, rot_kernels, sigma):
+        feats, w_kc = _f32(feats), _f32(w_kc)
+        b, n, a, ci = feats.shape
+        p, nn = idx.shape[1], idx.shape[2]
+        k, co = rot_kernels.shape[1], w_kc.shape[0]
+        dev = feats.device
+        rows = b * p * a
+        g_hi = torch.empty((rows, k * ci), dtype=torch.bfloat16, device=dev)
+        g_lo = torch.empty((rows, k * ci), dtype=torch.bfloat16, device=dev)
+        ws = torch.empty(co * k * ci, dtype=torch.float32, device=dev)
+        out = torch.empty((rows, co), dtype=torch.float32, device=dev)
+        call("vgtkb_inter_conv_forward", dev, b, n, p, nn, a, k, ci, co, ptr(xyz), ptr(sample_xyz), ptr(idx), ptr(rot_kernels),
+             float(sigma), ptr(feats), ptr(w_kc), ptr(g_hi), ptr(g_lo), ptr(ws), ptr(out))
+        ctx.save_for_backward(xyz, sample_xyz, idx, rot_kernels, w_kc, g_hi, g_lo)
+        ctx.meta = (b, n, p, nn, a, k, ci, co, float(sigma))
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        xyz, sample_xyz, idx, rot_kernels, w_kc, g_hi, g_lo = ctx.saved_tensors
+        b, n, p, nn, a, k, ci, co, sigma = ctx.meta
+        gy = _f32(gy)
+        dev = gy.device
+        rows, kc = b * p * a, k * ci
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gx = torch.empty((b, n, a, ci), dtype=torch.float32, device=dev) if need_x else None
+        dg = torch.empty((rows, kc), dtype=torch.float32, device=dev) if need_x else None
+        gw = torch.empty((co, kc), dtype=torch.float32, device=dev) if need_w else None
+        ws = torch.empty(max(rows * co, 2 * kc * co), dtype=torch.float32, device=dev)
+        call("vgtkb_inter_conv_backward", dev, b, n, p, nn, a, k, ci, co, ptr(xyz), ptr(sample_xyz), ptr(idx), ptr(rot_kernels),
+             sigma, ptr(w_kc), ptr(g_hi), ptr(g_lo), ptr(gy), ptr(dg), ptr(gx), ptr(gw), ptr(ws))
+        return gx, gw, None, None, None, None, None
+
+
 def pose_neighbourhood(xyz, pose, idx, anchors, with_perm=True):
     """xyz [B,3,N], pose [B,N,4,4], idx [B,N,nn] int32, anchors [A,3,3] -> rotated neighbour offsets [B,N,nn,3] and the
     anchor permutation table [B,N,nn,A] uint8 (None when with_perm is False)."""

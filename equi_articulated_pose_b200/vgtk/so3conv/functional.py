@@ -110,10 +110,10 @@ def _channels_last(feats):
     return feats.permute(0, 2, 3, 1).contiguous()
 
 
-def inter_so3conv_grouping(xyz, feats, stride, n_neighbor, anchors, kernels, radius, sigma, inter_idx=None,
-                           inter_w=None, lazy_sample=True, radius_expansion=1.0, pooling=None, rot_kernels=None):
-    """Reference :144-203.  xyz [b,3,p1], feats [b,c,p1,a] ->
-    (inter_idx [b,p2,nn], inter_w (lazy), new_xyz [b,3,p2], new_feats [b,c,k,p2,a] (view), sample_idx)."""
+def _inter_so3conv_indices(xyz, feats, stride, n_neighbor, anchors, kernels, radius, sigma, inter_idx, inter_w, lazy_sample,
+                           radius_expansion, pooling, rot_kernels):
+    """Index part of inter_so3conv_grouping (reference :144-189): optional pooling, ball query / cached indices.
+    -> (xyz, feats, inter_idx, inter_w, new_xyz, sample_idx)."""
     if pooling is not None and stride > 1 and feats.shape[1] > 1:
         if pooling == 'stride':
             pool_stride, stride_nn, stride = stride, int(n_neighbor * stride ** 0.5), 1
@@ -133,10 +133,20 @@ def inter_so3conv_grouping(xyz, feats, stride, n_neighbor, anchors, kernels, rad
         inter_w = LazyInterWeights(xyz, new_xyz.contiguous(), inter_idx, rot_kernels, sigma)
     else:
         sample_idx, new_xyz = None, xyz
-        if not isinstance(inter_w, LazyInterWeights):
-            # explicit weights handed in by the caller: literal (unfused) evaluation
-            new_feats = inter_so3conv_feat_grouping(inter_idx, inter_w, feats)
-            return inter_idx, inter_w, new_xyz, new_feats, sample_idx
+    return xyz, feats, inter_idx, inter_w, new_xyz, sample_idx
+
+
+def inter_so3conv_grouping(xyz, feats, stride, n_neighbor, anchors, kernels, radius, sigma, inter_idx=None,
+                           inter_w=None, lazy_sample=True, radius_expansion=1.0, pooling=None, rot_kernels=None):
+    """Reference :144-203.  xyz [b,3,p1], feats [b,c,p1,a] ->
+    (inter_idx [b,p2,nn], inter_w (lazy), new_xyz [b,3,p2], new_feats [b,c,k,p2,a] (view), sample_idx)."""
+    xyz, feats, inter_idx, inter_w, new_xyz, sample_idx = _inter_so3conv_indices(
+        xyz, feats, stride, n_neighbor, anchors, kernels, radius, sigma, inter_idx, inter_w, lazy_sample, radius_expansion,
+        pooling, rot_kernels)
+    if not isinstance(inter_w, LazyInterWeights):
+        # explicit weights handed in by the caller: literal (unfused) evaluation
+        new_feats = inter_so3conv_feat_grouping(inter_idx, inter_w, feats)
+        return inter_idx, inter_w, new_xyz, new_feats, sample_idx
 
     w = inter_w
     g = _ops.InterGroupFn.apply(_channels_last(feats), w.xyz, w.sample_xyz, w.idx, w.rot_kernels, w.sigma)
@@ -144,6 +154,30 @@ def inter_so3conv_grouping(xyz, feats, stride, n_neighbor, anchors, kernels, rad
     k = w.rot_kernels.shape[1]
     new_feats = g.view(b, p, a, k, kc // k).permute(0, 4, 3, 1, 2)          # logical [b,c,k,p,a]
     return inter_idx, inter_w, new_xyz, new_feats, sample_idx
+
+
+def inter_so3conv(xyz, feats, w_kc, stride, n_neighbor, anchors, kernels, radius, sigma, inter_idx=None, inter_w=None,
+                  lazy_sample=True, radius_expansion=1.0, pooling=None, rot_kernels=None):
+    """inter_so3conv_grouping + BasicSO3Conv in one call (vgtkb_inter_conv_forward) when the shape is taken: the grouped
+    tensor of the reference (:192-203) only exists as the contraction's bf16 operand planes.
+    -> (inter_idx, inter_w, new_xyz, out_feats logical [b,co,p2,a], sample_idx), or None when the caller has to take the
+    two-step path (explicit weights, shapes outside the fused kernels, contraction modes other than bf16x3)."""
+    if not feats.is_cuda or (inter_idx is not None and not isinstance(inter_w, LazyInterWeights)):
+        return None
+    xyz, feats, inter_idx, inter_w, new_xyz, sample_idx = _inter_so3conv_indices(
+        xyz, feats, stride, n_neighbor, anchors, kernels, radius, sigma, inter_idx, inter_w, lazy_sample, radius_expansion,
+        pooling, rot_kernels)
+    w = inter_w
+    b, ci, n, a = feats.shape
+    p, nn = w.idx.shape[1], w.idx.shape[2]
+    k, co = w.rot_kernels.shape[1], w_kc.shape[0]
+    if not _ops.inter_conv_supported(b, n, p, nn, a, k, ci, co):
+        g = _ops.InterGroupFn.apply(_channels_last(feats), w.xyz, w.sample_xyz, w.idx, w.rot_kernels, w.sigma)
+        rows = _ops.LinearFn.apply(g.view(b * p * a, k * ci), w_kc, None)
+    else:
+        rows = _ops.InterConvFn.apply(_channels_last(feats), w_kc, w.xyz, w.sample_xyz, w.idx, w.rot_kernels, w.sigma)
+    out = rows.view(b, p, a, co).permute(0, 3, 1, 2)
+    return inter_idx, inter_w, new_xyz, out, sample_idx
 
 
 def intra_so3conv_grouping(intra_idx, feature):

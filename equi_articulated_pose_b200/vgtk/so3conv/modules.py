@@ -75,6 +75,12 @@ class InterSO3Conv(nn.Module):
         return self._rk
 
     def forward(self, x, inter_idx=None, inter_w=None):
+        fused = L.inter_so3conv(x.xyz, x.feats, self.basic_conv.weight_kc(), self.stride, self.n_neighbor, self.anchors,
+                                self.kernels, self.radius, self.sigma, inter_idx, inter_w, self.lazy_sample,
+                                pooling=self.pooling, rot_kernels=self.rot_kernels())
+        if fused is not None:
+            inter_idx, inter_w, xyz, feats, sample_idx = fused
+            return inter_idx, inter_w, sample_idx, SphericalPointCloud(xyz, feats, self.anchors)
         inter_idx, inter_w, xyz, feats, sample_idx = L.inter_so3conv_grouping(
             x.xyz, x.feats, self.stride, self.n_neighbor, self.anchors, self.kernels, self.radius, self.sigma,
             inter_idx, inter_w, self.lazy_sample, pooling=self.pooling, rot_kernels=self.rot_kernels())

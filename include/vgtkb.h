@@ -287,12 +287,12 @@ int vgtkb_three_interpolate_forward(int b, int n1, int n2, int c, const float* f
 int vgtkb_three_interpolate_backward(int b, int n1, int n2, int c, const float* grad_out, const int32_t* idx, const float* w,
                                      float* grad_feat, void* stream);
 
-/* EXPERIMENTAL (round-2 groundwork; no default path calls these, csrc/gemm_tc.cu): activation operand stored once as two
- * bf16 planes (hi = bf16_rn(x), lo = bf16_rn(x - hi)) by its producer, consumed by the contraction without the in-kernel
- * operand conversion that bounds the narrow layers.
+/* Plane operands (csrc/gemm_tc.cu): an activation operand stored once as two bf16 planes (hi = bf16_rn(x),
+ * lo = bf16_rn(x - hi)) by its producer and consumed by the contraction without the in-kernel operand conversion that
+ * bounds the narrow layers.  vgtkb_inter_conv_* below is built on them.
  *   split_bf16:        hi / lo planes (uint16 bf16 bit patterns, n elements each) of an fp32 array
- *   gemm_nt_presplit:  C [M, N] = (a_hi + a_lo) [M, K] * B [N, K]^T (+ bias), bf16x3 arithmetic of vgtkb_gemm_nt mode 3;
- *                      K % 8 == 0, K >= 64; workspace: N*K floats (hi / lo planes of B), 16-byte aligned */
+ *   gemm_nt_presplit:  C [M, N] = (a_hi + a_lo) [M, K] * B [N, K]^T (+ bias), bf16x3 arithmetic of vgtkb_gemm_nt mode 3
+ *                      (bit-identical results); K % 8 == 0, K >= 64; workspace: N*K floats (hi / lo planes of B), 16-byte aligned */
 int vgtkb_split_bf16(int64_t n, const float* x, void* hi, void* lo, void* stream);
 int vgtkb_gemm_nt_presplit(int64_t M, int N, int K, const void* a_hi, const void* a_lo, const float* B, const float* bias,
                            float* C, float* workspace, void* stream);
@@ -300,6 +300,28 @@ int vgtkb_gemm_nt_presplit(int64_t M, int N, int K, const void* a_hi, const void
  *                      M % 8 == 0, M <= 256, N % 8 == 0, R >= 64; workspace: R*M floats (split of the narrow operand) */
 int vgtkb_gemm_tn_presplit(int M, int N, int64_t R, const float* A, const void* b_hi, const void* b_lo, float* C, int accumulate,
                            float* workspace, void* stream);
+
+/* InterSO3Conv as one call per direction: ball-neighbourhood grouping under the kernel-point correlation + contraction with W
+ * (reference: inter_so3conv_grouping, vgtk/vgtk/so3conv/functional.py:144-203 -> inter_zpconv_grouping_naive,
+ * vgtk/vgtk/spconv/functional.py:375-406 -> BasicSO3Conv.forward, vgtk/vgtk/so3conv/modules.py:48-55; backward = what autograd
+ * derives from those three).  bf16x3 tensor-core arithmetic (mode 3).
+ *   forward:  feats X [b,n,a,ci] (channels-last), w_kc [co, k*ci] (column k*ci + c) -> out [b*p*a, co].
+ *             g_hi / g_lo [b*p*a, k*ci] bf16 each: the grouped tensor in the contraction's operand format, written once by
+ *             the grouping kernel and read by TMA only (forward contraction here, weight gradient in backward); the caller
+ *             keeps them for backward.  workspace: co*k*ci floats.
+ *   backward: grad_out [b*p*a, co] -> grad_w [co, k*ci] (overwritten; NULL = skip) and grad_feats [b,n,a,ci] (overwritten;
+ *             NULL = skip; needs the scratch grad_grouped [b*p*a, k*ci] fp32).  workspace: max(b*p*a*co, 2*k*ci*co) floats.
+ *   supported: 1 iff the shape is taken (k <= 24, nn <= 32, ci % 32 == 0, co % 8 == 0, co <= 256, b*p*a >= 64, 32-bit offsets);
+ *             other shapes run vgtkb_inter_group_* + vgtkb_gemm_*. */
+int vgtkb_inter_conv_supported(int b, int n, int p, int nn, int a, int k, int ci, int co);
+int vgtkb_inter_conv_forward(int b, int n, int p, int nn, int a, int k, int ci, int co, const float* xyz,
+                             const float* sample_xyz, const int32_t* idx, const float* rot_kernels, float sigma,
+                             const float* feats, const float* w_kc, void* g_hi, void* g_lo, float* workspace, float* out,
+                             void* stream);
+int vgtkb_inter_conv_backward(int b, int n, int p, int nn, int a, int k, int ci, int co, const float* xyz,
+                              const float* sample_xyz, const int32_t* idx, const float* rot_kernels, float sigma,
+                              const float* w_kc, const void* g_hi, const void* g_lo, const float* grad_out,
+                              float* grad_grouped, float* grad_feats, float* grad_w, float* workspace, void* stream);
 
 /* column sums of a row-major [rows, c] matrix (bias gradient of the skip conv) */
 int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream);

@@ -1,0 +1,109 @@
+"""vgtkb_inter_conv_forward / _backward (InterSO3Conv in one call per direction, grouped tensor only as bf16 operand
+planes) against (1) the two-step path vgtkb_inter_group_* + vgtkb_gemm_* it replaces -- forward bit-identical: same
+fp32 grouping accumulators, same hi/lo split, same MMA order -- and (2) the fp64 evaluation of the reference's
+expressions (oracle/so3.py: inter_so3conv_grouping_anchor + inter_zpconv_grouping_naive + BasicSO3Conv, reference
+vgtk/vgtk/so3conv/functional.py:2508-2549, vgtk/vgtk/spconv/functional.py:375-406, vgtk/vgtk/so3conv/modules.py:48-55)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from equi_articulated_pose_b200 import lib
+    lib.load()
+    return torch.device("cuda:0")
+
+
+def _case(dev, b, n, p, nn, ci, co, radius, sigma, seed, a=60):
+    from oracle import so3 as O
+    from equi_articulated_pose_b200 import ops, so3_constants as C
+    import equi_articulated_pose_b200 as pkg
+    pkg.install()
+    import vgtk.so3conv.functional as L
+    g = torch.Generator().manual_seed(seed)
+    xyz = O.synthetic_cloud(b, n, seed).permute(0, 2, 1).contiguous().to(dev)
+    sxyz = xyz[:, :, :p].contiguous()
+    idx = ops.ball_query(sxyz, xyz, radius, nn)
+    anchors = torch.from_numpy(C.get_anchors(a)).to(dev)
+    kernels = torch.from_numpy(C.scaled_kernel_points(0.7 * radius, 1)).to(dev)
+    rk = L.rotated_kernels(anchors, kernels)
+    k = rk.shape[1]
+    feats = torch.randn(b, n, a, ci, generator=g).to(dev)
+    w_kc = (torch.randn(co, k * ci, generator=g) / (k * ci) ** 0.5).to(dev)
+    gy = torch.randn(b * p * a, co, generator=g).to(dev)
+    return xyz, sxyz, idx, rk, feats, w_kc, gy, sigma
+
+
+SHAPES = [
+    # b, n, p, nn, ci, co, radius, sigma
+    (2, 128, 128, 16, 64, 64, 0.45, 0.08),      # layer 0.1 geometry (stride 1, nn = 16)
+    (2, 128, 64, 32, 64, 128, 0.5, 0.1),        # strided, nn = 32
+    (1, 96, 96, 12, 32, 72, 0.5, 0.1),          # ragged: nn not a multiple of 8, co = 72, ci = 32
+    (2, 64, 32, 20, 128, 256, 0.7, 0.2),        # wide output
+    (8, 512, 512, 16, 64, 64, 0.2828, 0.04),    # config 2 layer 0.1 at full size
+]
+
+
+@pytest.mark.parametrize("b,n,p,nn,ci,co,radius,sigma", SHAPES)
+def test_inter_conv_matches_two_step_and_fp64(dev, b, n, p, nn, ci, co, radius, sigma):
+    from equi_articulated_pose_b200 import ops
+    xyz, sxyz, idx, rk, feats, w_kc, gy, sigma = _case(dev, b, n, p, nn, ci, co, radius, sigma, 11 * n + co)
+    a, k = rk.shape[0], rk.shape[1]
+    assert ops.inter_conv_supported(b, n, p, nn, a, k, ci, co)
+
+    f1 = feats.clone().requires_grad_(True)
+    w1 = w_kc.clone().requires_grad_(True)
+    out1 = ops.InterConvFn.apply(f1, w1, xyz, sxyz, idx, rk, sigma)
+    out1.backward(gy)
+
+    f2 = feats.clone().requires_grad_(True)
+    w2 = w_kc.clone().requires_grad_(True)
+    g2 = ops.InterGroupFn.apply(f2, xyz, sxyz, idx, rk, sigma)
+    out2 = ops.LinearFn.apply(g2.view(b * p * a, k * ci), w2, None)
+    out2.backward(gy)
+
+    assert torch.equal(out1, out2), "forward must be bit-identical to the two-step bf16x3 path"
+    assert torch.equal(f1.grad, f2.grad) or float((f1.grad - f2.grad).abs().max()) <= 1e-6 * float(f2.grad.abs().max())
+    assert float((w1.grad - w2.grad).abs().max()) <= 3e-6 * float(w2.grad.abs().max())
+
+    if b * p * a * k * ci <= 40_000_000:     # fp64 ground truth of the reference expressions (materialised weights)
+        w = ops.inter_weights(xyz, sxyz, idx, rk, sigma).double()                      # [b,p,a,k,nn]
+        fd = feats.double().requires_grad_(True)
+        wd = w_kc.double().requires_grad_(True)
+        gathered = torch.stack([fd[i][idx[i].long()] for i in range(b)])               # [b,p,nn,a,ci]
+        G = torch.einsum('bpnac,bpakn->bpakc', gathered, w).reshape(b * p * a, k * ci)
+        ref = G @ wd.t()
+        ref.backward(gy.double())
+        s = float(ref.abs().max())
+        assert float((out1.double() - ref).abs().max()) <= 3e-5 * s
+        assert float((f1.grad.double() - fd.grad).abs().max()) <= 5e-5 * float(fd.grad.abs().max())
+        assert float((w1.grad.double() - wd.grad).abs().max()) <= 5e-5 * float(wd.grad.abs().max())
+
+
+def test_inter_conv_module_path_is_default(dev):
+    """InterSO3Conv.forward takes the one-call path for the shapes it covers and its outputs equal the two-step path."""
+    import equi_articulated_pose_b200 as pkg
+    pkg.install()
+    import vgtk.so3conv as sptk
+    import vgtk.spconv as zptk
+    from oracle import so3 as O
+    from equi_articulated_pose_b200 import lib, ops
+    torch.manual_seed(3)
+    conv = sptk.InterSO3Conv(64, 64, 1, 1, 0.45, 0.08, 16).to(dev)
+    xyz = O.synthetic_cloud(2, 128, 5).permute(0, 2, 1).contiguous().to(dev)
+    feats = torch.randn(2, 128, 60, 64, device=dev).permute(0, 3, 1, 2)
+    lib.PROFILE = []
+    _, _, _, y = conv(zptk.SphericalPointCloud(xyz, feats, None))
+    names = [r[0] for r in lib.PROFILE]
+    lib.PROFILE = None
+    assert "vgtkb_inter_conv_forward" in names and "vgtkb_inter_group_forward" not in names
+    prev = ops.get_gemm_mode()
+    try:
+        ops.set_gemm_mode(1)                 # 3xTF32: the two-step path
+        _, _, _, y1 = conv(zptk.SphericalPointCloud(xyz, feats, None))
+    finally:
+        ops.set_gemm_mode(prev)
+    assert float((y.feats - y1.feats).abs().max()) <= 2e-5 * float(y1.feats.abs().max())
