@@ -62,6 +62,8 @@ class FusedBatchNorm2d(nn.BatchNorm2d):
     `sync_group` (set by convert_sync_batchnorm): statistics over all data-parallel ranks, nn.SyncBatchNorm semantics."""
 
     sync_group = None
+    planes_fwd = False      # the result feeds a tensor-core contraction: also write its bf16 operand planes
+    planes_bwd = False      # the input comes from a contraction: write the planes of its gradient in backward
 
     def forward_rows(self, rows, slope, residual=None):
         training = self.training or not self.track_running_stats
@@ -71,16 +73,21 @@ class FusedBatchNorm2d(nn.BatchNorm2d):
         return _ops.norm_act(rows.unsqueeze(0), self.weight, self.bias, None if residual is None else residual.unsqueeze(0),
                              self.running_mean if training else self.running_mean,
                              self.running_var if training else self.running_var,
-                             mom, self.eps, slope, use_running=not training, sync_group=self.sync_group).squeeze(0)
+                             mom, self.eps, slope, use_running=not training, sync_group=self.sync_group,
+                             planes_fwd=self.planes_fwd, planes_bwd=self.planes_bwd and training).squeeze(0)
 
 
 class FusedInstanceNorm2d(nn.InstanceNorm2d):
     """nn.InstanceNorm2d(affine=False): per-(sample, channel) statistics over (points, anchors)."""
 
+    planes_fwd = False
+    planes_bwd = False
+
     def forward_rows(self, rows, batch, slope, residual=None):
         m, c = rows.shape
         res = None if residual is None else residual.view(batch, m // batch, c)
-        return _ops.norm_act(rows.view(batch, m // batch, c), None, None, res, None, None, 0.1, self.eps, slope).view(m, c)
+        return _ops.norm_act(rows.view(batch, m // batch, c), None, None, res, None, None, 0.1, self.eps, slope,
+                             planes_fwd=self.planes_fwd, planes_bwd=self.planes_bwd).view(m, c)
 
 
 def convert_sync_batchnorm(module, process_group=None, peer_memory=True):
@@ -126,6 +133,7 @@ class IntraSO3ConvBlock(nn.Module):
         super().__init__()
         self.conv = sptk.IntraSO3Conv(dim_in, dim_out)
         self.norm = _make_norm(norm, dim_out)
+        self.norm.planes_bwd = dim_in % 64 == 0 and dim_out % 64 == 0    # the gradient of the conv output feeds two contractions
         self.slope = _slope(activation)
         self.dropout = nn.Dropout(dropout_rate) if dropout_rate > 0 else None
 
@@ -150,6 +158,7 @@ class InterSO3ConvBlock(nn.Module):
         self.conv = sptk.InterSO3Conv(dim_in, dim_out, kernel_size, stride, radius, sigma, n_neighbor,
                                       kanchor=kanchor, lazy_sample=lazy_sample, pooling=pooling_method)
         self.norm = _make_norm(norm, dim_out)
+        self.norm.planes_bwd = dim_in % 32 == 0 and dim_out % 64 == 0     # consumed by vgtkb_inter_conv_backward
         self.slope = _slope(activation)
         self.dropout = nn.Dropout(dropout_rate) if dropout_rate > 0 else None
 
@@ -173,6 +182,8 @@ class SeparableSO3ConvBlock(nn.Module):
         if self.use_intra:
             self.intra_conv = IntraSO3ConvBlock(dim_in=dim_out, dim_out=dim_out, dropout_rate=params['dropout_rate'],
                                                 activation=params['activation'])
+            # operand planes: the inter norm's result feeds the intra gather-GEMM
+            self.inter_conv.norm.planes_fwd = dim_out % 64 == 0
         self.stride = params['stride']
         self.skip_conv = nn.Conv2d(dim_in, dim_out, 1)
         self.norm = _make_norm(params.get('norm'), dim_out)

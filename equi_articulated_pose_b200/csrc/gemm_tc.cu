@@ -1730,26 +1730,94 @@ int tc_gemm_nt_planes(int64_t M, int N, int K, const void* a_hi, const void* a_l
     return launch_nt_pair<256, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo);
 }
 
-// C[M,N] (+)= A[R,M]^T * (b_hi + b_lo)[R,N]; workspace: R*M floats (bf16 hi/lo split of A)
-int tc_gemm_tn_planes(int M, int N, int64_t R, const float* A, const void* b_hi, const void* b_lo, float* C, int accumulate,
-                      float* workspace, cudaStream_t st) {
-    if (M < 8 || M % 8 != 0 || M > 256 || N < 64 || N % 8 != 0 || R < 64 || R >= ((int64_t)1 << 31) || workspace == nullptr ||
-        ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo) |
-          reinterpret_cast<uintptr_t>(workspace)) & 15) != 0)
+// split `n` floats into bf16 hi / lo planes at the start of `workspace` unless the planes are given
+static int planes_or_split(const float* x, const void* x_hi, const void* x_lo, int64_t n, float* workspace, const void** hi,
+                           const void** lo, cudaStream_t st) {
+    if (x_hi != nullptr && x_lo != nullptr) {
+        *hi = x_hi;
+        *lo = x_lo;
+        return VGTKB_OK;
+    }
+    if (x == nullptr || workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return VGTKB_EUNSUP;
+    uint16_t* h = reinterpret_cast<uint16_t*>(workspace);
+    uint16_t* l = h + n;
+    const int blocks = (int)(ceil_div64(n, 256) < 2368 ? ceil_div64(n, 256) : 2368);
+    split_bf16_kernel<<<blocks, 256, 0, st>>>(n, x, h, l);
+    *hi = h;
+    *lo = l;
+    return VGTKB_OK;
+}
+
+// C[M,N] (+)= A[R,M]^T * B[R,N]; the narrow operand A as planes (a_hi / a_lo) or fp32 (split into workspace: R*M floats);
+// the wide operand B as planes (b_hi / b_lo: pure TMA -> MMA stream) or fp32 (B: converted in the kernel)
+int tc_gemm_tn_planes(int M, int N, int64_t R, const float* A, const void* a_hi, const void* a_lo, const float* B,
+                      const void* b_hi, const void* b_lo, float* C, int accumulate, float* workspace, cudaStream_t st) {
+    const bool bpl = b_hi != nullptr && b_lo != nullptr;
+    if (M < 8 || M % 8 != 0 || M > 256 || N < 64 || N % 8 != 0 || R < 64 || R >= ((int64_t)1 << 31) ||
+        ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) |
+          reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo)) & 15) != 0 ||
+        (!bpl && B == nullptr))
         return VGTKB_EUNSUP;
+    const void *hi, *lo;
+    const int rc = planes_or_split(A, a_hi, a_lo, R * (int64_t)M, workspace, &hi, &lo, st);
+    if (rc) return rc;
     if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
-    const int64_t na = R * (int64_t)M;
-    uint16_t* hi = reinterpret_cast<uint16_t*>(workspace);
-    uint16_t* lo = hi + na;
-    const int blocks = (int)(ceil_div64(na, 256) < 2368 ? ceil_div64(na, 256) : 2368);
-    split_bf16_kernel<<<blocks, 256, 0, st>>>(na, A, hi, lo);
     const TcGather none{0, 0, 0, nullptr};
-    if (M <= 64) return launch_tn<64, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
+    if (bpl) {
+        if (M <= 64) return launch_tn<64, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
+        if (N > TC_BM)
+            return M <= 128 ? launch_tn_pair<128, true>(b_hi, N, hi, lo, M, C, N, R, st, none, b_lo)
+                            : launch_tn_pair<256, true>(b_hi, N, hi, lo, M, C, N, R, st, none, b_lo);
+        if (M <= 128) return launch_tn<128, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
+        return launch_tn<256, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
+    }
+    if (M <= 64) return launch_tn<64, true>(B, N, hi, lo, M, C, N, R, 3, st);
+    if (tn_pairs_enabled() && N > TC_BM)
+        return M <= 128 ? launch_tn_pair<128>(B, N, hi, lo, M, C, N, R, st) : launch_tn_pair<256>(B, N, hi, lo, M, C, N, R, st);
+    if (M <= 128) return launch_tn<128, true>(B, N, hi, lo, M, C, N, R, 3, st);
+    return launch_tn<256, true>(B, N, hi, lo, M, C, N, R, 3, st);
+}
+
+// gather-GEMM (intra conv) with the activation operand X [points, anchors, c_n] as bf16 planes; workspace: N*kk_n*c_n floats
+int tc_gemm_nt_gather_planes(int64_t points, int anchors, int kk_n, int c_n, int N, const int32_t* table, const void* x_hi,
+                             const void* x_lo, const float* B, const float* bias, float* C, float* workspace, cudaStream_t st) {
+    const int K = kk_n * c_n;
+    if (c_n % 64 != 0 || anchors < 1 || kk_n < 1 || points < 1 || points >= ((int64_t)1 << 31) || workspace == nullptr ||
+        ((reinterpret_cast<uintptr_t>(x_hi) | reinterpret_cast<uintptr_t>(x_lo) | reinterpret_cast<uintptr_t>(B) |
+          reinterpret_cast<uintptr_t>(workspace)) & 15) != 0 ||
+        (bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) != 0))
+        return VGTKB_EUNSUP;
+    const int64_t nb = (int64_t)N * K;
+    const int blocks = (int)(ceil_div64(nb, 256) < 1184 ? ceil_div64(nb, 256) : 1184);
+    uint16_t* bhi = reinterpret_cast<uint16_t*>(workspace);
+    uint16_t* blo = bhi + nb;
+    split_bf16_kernel<<<blocks, 256, 0, st>>>(nb, B, bhi, blo);
+    const TcGather ga{anchors, kk_n, c_n, table};
+    if (N <= 64) return launch_nt_pair<64, true>(points, N, K, x_hi, bhi, blo, bias, C, st, ga, x_lo);
+    if (N <= 128) return launch_nt_pair<128, true>(points, N, K, x_hi, bhi, blo, bias, C, st, ga, x_lo);
+    return launch_nt_pair<256, true>(points, N, K, x_hi, bhi, blo, bias, C, st, ga, x_lo);
+}
+
+// weight gradient of the gather-GEMM with X as planes; Y [points*anchors, M] as planes or fp32 (split into workspace)
+int tc_gemm_tn_gather_planes(int64_t points, int anchors, int kk_n, int c_n, int M, const int32_t* table, const void* x_hi,
+                             const void* x_lo, const float* Y, const void* y_hi, const void* y_lo, float* C, int accumulate,
+                             float* workspace, cudaStream_t st) {
+    const int N = kk_n * c_n;
+    if (c_n % 64 != 0 || M % 8 != 0 || M < 8 || M > 256 || points < 64 || points >= ((int64_t)1 << 31) ||
+        ((reinterpret_cast<uintptr_t>(x_hi) | reinterpret_cast<uintptr_t>(x_lo) | reinterpret_cast<uintptr_t>(Y) |
+          reinterpret_cast<uintptr_t>(y_hi) | reinterpret_cast<uintptr_t>(y_lo)) & 15) != 0)
+        return VGTKB_EUNSUP;
+    const void *hi, *lo;
+    const int rc = planes_or_split(Y, y_hi, y_lo, points * anchors * (int64_t)M, workspace, &hi, &lo, st);
+    if (rc) return rc;
+    if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+    const TcGather ga{anchors, kk_n, c_n, table};
+    if (M <= 64) return launch_tn<64, true, true>(x_hi, N, hi, lo, M, C, N, points, 3, st, ga, x_lo);
     if (N > TC_BM)
-        return M <= 128 ? launch_tn_pair<128, true>(b_hi, N, hi, lo, M, C, N, R, st, none, b_lo)
-                        : launch_tn_pair<256, true>(b_hi, N, hi, lo, M, C, N, R, st, none, b_lo);
-    if (M <= 128) return launch_tn<128, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
-    return launch_tn<256, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
+        return M <= 128 ? launch_tn_pair<128, true>(x_hi, N, hi, lo, M, C, N, points, st, ga, x_lo)
+                        : launch_tn_pair<256, true>(x_hi, N, hi, lo, M, C, N, points, st, ga, x_lo);
+    if (M <= 128) return launch_tn<128, true, true>(x_hi, N, hi, lo, M, C, N, points, 3, st, ga, x_lo);
+    return launch_tn<256, true, true>(x_hi, N, hi, lo, M, C, N, points, 3, st, ga, x_lo);
 }
 }  // namespace vgtkb
 
@@ -1767,10 +1835,39 @@ extern "C" int vgtkb_gemm_nt_presplit(int64_t M, int N, int K, const void* a_hi,
 // vgtkb_gemm_tn, the wide operand arrives as bf16 planes.  workspace: R*M floats.
 extern "C" int vgtkb_gemm_tn_presplit(int M, int N, int64_t R, const float* A, const void* b_hi, const void* b_lo, float* C,
                                       int accumulate, float* workspace, void* stream) {
+    return vgtkb_gemm_tn_planes(M, N, R, A, nullptr, nullptr, nullptr, b_hi, b_lo, C, accumulate, workspace, stream);
+}
+
+extern "C" int vgtkb_gemm_tn_planes(int M, int N, int64_t R, const float* A, const void* a_hi, const void* a_lo, const float* B,
+                                    const void* b_hi, const void* b_lo, float* C, int accumulate, float* workspace, void* stream) {
     using namespace vgtkb;
-    const int rc = tc_gemm_tn_planes(M, N, R, A, b_hi, b_lo, C, accumulate, workspace, (cudaStream_t)stream);
+    const int rc = tc_gemm_tn_planes(M, N, R, A, a_hi, a_lo, B, b_hi, b_lo, C, accumulate, workspace, (cudaStream_t)stream);
     if (rc == VGTKB_EUNSUP)
-        set_error("gemm_tn_presplit: needs M %% 8 == 0, 8 <= M <= 256, N %% 8 == 0, N >= 64, R >= 64, 16-byte aligned operands "
-                  "and a workspace of R*M floats");
+        set_error("gemm_tn_planes: needs M %% 8 == 0, 8 <= M <= 256, N %% 8 == 0, N >= 64, R >= 64, 16-byte aligned operands, "
+                  "and either planes or fp32 + a workspace of R*M floats for the narrow operand");
+    return rc;
+}
+
+extern "C" int vgtkb_gather_gemm_nt_planes(int64_t points, int anchors, int kk, int c, int n, const int32_t* table,
+                                           const void* x_hi, const void* x_lo, const float* w, const float* bias, float* out,
+                                           float* workspace, void* stream) {
+    using namespace vgtkb;
+    VGTKB_REQUIRE(points >= 0 && anchors > 0 && kk > 0 && c > 0 && n > 0, "gather_gemm_nt_planes: bad size");
+    if (points == 0) return VGTKB_OK;
+    const int rc = tc_gemm_nt_gather_planes(points, anchors, kk, c, n, table, x_hi, x_lo, w, bias, out, workspace,
+                                            (cudaStream_t)stream);
+    if (rc == VGTKB_EUNSUP) set_error("gather_gemm_nt_planes: unsupported shape (needs c %% 64 == 0, 16-byte aligned operands, workspace)");
+    return rc;
+}
+
+extern "C" int vgtkb_gather_gemm_tn_planes(int64_t points, int anchors, int kk, int c, int m, const int32_t* table,
+                                           const void* x_hi, const void* x_lo, const float* y, const void* y_hi, const void* y_lo,
+                                           float* out, int accumulate, float* workspace, void* stream) {
+    using namespace vgtkb;
+    VGTKB_REQUIRE(points >= 0 && anchors > 0 && kk > 0 && c > 0 && m > 0, "gather_gemm_tn_planes: bad size");
+    const int rc = tc_gemm_tn_gather_planes(points, anchors, kk, c, m, table, x_hi, x_lo, y, y_hi, y_lo, out, accumulate, workspace,
+                                            (cudaStream_t)stream);
+    if (rc == VGTKB_EUNSUP)
+        set_error("gather_gemm_tn_planes: unsupported shape (needs c %% 64 == 0, m %% 8 == 0, m <= 256, points >= 64, aligned operands)");
     return rc;
 }

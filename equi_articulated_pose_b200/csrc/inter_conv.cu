@@ -16,8 +16,8 @@ int inter_group_forward_planes(int b, int n, int p, int nn, int a, int k, int ci
                                void* g_lo, cudaStream_t st);
 int tc_gemm_nt_planes(int64_t M, int N, int K, const void* a_hi, const void* a_lo, const float* B, const float* bias, float* C,
                       float* workspace, cudaStream_t st);
-int tc_gemm_tn_planes(int M, int N, int64_t R, const float* A, const void* b_hi, const void* b_lo, float* C, int accumulate,
-                      float* workspace, cudaStream_t st);
+int tc_gemm_tn_planes(int M, int N, int64_t R, const float* A, const void* a_hi, const void* a_lo, const float* B,
+                      const void* b_hi, const void* b_lo, float* C, int accumulate, float* workspace, cudaStream_t st);
 int tc_gemm_nt(int64_t M, int N, int K, const float* A, const float* B, const float* bias, float* C, int passes,
                float* workspace, cudaStream_t st);
 
@@ -70,8 +70,8 @@ extern "C" int vgtkb_inter_conv_forward(int b, int n, int p, int nn, int a, int 
 extern "C" int vgtkb_inter_conv_backward(int b, int n, int p, int nn, int a, int k, int ci, int co, const float* xyz,
                                          const float* sample_xyz, const int32_t* idx, const float* rot_kernels, float sigma,
                                          const float* w_kc, const void* g_hi, const void* g_lo, const float* grad_out,
-                                         float* grad_grouped, float* grad_feats, float* grad_w, float* workspace,
-                                         void* stream) {
+                                         const void* grad_out_hi, const void* grad_out_lo, float* grad_grouped,
+                                         float* grad_feats, float* grad_w, float* workspace, void* stream) {
     VGTKB_REQUIRE(conv_shape_ok(b, n, p, nn, a, k, ci, co), "inter_conv_backward: unsupported shape");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t rows = (int64_t)b * p * a;
@@ -79,7 +79,7 @@ extern "C" int vgtkb_inter_conv_backward(int b, int n, int p, int nn, int a, int
     int rc;
     if (grad_w != nullptr) {
         // dW [co, k*ci] = grad_out^T G: wide operand G straight from its planes; workspace = split of grad_out
-        rc = tc_gemm_tn_planes(co, kc, rows, grad_out, g_hi, g_lo, grad_w, 0, workspace, st);
+        rc = tc_gemm_tn_planes(co, kc, rows, grad_out, grad_out_hi, grad_out_lo, nullptr, g_hi, g_lo, grad_w, 0, workspace, st);
         if (rc == VGTKB_EUNSUP) set_error("inter_conv_backward: weight-gradient operands must be 16-byte aligned, rows >= 64");
         if (rc) return rc;
     }
@@ -89,7 +89,10 @@ extern "C" int vgtkb_inter_conv_backward(int b, int n, int p, int nn, int a, int
         float* wt = workspace;                       // [kc, co]
         float* wsplit = workspace + (size_t)kc * co; // hi/lo split of W^T (kc*co floats)
         transpose_kernel<<<dim3(ceil_div(kc, 32), ceil_div(co, 32)), dim3(32, 8), 0, st>>>(co, kc, w_kc, wt);
-        rc = tc_gemm_nt(rows, kc, co, grad_out, wt, nullptr, grad_grouped, 6, wsplit, st);
+        // (the planes of grad_out, when the producer wrote them, feed the contraction without conversion)
+        rc = (grad_out_hi != nullptr && grad_out_lo != nullptr && co >= 64)
+                 ? tc_gemm_nt_planes(rows, kc, co, grad_out_hi, grad_out_lo, wt, nullptr, grad_grouped, wsplit, st)
+                 : tc_gemm_nt(rows, kc, co, grad_out, wt, nullptr, grad_grouped, 6, wsplit, st);
         if (rc == VGTKB_EUNSUP) set_error("inter_conv_backward: dG contraction shape not covered (co %% 8 == 0, aligned operands)");
         if (rc) return rc;
         VGTKB_CUDA(cudaMemsetAsync(grad_feats, 0, sizeof(float) * (size_t)b * n * a * ci, st));

@@ -381,11 +381,28 @@ __global__ void norm_act_bwd_apply4_kernel(int64_t total4, int64_t rows, int64_t
 // batched forward / backward apply for c/4 dividing NT: grid (x, groups); the channel quad of a thread never changes
 // (the grid stride is a multiple of c/4), so the per-channel coefficients live in registers and a thread keeps U
 // independent 16-byte loads per array in flight.
+// bf16 hi / lo planes of four adjacent values (the operand split of the bf16x3 contractions, tc_common.cuh): written
+// next to the fp32 result when the consumer of this tensor is a tensor-core contraction, which then loads its operand
+// by TMA in the MMA's layout instead of converting it in the kernel (once here instead of once per k-block there).
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float a, float b) {   // a -> low half
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ void store_planes4(uint2* hi, uint2* lo, size_t i, const float (&o)[4]) {
+    const uint32_t h0 = pack_bf16x2_rn(o[0], o[1]), h1 = pack_bf16x2_rn(o[2], o[3]);
+    const uint32_t l0 = pack_bf16x2_rn(o[0] - __uint_as_float(h0 << 16), o[1] - __uint_as_float(h0 & 0xFFFF0000u));
+    const uint32_t l1 = pack_bf16x2_rn(o[2] - __uint_as_float(h1 << 16), o[3] - __uint_as_float(h1 & 0xFFFF0000u));
+    hi[i] = make_uint2(h0, h1);
+    lo[i] = make_uint2(l0, l1);
+}
+
 template <int U>
 __global__ void __launch_bounds__(NT, 4)
 norm_act_fwd4b_kernel(int64_t rows4, int c4, const float4* __restrict__ x, const float* __restrict__ stats,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
-                      const float4* __restrict__ res, float4* __restrict__ y) {
+                      const float4* __restrict__ res, float4* __restrict__ y, uint2* __restrict__ y_hi,
+                      uint2* __restrict__ y_lo) {
     const int c = c4 * 4, g = blockIdx.y;
     const int64_t t0 = (int64_t)blockIdx.x * NT + threadIdx.x, stride = (int64_t)gridDim.x * NT;
     const int ch = (int)(t0 % c4) * 4;
@@ -415,6 +432,7 @@ norm_act_fwd4b_kernel(int64_t rows4, int c4, const float4* __restrict__ x, const
                 for (int i = 0; i < 4; ++i) o[i] = o[i] > 0.f ? o[i] : o[i] * slope;
                 if (res) { o[0] += r[u].x; o[1] += r[u].y; o[2] += r[u].z; o[3] += r[u].w; }
                 y[base + tt] = make_float4(o[0], o[1], o[2], o[3]);
+                if (y_hi != nullptr) store_planes4(y_hi, y_lo, base + tt, o);
             }
         }
     }
@@ -423,7 +441,8 @@ norm_act_fwd4b_kernel(int64_t rows4, int c4, const float4* __restrict__ x, const
 template <int U>
 __global__ void __launch_bounds__(NT, 3)
 norm_act_bwd_apply4b_kernel(int64_t rows4, int64_t rows, int64_t nrows, int c4, const float4* __restrict__ x, OpBwd bw,
-                            const double* __restrict__ scratch, float4* __restrict__ gx) {
+                            const double* __restrict__ scratch, float4* __restrict__ gx, uint2* __restrict__ gx_hi,
+                            uint2* __restrict__ gx_lo) {
     const int c = c4 * 4, g = blockIdx.y;
     const int64_t t0 = (int64_t)blockIdx.x * NT + threadIdx.x, stride = (int64_t)gridDim.x * NT;
     const int ch = (int)(t0 % c4) * 4;
@@ -464,6 +483,7 @@ norm_act_bwd_apply4b_kernel(int64_t rows4, int64_t rows, int64_t nrows, int c4, 
                     o[i] = a[i] * (d - m1[i] - xh * m2[i]);
                 }
                 gx[base + tt] = make_float4(o[0], o[1], o[2], o[3]);
+                if (gx_hi != nullptr) store_planes4(gx_hi, gx_lo, base + tt, o);
             }
         }
     }
@@ -536,7 +556,14 @@ extern "C" int vgtkb_norm_stats(int groups, int64_t rows, int c, const float* x,
 extern "C" int vgtkb_norm_act_forward(int groups, int64_t rows, int c, const float* x, const float* stats,
                                       const float* gamma, const float* beta, float slope, const float* residual,
                                       float* y, void* stream) {
+    return vgtkb_norm_act_forward_planes(groups, rows, c, x, stats, gamma, beta, slope, residual, y, nullptr, nullptr, stream);
+}
+
+extern "C" int vgtkb_norm_act_forward_planes(int groups, int64_t rows, int c, const float* x, const float* stats,
+                                             const float* gamma, const float* beta, float slope, const float* residual,
+                                             float* y, void* y_hi, void* y_lo, void* stream) {
     VGTKB_REQUIRE(groups > 0 && rows > 0 && c > 0, "norm_act: bad size");
+    VGTKB_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "norm_act: both planes or none");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = (int64_t)groups * rows * c;
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -544,13 +571,17 @@ extern "C" int vgtkb_norm_act_forward(int groups, int64_t rows, int c, const flo
                     (!residual || al(residual));
     const int64_t work = v4 ? total / 4 : total;
     const unsigned grid = (unsigned)(ceil_div64(work, NT) < (int64_t)kNumSMs * 16 ? ceil_div64(work, NT) : kNumSMs * 16);
+    const bool planes_ok = v4 && NT % (c / 4) == 0 && groups <= 65535 &&
+                           ((reinterpret_cast<uintptr_t>(y_hi) | reinterpret_cast<uintptr_t>(y_lo)) & 7) == 0;
+    VGTKB_REQUIRE(y_hi == nullptr || planes_ok, "norm_act: planes need c %% 4 == 0, 256 %% (c/4) == 0 and aligned tensors");
     if (v4 && NT % (c / 4) == 0 && groups <= 65535) {
         const int64_t rows4 = rows * (c / 4);
         int64_t gx = ceil_div64(rows4, (int64_t)NT * 4);
         const int64_t cap = ceil_div64((int64_t)kNumSMs * 8, groups);
         if (gx > cap) gx = cap;
         norm_act_fwd4b_kernel<4><<<dim3((unsigned)gx, groups), NT, 0, st>>>(rows4, c / 4, (const float4*)x, stats, gamma, beta, slope,
-                                                                           (const float4*)residual, (float4*)y);
+                                                                           (const float4*)residual, (float4*)y, (uint2*)y_hi,
+                                                                           (uint2*)y_lo);
     } else if (v4)
         norm_act_fwd_kernel<<<grid, NT, 0, st>>>(work, rows, c / 4, (const float4*)x, stats, gamma, beta, slope,
                                                  (const float4*)residual, (float4*)y);
@@ -582,7 +613,15 @@ extern "C" int vgtkb_norm_bwd_sums(int groups, int64_t rows, int c, const float*
 extern "C" int vgtkb_norm_bwd_apply(int groups, int64_t rows, int64_t total_rows, int c, const float* x, const float* stats,
                                     const float* gamma, const float* beta, float slope, const float* grad_y,
                                     const double* scratch, float* grad_x, void* stream) {
+    return vgtkb_norm_bwd_apply_planes(groups, rows, total_rows, c, x, stats, gamma, beta, slope, grad_y, scratch, grad_x, nullptr,
+                                       nullptr, stream);
+}
+
+extern "C" int vgtkb_norm_bwd_apply_planes(int groups, int64_t rows, int64_t total_rows, int c, const float* x, const float* stats,
+                                           const float* gamma, const float* beta, float slope, const float* grad_y,
+                                           const double* scratch, float* grad_x, void* gx_hi, void* gx_lo, void* stream) {
     VGTKB_REQUIRE(groups > 0 && rows > 0 && (total_rows <= 0 || total_rows >= rows) && c > 0, "norm_bwd_apply: bad size");
+    VGTKB_REQUIRE((gx_hi == nullptr) == (gx_lo == nullptr), "norm_bwd_apply: both planes or none");
     VGTKB_REQUIRE(groups <= 65535, "norm_bwd_apply: too many groups");
     cudaStream_t st = (cudaStream_t)stream;
     OpBwd bw{grad_y, stats, gamma, beta, slope, c};
@@ -594,7 +633,10 @@ extern "C" int vgtkb_norm_bwd_apply(int groups, int64_t rows, int64_t total_rows
         const int64_t cap = ceil_div64((int64_t)kNumSMs * 6, groups);
         if (gx4 > cap) gx4 = cap;
         norm_act_bwd_apply4b_kernel<4><<<dim3((unsigned)gx4, groups), NT, 0, st>>>(rows4, rows, total_rows, c / 4, (const float4*)x, bw,
-                                                                                  scratch, (float4*)grad_x);
+                                                                                  scratch, (float4*)grad_x, (uint2*)gx_hi, (uint2*)gx_lo);
+    } else if (gx_hi != nullptr) {
+        set_error("norm_bwd_apply: planes need c %% 4 == 0, 256 %% (c/4) == 0 and 16-byte aligned tensors");
+        return VGTKB_EINVAL;
     } else if (c % 4 == 0 && al16(x) && al16(grad_y) && al16(grad_x)) {
         const int64_t total4 = total / 4;
         const unsigned grid4 = (unsigned)(ceil_div64(total4, NT) < (int64_t)kNumSMs * 16 ? ceil_div64(total4, NT) : kNumSMs * 16);
@@ -610,9 +652,18 @@ extern "C" int vgtkb_norm_act_backward(int groups, int64_t rows, int c, const fl
                                        const float* gamma, const float* beta, float slope, const float* grad_y,
                                        double* scratch, float* grad_x, float* grad_gamma, float* grad_beta,
                                        void* stream) {
+    return vgtkb_norm_act_backward_planes(groups, rows, c, x, stats, gamma, beta, slope, grad_y, scratch, grad_x, grad_gamma,
+                                          grad_beta, nullptr, nullptr, stream);
+}
+
+extern "C" int vgtkb_norm_act_backward_planes(int groups, int64_t rows, int c, const float* x, const float* stats,
+                                              const float* gamma, const float* beta, float slope, const float* grad_y,
+                                              double* scratch, float* grad_x, float* grad_gamma, float* grad_beta,
+                                              void* gx_hi, void* gx_lo, void* stream) {
     const int rc = vgtkb_norm_bwd_sums(groups, rows, c, x, stats, gamma, beta, slope, grad_y, scratch, grad_gamma, grad_beta, stream);
     if (rc != 0) return rc;
-    return vgtkb_norm_bwd_apply(groups, rows, rows, c, x, stats, gamma, beta, slope, grad_y, scratch, grad_x, stream);
+    return vgtkb_norm_bwd_apply_planes(groups, rows, rows, c, x, stats, gamma, beta, slope, grad_y, scratch, grad_x, gx_hi, gx_lo,
+                                       stream);
 }
 
 extern "C" int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream) {

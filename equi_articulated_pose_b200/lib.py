@@ -61,7 +61,13 @@ SIGNATURES = {
     "vgtkb_gemm_nt_presplit": [c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_gemm_tn_presplit": [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp],
     "vgtkb_inter_conv_forward": [c_int] * 8 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
-    "vgtkb_inter_conv_backward": [c_int] * 8 + [c_vp, c_vp, c_vp, c_vp, c_f32] + [c_vp] * 9,
+    "vgtkb_inter_conv_backward": [c_int] * 8 + [c_vp, c_vp, c_vp, c_vp, c_f32] + [c_vp] * 11,
+    "vgtkb_gemm_tn_planes": [c_int, c_int, c_i64] + [c_vp] * 7 + [c_int, c_vp, c_vp],
+    "vgtkb_gather_gemm_nt_planes": [c_i64, c_int, c_int, c_int, c_int] + [c_vp] * 8,
+    "vgtkb_gather_gemm_tn_planes": [c_i64, c_int, c_int, c_int, c_int] + [c_vp] * 7 + [c_int, c_vp, c_vp],
+    "vgtkb_norm_act_forward_planes": [c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_norm_bwd_apply_planes": [c_int, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "vgtkb_norm_act_backward_planes": [c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_knn_query": [c_int] * 4 + [c_vp] * 5,
     "vgtkb_sa_group_forward": [c_int] * 6 + [c_vp] * 6,
     "vgtkb_sa_group_backward": [c_int] * 6 + [c_vp] * 4,
@@ -172,4 +178,5 @@ KERNELS_PER_CALL = {"vgtkb_gemm_nt": 2, "vgtkb_gemm_tn": 2, "vgtkb_gather_gemm_n
                     "vgtkb_chamfer_forward": 2, "vgtkb_chamfer_backward": 4, "vgtkb_anchor_chamfer_forward": 2, "vgtkb_anchor_chamfer_backward": 2, "vgtkb_norm_stats": 2,
                     "vgtkb_norm_act_backward": 3, "vgtkb_norm_bwd_sums": 2, "vgtkb_col_sum": 2,
                     "vgtkb_inter_conv_forward": 3, "vgtkb_inter_conv_backward": 6, "vgtkb_gemm_nt_presplit": 2,
-                    "vgtkb_gemm_tn_presplit": 2}
+                    "vgtkb_gemm_tn_presplit": 2, "vgtkb_gemm_tn_planes": 1, "vgtkb_gather_gemm_nt_planes": 2,
+                    "vgtkb_gather_gemm_tn_planes": 1, "vgtkb_norm_act_backward_planes": 3}

@@ -188,6 +188,49 @@ class InterGroupFn(torch.autograd.Function):
         return gx, None, None, None, None, None
 
 
+# ----------------------------------------------------------------------------- operand planes
+# A producer kernel (norm apply forward / backward) can write the bf16 hi / lo planes of its fp32 result; the contraction
+# that consumes the tensor then loads its operand by TMA without converting it.  The planes travel beside the fp32 tensor
+# in this table, keyed by the tensor's address (views keep it); an entry keeps the fp32 tensor alive, so the address cannot
+# be reused while the entry exists, and is dropped by its (single) consumer.  A miss just means the fp32 operand is used.
+_PLANES = {}
+_PLANES_MAX = 64
+PLANE_STATS = {"hit": 0, "miss": 0}
+
+
+def register_planes(t, hi, lo):
+    if len(_PLANES) >= _PLANES_MAX:
+        _PLANES.pop(next(iter(_PLANES)))
+    _PLANES[t.data_ptr()] = (t, t._version, hi, lo)
+
+
+def take_planes(t, keep=False):
+    """(hi, lo) planes registered for the storage `t` views (same start, same size, unmodified since), else (None, None)."""
+    e = _PLANES.get(t.data_ptr()) if t.is_cuda else None
+    if e is None or e[0].numel() != t.numel() or e[0]._version != e[1] or not t.is_contiguous():
+        PLANE_STATS["miss"] += 1
+        return None, None
+    if not keep:
+        del _PLANES[t.data_ptr()]
+    PLANE_STATS["hit"] += 1
+    return e[2], e[3]
+
+
+def clear_planes():
+    _PLANES.clear()
+
+
+def planes_enabled():
+    return _GEMM_MODE == 3 and _USE_PLANES
+
+
+_USE_PLANES = True
+
+
+def _alloc_planes(t):
+    return (torch.empty(t.shape, dtype=torch.bfloat16, device=t.device), torch.empty(t.shape, dtype=torch.bfloat16, device=t.device))
+
+
 def inter_conv_supported(b, n, p, nn, a, k, ci, co):
     """Shapes vgtkb_inter_conv_forward/backward take (mode 3 only; the others run InterGroupFn + LinearFn)."""
     return _GEMM_MODE == 3 and bool(_lib.load().vgtkb_inter_conv_supported(b, n, p, nn, a, k, ci, co))
@@ -229,8 +272,9 @@ class InterConvFn(torch.autograd.Function):
         dg = torch.empty((rows, kc), dtype=torch.float32, device=dev) if need_x else None
         gw = torch.empty((co, kc), dtype=torch.float32, device=dev) if need_w else None
         ws = torch.empty(max(rows * co, 2 * kc * co), dtype=torch.float32, device=dev)
+        gy_hi, gy_lo = take_planes(gy)
         call("vgtkb_inter_conv_backward", dev, b, n, p, nn, a, k, ci, co, ptr(xyz), ptr(sample_xyz), ptr(idx), ptr(rot_kernels),
-             sigma, ptr(w_kc), ptr(g_hi), ptr(g_lo), ptr(gy), ptr(dg), ptr(gx), ptr(gw), ptr(ws))
+             sigma, ptr(w_kc), ptr(g_hi), ptr(g_lo), ptr(gy), ptr(gy_hi), ptr(gy_lo), ptr(dg), ptr(gx), ptr(gw), ptr(ws))
         return gx, gw, None, None, None, None, None
 
 
@@ -331,29 +375,72 @@ def gather_gemm_supported(c_in, c_out, points):
     return _GEMM_MODE != 0 and c_in % 64 == 0 and c_out % 64 == 0 and points >= 64
 
 
+def gather_gemm_nt_planes(x_hi, x_lo, table, w, bias=None):
+    """gather_gemm_nt with x [points, A, C] given as bf16 planes (no operand conversion in the kernel)."""
+    w = _f32(w)
+    pts, a, c = x_hi.shape
+    kk, n = table.shape[1], w.shape[0]
+    assert w.shape[1] == kk * c and table.shape[0] == a and table.dtype == torch.int32
+    out = torch.empty((pts * a, n), dtype=torch.float32, device=w.device)
+    ws = torch.empty(n * kk * c, dtype=torch.float32, device=w.device)
+    call("vgtkb_gather_gemm_nt_planes", w.device, pts, a, kk, c, n, ptr(table), ptr(x_hi), ptr(x_lo), ptr(w),
+         ptr(bias.contiguous()) if bias is not None else None, ptr(out), ptr(ws))
+    return out
+
+
+def gather_gemm_tn_planes(x_hi, x_lo, table, y, y_hi=None, y_lo=None):
+    """gather_gemm_tn with x as planes and y [points*A, m] as fp32 or planes -> [m, kk*C]."""
+    pts, a, c = x_hi.shape
+    kk, m = table.shape[1], y.shape[1]
+    out = torch.empty((m, kk * c), dtype=torch.float32, device=y.device)
+    ws = torch.empty(pts * a * m, dtype=torch.float32, device=y.device) if y_hi is None else None
+    call("vgtkb_gather_gemm_tn_planes", y.device, pts, a, kk, c, m, ptr(table), ptr(x_hi), ptr(x_lo), ptr(y), ptr(y_hi), ptr(y_lo),
+         ptr(out), 0, ptr(ws))
+    return out
+
+
 class IntraConvFn(torch.autograd.Function):
     """Intra-anchor group convolution as gather-GEMMs (forward, data gradient with the inverse table, weight
-    gradient); x [points, A, C] channels-last, w_kc [Co, KK*C] -> [points*A, Co].  No gathered tensor exists."""
+    gradient); x [points, A, C] channels-last, w_kc [Co, KK*C] -> [points*A, Co].  No gathered tensor exists.
+    When the producers of x / of the output gradient registered operand planes (norm kernels), the contractions read
+    them instead of converting the fp32 tensors k-block by k-block (the intra conv re-reads every element 12 times)."""
 
     @staticmethod
     def forward(ctx, x, w_kc, table, table_inv):
         x, w_kc = _f32(x), _f32(w_kc)
+        x_hi, x_lo = take_planes(x) if planes_enabled() and x.shape[2] % 64 == 0 else (None, None)
+        ctx.planes = x_hi is not None
+        if ctx.planes:
+            x_hi, x_lo = x_hi.view(x.shape), x_lo.view(x.shape)
+            ctx.save_for_backward(x_hi, x_lo, w_kc, table, table_inv)
+            return gather_gemm_nt_planes(x_hi, x_lo, table, w_kc)
         ctx.save_for_backward(x, w_kc, table, table_inv)
         return gather_gemm_nt(x, table, w_kc)
 
     @staticmethod
     def backward(ctx, gy):
-        x, w_kc, table, table_inv = ctx.saved_tensors
-        pts, a, c = x.shape
+        if ctx.planes:
+            x_hi, x_lo, w_kc, table, table_inv = ctx.saved_tensors
+            pts, a, c = x_hi.shape
+        else:
+            x, w_kc, table, table_inv = ctx.saved_tensors
+            pts, a, c = x.shape
         kk, co = table.shape[1], w_kc.shape[0]
         gy = _f32(gy)
+        gy_hi, gy_lo = take_planes(gy) if planes_enabled() and co % 64 == 0 else (None, None)
         gx = gw = None
         if ctx.needs_input_grad[0]:
             # gx[(pt,a'), c] = sum_{kk,o} gy[pt, inv[a',kk], o] * w_kc[o, kk*C + c]
             wt = w_kc.view(co, kk, c).permute(2, 1, 0).reshape(c, kk * co).contiguous()
-            gx = gather_gemm_nt(gy.view(pts, a, co), table_inv, wt).view(pts, a, c)
+            if gy_hi is not None:
+                gx = gather_gemm_nt_planes(gy_hi.view(pts, a, co), gy_lo.view(pts, a, co), table_inv, wt).view(pts, a, c)
+            else:
+                gx = gather_gemm_nt(gy.view(pts, a, co), table_inv, wt).view(pts, a, c)
         if ctx.needs_input_grad[1]:
-            gw = gather_gemm_tn(x, table, gy)
+            if ctx.planes:
+                gw = gather_gemm_tn_planes(x_hi, x_lo, table, gy, gy_hi, gy_lo)
+            else:
+                gw = gather_gemm_tn(x, table, gy)
         return gx, gw, None, None
 
 
@@ -488,7 +575,8 @@ class NormActFn(torch.autograd.Function):
     (nn.SyncBatchNorm semantics: SPConvNets/trainer_unsup_arti_align.py:430 converts every BatchNorm)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, momentum, eps, slope, use_running, sync_group=None):
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, momentum, eps, slope, use_running, sync_group=None,
+                planes_fwd=False, planes_bwd=False):
         x = _f32(x)
         g, rows, c = x.shape
         dev = x.device
@@ -517,10 +605,18 @@ class NormActFn(torch.autograd.Function):
         gam = gamma.contiguous() if gamma is not None else None
         bet = beta.contiguous() if beta is not None else None
         res = _f32(residual) if residual is not None else None
-        call("vgtkb_norm_act_forward", dev, g, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), float(slope), ptr(res),
-             ptr(y))
+        pl_ok = planes_enabled() and c % 4 == 0 and 256 % (c // 4) == 0
+        if planes_fwd and pl_ok:
+            y_hi, y_lo = _alloc_planes(y)
+            call("vgtkb_norm_act_forward_planes", dev, g, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), float(slope), ptr(res),
+                 ptr(y), ptr(y_hi), ptr(y_lo))
+            register_planes(y, y_hi, y_lo)
+        else:
+            call("vgtkb_norm_act_forward", dev, g, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), float(slope), ptr(res),
+                 ptr(y))
         ctx.save_for_backward(x, stats, gam, bet)
         ctx.meta = (g, rows, c, float(slope), use_running, residual is not None, sync_group if sync else None)
+        ctx.planes_bwd = bool(planes_bwd and pl_ok)
         return y
 
     @staticmethod
@@ -534,24 +630,30 @@ class NormActFn(torch.autograd.Function):
         gx = torch.empty_like(x)
         ggam = torch.empty(c, dtype=torch.float32, device=dev) if gam is not None else None
         gbet = torch.empty(c, dtype=torch.float32, device=dev) if bet is not None else None
+        gx_hi, gx_lo = _alloc_planes(gx) if ctx.planes_bwd else (None, None)
         if sync_group is not None:
             scratch = torch.empty(2 * c + 1, dtype=torch.float64, device=dev)
             scratch[2 * c:].fill_(float(rows))
             call("vgtkb_norm_bwd_sums", dev, 1, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), slope, ptr(gy),
                  ptr(scratch), ptr(ggam), ptr(gbet))       # affine gradients: local sums, reduced with the other parameters
             _all_reduce_sums(scratch, sync_group)
-            call("vgtkb_norm_bwd_apply", dev, 1, rows, 0, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), slope, ptr(gy),
-                 ptr(scratch), ptr(gx))
+            call("vgtkb_norm_bwd_apply_planes", dev, 1, rows, 0, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), slope, ptr(gy),
+                 ptr(scratch), ptr(gx), ptr(gx_hi), ptr(gx_lo))
         else:
             scratch = torch.empty((g, 2, c), dtype=torch.float64, device=dev)
-            call("vgtkb_norm_act_backward", dev, g, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), slope, ptr(gy),
-                 ptr(scratch), ptr(gx), ptr(ggam), ptr(gbet))
-        return gx, ggam, gbet, (gy if has_res else None), None, None, None, None, None, None, None
+            call("vgtkb_norm_act_backward_planes", dev, g, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), slope, ptr(gy),
+                 ptr(scratch), ptr(gx), ptr(ggam), ptr(gbet), ptr(gx_hi), ptr(gx_lo))
+        if gx_hi is not None:
+            register_planes(gx, gx_hi, gx_lo)
+        return gx, ggam, gbet, (gy if has_res else None), None, None, None, None, None, None, None, None, None
 
 
 def norm_act(x, gamma=None, beta=None, residual=None, running_mean=None, running_var=None, momentum=0.1, eps=1e-5,
-             slope=LEAKY_SLOPE, use_running=False, sync_group=None):
-    return NormActFn.apply(x, gamma, beta, residual, running_mean, running_var, momentum, eps, slope, use_running, sync_group)
+             slope=LEAKY_SLOPE, use_running=False, sync_group=None, planes_fwd=False, planes_bwd=False):
+    """planes_fwd: also write the bf16 operand planes of the result (its consumer is a tensor-core contraction);
+    planes_bwd: likewise for the input gradient in backward (the producer of x is a contraction)."""
+    return NormActFn.apply(x, gamma, beta, residual, running_mean, running_var, momentum, eps, slope, use_running, sync_group,
+                           planes_fwd, planes_bwd)
 
 
 class AnchorChamferFn(torch.autograd.Function):

@@ -301,6 +301,29 @@ int vgtkb_gemm_nt_presplit(int64_t M, int N, int K, const void* a_hi, const void
 int vgtkb_gemm_tn_presplit(int M, int N, int64_t R, const float* A, const void* b_hi, const void* b_lo, float* C, int accumulate,
                            float* workspace, void* stream);
 
+/*   gemm_tn_planes:    general form: narrow operand A as planes (a_hi / a_lo) or fp32 (split into workspace), wide operand B
+ *                      as planes (b_hi / b_lo) or fp32 (B, converted in the kernel)
+ *   gather_gemm_*_planes: the intra-conv gather-GEMMs (vgtkb_gather_gemm_nt / _tn) with X [points, a, c] given as planes
+ *                      (c % 64 == 0); the weight gradient takes Y as planes too, or as fp32 (split into workspace: points*a*m floats) */
+int vgtkb_gemm_tn_planes(int M, int N, int64_t R, const float* A, const void* a_hi, const void* a_lo, const float* B,
+                         const void* b_hi, const void* b_lo, float* C, int accumulate, float* workspace, void* stream);
+int vgtkb_gather_gemm_nt_planes(int64_t points, int anchors, int kk, int c, int n, const int32_t* table, const void* x_hi,
+                                const void* x_lo, const float* w, const float* bias, float* out, float* workspace, void* stream);
+int vgtkb_gather_gemm_tn_planes(int64_t points, int anchors, int kk, int c, int m, const int32_t* table, const void* x_hi,
+                                const void* x_lo, const float* y, const void* y_hi, const void* y_lo, float* out, int accumulate,
+                                float* workspace, void* stream);
+/* norm kernels that also write the bf16 planes of their result (y_hi / y_lo resp. gx_hi / gx_lo, same shape as the fp32
+ * output; both NULL = plain call): the consumer contraction then needs no operand conversion.  c % 4 == 0, 256 % (c/4) == 0. */
+int vgtkb_norm_act_forward_planes(int groups, int64_t rows, int c, const float* x, const float* stats, const float* gamma,
+                                  const float* beta, float slope, const float* residual, float* y, void* y_hi, void* y_lo,
+                                  void* stream);
+int vgtkb_norm_bwd_apply_planes(int groups, int64_t rows, int64_t total_rows, int c, const float* x, const float* stats,
+                                const float* gamma, const float* beta, float slope, const float* grad_y, const double* scratch,
+                                float* grad_x, void* gx_hi, void* gx_lo, void* stream);
+int vgtkb_norm_act_backward_planes(int groups, int64_t rows, int c, const float* x, const float* stats, const float* gamma,
+                                   const float* beta, float slope, const float* grad_y, double* scratch, float* grad_x,
+                                   float* grad_gamma, float* grad_beta, void* gx_hi, void* gx_lo, void* stream);
+
 /* InterSO3Conv as one call per direction: ball-neighbourhood grouping under the kernel-point correlation + contraction with W
  * (reference: inter_so3conv_grouping, vgtk/vgtk/so3conv/functional.py:144-203 -> inter_zpconv_grouping_naive,
  * vgtk/vgtk/spconv/functional.py:375-406 -> BasicSO3Conv.forward, vgtk/vgtk/so3conv/modules.py:48-55; backward = what autograd
@@ -311,6 +334,8 @@ int vgtkb_gemm_tn_presplit(int M, int N, int64_t R, const float* A, const void* 
  *             keeps them for backward.  workspace: co*k*ci floats.
  *   backward: grad_out [b*p*a, co] -> grad_w [co, k*ci] (overwritten; NULL = skip) and grad_feats [b,n,a,ci] (overwritten;
  *             NULL = skip; needs the scratch grad_grouped [b*p*a, k*ci] fp32).  workspace: max(b*p*a*co, 2*k*ci*co) floats.
+ *             grad_out_hi / grad_out_lo: optional bf16 planes of grad_out (vgtkb_norm_bwd_apply_planes writes them); NULL =
+ *             grad_out is split / converted here.
  *   supported: 1 iff the shape is taken (k <= 24, nn <= 32, ci % 32 == 0, co % 8 == 0, co <= 256, b*p*a >= 64, 32-bit offsets);
  *             other shapes run vgtkb_inter_group_* + vgtkb_gemm_*. */
 int vgtkb_inter_conv_supported(int b, int n, int p, int nn, int a, int k, int ci, int co);
@@ -321,7 +346,8 @@ int vgtkb_inter_conv_forward(int b, int n, int p, int nn, int a, int k, int ci, 
 int vgtkb_inter_conv_backward(int b, int n, int p, int nn, int a, int k, int ci, int co, const float* xyz,
                               const float* sample_xyz, const int32_t* idx, const float* rot_kernels, float sigma,
                               const float* w_kc, const void* g_hi, const void* g_lo, const float* grad_out,
-                              float* grad_grouped, float* grad_feats, float* grad_w, float* workspace, void* stream);
+                              const void* grad_out_hi, const void* grad_out_lo, float* grad_grouped, float* grad_feats,
+                              float* grad_w, float* workspace, void* stream);
 
 /* column sums of a row-major [rows, c] matrix (bias gradient of the skip conv) */
 int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream);

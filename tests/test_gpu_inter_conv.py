@@ -107,3 +107,39 @@ def test_inter_conv_module_path_is_default(dev):
     finally:
         ops.set_gemm_mode(prev)
     assert float((y.feats - y1.feats).abs().max()) <= 2e-5 * float(y1.feats.abs().max())
+
+
+def test_operand_planes_block_matches_fp32_operands(dev):
+    """A separable block with the norm kernels writing operand planes (default) against the same block with the planes
+    switched off (every contraction converts its fp32 operand itself): same arithmetic, so outputs and gradients agree to
+    the order of the atomics; and the planes are actually consumed (no silent fallback)."""
+    from equi_articulated_pose_b200 import blocks, ops
+    from oracle import so3 as O
+    import vgtk.spconv as zptk
+    params = {'dim_in': 64, 'dim_out': 64, 'kernel_size': 1, 'stride': 1, 'radius': 0.45, 'sigma': 0.08, 'n_neighbor': 16,
+              'lazy_sample': True, 'dropout_rate': 0.0, 'multiplier': 2, 'activation': 'leaky_relu', 'pooling': None,
+              'kanchor': 60, 'norm': 'BatchNorm2d'}
+    torch.manual_seed(1)
+    blk = blocks.SeparableSO3ConvBlock(params).to(dev).train()
+    xyz = O.synthetic_cloud(2, 128, 9).permute(0, 2, 1).contiguous().to(dev)
+    f0 = torch.randn(2, 128, 60, 64, device=dev)
+    res = []
+    for use in (True, False):
+        ops._USE_PLANES = use
+        ops.clear_planes()
+        ops.PLANE_STATS.update(hit=0, miss=0)
+        try:
+            blk.zero_grad(set_to_none=True)
+            f = f0.clone().requires_grad_(True)
+            _, _, _, y = blk(zptk.SphericalPointCloud(xyz, f.permute(0, 3, 1, 2), None), None, None)
+            y.feats.square().mean().backward()
+            res.append((y.feats.detach().clone(), f.grad.clone(), {k: p.grad.clone() for k, p in blk.named_parameters()},
+                        dict(ops.PLANE_STATS)))
+        finally:
+            ops._USE_PLANES = True
+    (y1, g1, p1, st1), (y0, g0, p0, _) = res
+    assert st1["hit"] >= 3 and st1["miss"] == 0, st1       # x planes (intra fwd), gy planes (intra bwd, inter bwd)
+    assert float((y1 - y0).abs().max()) <= 1e-6 * float(y0.abs().max())
+    assert float((g1 - g0).abs().max()) <= 2e-5 * float(g0.abs().max())
+    for k in p0:
+        assert float((p1[k] - p0[k]).abs().max()) <= 2e-5 * float(p0[k].abs().max()) + 1e-9, k
