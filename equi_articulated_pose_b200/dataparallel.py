@@ -158,14 +158,23 @@ class PeerMailbox:
         dist.barrier(group=group)
 
     def next_seq(self):
-        self.seq += 1
-        return self.seq
+        """Sequence argument of the exchange kernels: 0 = the kernel takes the next value of the mailbox's device-side
+        counter, so the call can be captured in a CUDA graph and replayed (every rank runs the same exchanges)."""
+        return 0
 
     def all_reduce_sums(self, buf):
         """buf (fp64, <= 2049 elements) <- sum over ranks, in place, on the current stream."""
         from . import lib
         lib.call("vgtkb_peer_allreduce_f64", self.device, buf.numel(), lib.ptr(buf), self.rank, self.world, self.ptrs,
                  self.next_seq())
+
+    def status(self):
+        """0, or r + 1 when rank r missed an exchange (timeout VGTKB_PEER_TIMEOUT_S, default 600 s).  Synchronises."""
+        import ctypes
+        from . import lib
+        st = ctypes.c_int64(0)
+        lib.call("vgtkb_peer_status", self.device, self._own, self.world, ctypes.byref(st))
+        return int(st.value)
 
     def close(self):
         from . import lib

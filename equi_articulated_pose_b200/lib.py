@@ -78,6 +78,7 @@ SIGNATURES = {
     "vgtkb_three_interpolate_backward": [c_int] * 4 + [c_vp] * 5,
     "vgtkb_peer_allreduce_f64": [c_int, c_vp, c_int, c_int, c_vp, ctypes.c_uint64, c_vp],
     "vgtkb_norm_finalize_peer": [c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_int, c_vp, ctypes.c_uint64, c_vp],
+    "vgtkb_peer_status": [c_vp, c_int, ctypes.POINTER(c_i64), c_vp],
 }
 # entry points without a stream argument (setup of the peer mailboxes); status int like the others
 SETUP_SIGNATURES = {
@@ -87,6 +88,7 @@ SETUP_SIGNATURES = {
     "vgtkb_peer_close": [c_vp],
     "vgtkb_peer_free": [c_vp],
 }
+# (vgtkb_peer_status takes a stream but returns through a host pointer: bound in SIGNATURES below)
 NO_STATUS = {"vgtkb_last_error": (ctypes.c_char_p, []), "vgtkb_version": (c_int, []),
              "vgtkb_device_check": (c_int, []), "vgtkb_inter_conv_supported": (c_int, [c_int] * 8)}
 

@@ -233,9 +233,14 @@ int vgtkb_norm_bwd_apply(int groups, int64_t rows_per_group, int64_t total_rows,
  *   vgtkb_peer_alloc:  cudaMalloc + zero a mailbox on the current device, export its IPC handle (64 bytes)
  *   vgtkb_peer_open / vgtkb_peer_close: map / unmap a peer's mailbox from its handle;  vgtkb_peer_free: own mailbox
  *   vgtkb_peer_allreduce_f64: buf[0..n) <- sum over ranks, n <= 2049; one single-CTA kernel; `mailboxes` = HOST array of
- *       `world` device pointers (entry `rank` = own mailbox); `seq` = 1, 2, 3, ... identical on all ranks per call
+ *       `world` device pointers (entry `rank` = own mailbox); `seq` = 0: the kernel takes the next value of the mailbox's
+ *       device-side exchange counter (replayable from a CUDA graph; what the Python host passes), or an explicit 1, 2, 3, ...
+ *       identical on all ranks per call
  *   vgtkb_norm_finalize_peer: the exchange of scratch [2c sums | row count] fused with vgtkb_norm_finalize (groups = 1)
- * Every rank must issue the same sequence of exchanges; a peer that does not show up within 30 s traps the kernel. */
+ *   vgtkb_peer_status: 0, or r + 1 when rank r did not arrive within the timeout in some exchange (synchronises `stream`)
+ * Every rank must issue the same sequence of exchanges.  A peer that does not show up within VGTKB_PEER_TIMEOUT_S seconds
+ * (default 600, the order of a process-group timeout) makes the kernel give up: it records the status word, prints a
+ * message and returns with invalid sums -- the CUDA context survives (no trap).  VGTKB_PEER_SYNCBN=0 selects NCCL instead. */
 #define VGTKB_IPC_HANDLE_BYTES 64
 int vgtkb_peer_mailbox_bytes(int world, int64_t* bytes);
 int vgtkb_peer_alloc(int64_t bytes, void** dev_ptr, void* ipc_handle);
@@ -245,6 +250,7 @@ int vgtkb_peer_free(void* dev_ptr);
 int vgtkb_peer_allreduce_f64(int n, double* buf, int rank, int world, void* const* mailboxes, uint64_t seq, void* stream);
 int vgtkb_norm_finalize_peer(int c, float eps, double* scratch, float* stats, float* running_mean, float* running_var,
                              float momentum, int rank, int world, void* const* mailboxes, uint64_t seq, void* stream);
+int vgtkb_peer_status(const void* own_mailbox, int world, int64_t* status, void* stream);
 
 /* PointnetSO3Conv pooling head (vgtk/vgtk/so3conv/modules.py:376-413).  e [b, n, a, co]: rows of the feature part of
  * the 1x1 conv (vgtkb_gemm_nt with the bias); v [a, co, 3] = sum_i W_x[o,i] anchors[a,j,i]; xc [b, 3, n] centred xyz.
