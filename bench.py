@@ -378,6 +378,11 @@ def dp_parity_check(dev, rank, world, sync_bn):
     return res
 
 
+def log(msg):
+    if os.environ.get("VGTKB_BENCH_LOG", "0") == "1":
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -393,7 +398,9 @@ def run_ours(args):
     n_points = cfg["n_points"]
 
     sync_bn = world > 1 and not args.no_sync_bn
+    log(f"rank {rank}: dp_parity check")
     parity = dp_parity_check(dev, rank, world, sync_bn) if world > 1 else None
+    log(f"rank {rank}: dp_parity {parity}")
 
     net, params, clouds_host, total_clouds = build_workload(cfg, dev, world, rank)
     if sync_bn:
@@ -428,6 +435,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # step 0 in eager mode: its loss is checked against the oracle's value for this exact workload
+    log(f"rank {rank}: eager steps")
     loss0 = float(step(clouds_dev))
     loss_check = None
     want = ORACLE_STEP0_LOSS.get(args.config)
@@ -456,19 +464,36 @@ def run_ours(args):
     records, lib.PROFILE = lib.PROFILE, None
     launches_per_step = (lib.COUNTERS["kernels"] - k0) // args.steps
 
-    # ---- capture the step once; timed regions replay it
-    use_graph = not args.no_graph
-    graph_note = "eager launches (--no-graph)"
+    # ---- capture the step once; timed regions replay it.  N = 1: one graph (forward + backward + Adam).  N > 1: the NCCL
+    # gradient all-reduce stays an eager call between two graphs (forward + backward + bucket | Adam) -- the SyncBatchNorm
+    # exchanges inside the first graph are plain kernels over peer memory with a device-side sequence counter, so they
+    # replay; an NCCL-based SyncBatchNorm (no peer mailboxes) keeps the step eager.
+    use_graph = not args.no_graph and (world == 1 or not sync_bn or ops._PEER_MAILBOX is not None)
+    graph_note = "eager launches" + (" (--no-graph)" if args.no_graph else "")
     run_step = step
-    if use_graph:
-        try:
-            captured = G.CapturedStep(step, [clouds_dev], warmup=2)
-            run_step = captured
-            graph_note = "one CUDA graph per step (forward + backward + gradient exchange + Adam), replayed"
-        except Exception as e:  # noqa: BLE001
-            use_graph = False
-            graph_note = f"eager launches (graph capture failed: {str(e).splitlines()[0][:120]})"
-            torch.cuda.synchronize()
+    log(f"rank {rank}: capturing the step (graph={use_graph})")
+    if use_graph and world == 1:
+        captured = G.CapturedStep(step, [clouds_dev], warmup=2)
+        run_step = captured
+        graph_note = "one CUDA graph per step (forward + backward + Adam), replayed"
+    elif use_graph:
+        def step_a(pts):
+            bucket.zero_()
+            out = net(pts)
+            loss = out.feats.square().mean()
+            loss.backward()
+            bucket.collect()
+            return loss.detach()
+        captured = G.CapturedStep(step_a, [clouds_dev], warmup=2)
+        captured_b = G.CapturedStep(lambda: opt.step(), [], warmup=1)
+
+        def run_step(pts):
+            loss = captured(pts)
+            bucket.all_reduce_mean()
+            captured_b()
+            return loss
+        graph_note = "two CUDA graphs per step (forward + backward + SyncBatchNorm peer exchanges | Adam) around one eager NCCL all-reduce"
+    log(f"rank {rank}: capture done")
     dev_in = captured.static_in[0] if use_graph else clouds_dev      # graph: the static input buffer (holds the same clouds)
     for _ in range(2):
         run_step(dev_in)
@@ -476,6 +501,7 @@ def run_ours(args):
     barrier()
 
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------
+    log(f"rank {rank}: timed regions")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

@@ -69,5 +69,5 @@ def test_model38_backbone_on_articulated_clouds_vs_oracle(dev, kind, seed):
         if scale < 1e-6 * gmax:          # structurally zero gradients (bias in front of BatchNorm, constant first skip branch)
             assert e_gpu < 1e-4 * gmax, (name, e_gpu)
         else:                            # same bar as the classic backbone test: as close to fp64 as the fp32 reference
-            assert e_gpu <= max(5 * e_ref, 1e-1 * scale), (name, e_gpu / scale, e_ref / scale)
+            assert e_gpu <= max(5 * e_ref, 5e-2 * scale), (name, e_gpu / scale, e_ref / scale)
     print(kind, "fwd rel err", rel_err(out.feats, of), "worst grad err / scale", max(r[2] / r[1] for r in rows if r[1] >= 1e-6 * gmax))
