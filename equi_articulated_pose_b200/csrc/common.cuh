@@ -7,7 +7,7 @@
 
 #include "../../include/vgtkb.h"
 
-#define VGTKB_ABI_VERSION 10
+#define VGTKB_ABI_VERSION 11
 
 namespace vgtkb {
 

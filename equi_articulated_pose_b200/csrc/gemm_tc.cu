@@ -390,7 +390,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                        const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c, int tma_out,
                        const float* __restrict__ bias, float* __restrict__ C, int64_t M, int N, int K, int chunk_kb, TcGather ga,
-                       const __grid_constant__ CUtensorMap map_a2) {
+                       const __grid_constant__ CUtensorMap map_a2, int fast) {
+    // fast != 0: single-pass bf16 (contraction mode 4, BASELINE config 3): only the hi planes take part -- one MMA per k-step
+    // instead of three, and the lo planes are neither loaded (PRE) nor used
     using Cfg = PairCfg<BN_>;
     constexpr int STAGES = Cfg::STAGES, BN = Cfg::BN, KBE = 64, UK = 16;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -574,9 +576,13 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                             const uint64_t da_lo = make_smem_desc(a_lo + koff, 16, 1024);
                             const uint64_t db_lo = make_smem_desc(b_lo + koff, 16, 1024);
                             const uint32_t first = ((kb - kb0) | ks) != 0;
-                            umma_bf16_pair(d_tmem, da_lo, db_hi, idesc, first);
-                            umma_bf16_pair(d_tmem, da_hi, db_lo, idesc, 1);
-                            umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, 1);
+                            if (fast) {
+                                umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, first);
+                            } else {
+                                umma_bf16_pair(d_tmem, da_lo, db_hi, idesc, first);
+                                umma_bf16_pair(d_tmem, da_hi, db_lo, idesc, 1);
+                                umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, 1);
+                            }
                         }
                         umma_commit_pair(&bars.empty[s]);
                     }
@@ -593,7 +599,8 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             if (PRE) tma_prefetch_desc(&map_a2);
             tma_prefetch_desc(&map_bhi);
             tma_prefetch_desc(&map_blo);
-            const uint32_t tx = 2u * (uint32_t)Cfg::A_BYTES + 2u * (uint32_t)Cfg::BH_BYTES;
+            const bool skip_alo = PRE && fast;       // raw fp32 operands always arrive as two boxes
+            const uint32_t tx = (skip_alo ? 1u : 2u) * (uint32_t)Cfg::A_BYTES + (fast ? 1u : 2u) * (uint32_t)Cfg::BH_BYTES;
             int it = 0;
             for (int tile = pair; tile < total_tiles; tile += npairs) {
                 const int nt = tile % n_tiles, an = (tile / n_tiles) % a_cnt, mt = 2 * (tile / (n_tiles * a_cnt)) + (int)rank;
@@ -608,10 +615,10 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                             const int kcol = kb * KBE, kk = kcol / ga.c, c0 = kcol - kk * ga.c;
                             const int mid = __ldg(ga.table + an * ga.kk_n + kk);
                             tma_load_3d(st, &map_a, c0, mid, mt * TC_BM, &bars.raw_full[s]);
-                            tma_load_3d(st + Cfg::A_BYTES, &map_a2, c0, mid, mt * TC_BM, &bars.raw_full[s]);
+                            if (!fast) tma_load_3d(st + Cfg::A_BYTES, &map_a2, c0, mid, mt * TC_BM, &bars.raw_full[s]);
                         } else {
                             tma_load_2d(st, &map_a, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
-                            tma_load_2d(st + Cfg::A_BYTES, &map_a2, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
+                            if (!fast) tma_load_2d(st + Cfg::A_BYTES, &map_a2, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
                         }
                     } else if (ga.anchors > 0) {
                         const int kcol = kb * KBE, kk = kcol / ga.c, c0 = kcol - kk * ga.c;
@@ -623,7 +630,7 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                         tma_load_2d(st + Cfg::A_BYTES, &map_a, kb * KBE + 32, mt * TC_BM, &bars.raw_full[s]);
                     }
                     tma_load_2d(st + 2 * Cfg::A_BYTES, &map_bhi, kb * KBE, brow, &bars.raw_full[s]);
-                    tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::BH_BYTES, &map_blo, kb * KBE, brow, &bars.raw_full[s]);
+                    if (!fast) tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::BH_BYTES, &map_blo, kb * KBE, brow, &bars.raw_full[s]);
                 }
             }
         }
@@ -743,7 +750,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
                   const __grid_constant__ CUtensorMap map_q2, int Pw, int Qw,
                   float* __restrict__ C, int ldc, int64_t R, int64_t rows_per_split, int splits, int passes, int chunk_kb,
-                  TcGather ga, int anchors_per_item, const __grid_constant__ CUtensorMap map_p2) {
+                  TcGather ga, int anchors_per_item, const __grid_constant__ CUtensorMap map_p2, int fast) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr uint32_t MN_LBO = BF ? 8192 : 4096, K_SBO = BF ? 1024 : 512, L32 = BF ? 2 : 1;
@@ -887,7 +894,9 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
                             const uint64_t dp_hi = make_smem_desc(p_hi + koff, MN_LBO, K_SBO, L32);
                             const uint64_t dq_hi = make_smem_desc(q_hi + koff, MN_LBO, K_SBO, L32);
                             const uint32_t first = ((kb - kb0) | ks) != 0;
-                            if (BF) {
+                            if (BF && fast) {
+                                umma_bf16(d_tmem, dp_hi, dq_hi, idesc, first);
+                            } else if (BF) {
                                 const uint64_t dp_lo = make_smem_desc(p_lo + koff, MN_LBO, K_SBO, L32);
                                 const uint64_t dq_lo = make_smem_desc(q_lo + koff, MN_LBO, K_SBO, L32);
                                 umma_bf16(d_tmem, dp_lo, dq_hi, idesc, first);
@@ -917,7 +926,9 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
             tma_prefetch_desc(&map_p);
             tma_prefetch_desc(&map_q);
             if (BF) tma_prefetch_desc(&map_q2);
-            const uint32_t tx = ((uint32_t)Cfg::A_BYTES + (uint32_t)Cfg::B_BYTES) * (BF ? 2u : 1u);
+            // fast (bf16 single pass): the lo planes of Q, and of P when it arrives as planes, are not loaded
+            const uint32_t tx = BF ? ((PRE && fast) ? 1u : 2u) * (uint32_t)Cfg::A_BYTES + (fast ? 1u : 2u) * (uint32_t)Cfg::B_BYTES
+                                   : (uint32_t)Cfg::A_BYTES + (uint32_t)Cfg::B_BYTES;
             constexpr uint32_t BOX_BYTES = BF ? 8192 : 4096;
             int it = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -944,7 +955,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
                                 const int c0 = cc < Pw ? cc - kk * ga.c : ga.c;                 // out of bounds: zeros
                                 const int mid = cc < Pw ? __ldg(ga.table + an * ga.kk_n + kk) : 0;
                                 tma_load_3d(st + a * 8192, &map_p, c0, mid, row, &bars.raw_full[s]);
-                                tma_load_3d(st + Cfg::A_BYTES + a * 8192, &map_p2, c0, mid, row, &bars.raw_full[s]);
+                                if (!fast) tma_load_3d(st + Cfg::A_BYTES + a * 8192, &map_p2, c0, mid, row, &bars.raw_full[s]);
                             }
                         } else
 #pragma unroll
@@ -961,7 +972,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
 #pragma unroll
                             for (int a = 0; a < BN / 64; ++a) {
                                 tma_load_3d(st + 2 * Cfg::A_BYTES + a * 8192, &map_q, q0 + a * 64, an, row, &bars.raw_full[s]);
-                                tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + a * 8192, &map_q2, q0 + a * 64, an, row, &bars.raw_full[s]);
+                                if (!fast) tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + a * 8192, &map_q2, q0 + a * 64, an, row, &bars.raw_full[s]);
                             }
                         } else {
 #pragma unroll
@@ -974,7 +985,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
 #pragma unroll
                         for (int a = 0; a < TC_BM / 64; ++a) {
                             tma_load_2d(st + a * 8192, &map_p, p0 + a * 64, row, &bars.raw_full[s]);
-                            tma_load_2d(st + Cfg::A_BYTES + a * 8192, &map_p2, p0 + a * 64, row, &bars.raw_full[s]);
+                            if (!fast) tma_load_2d(st + Cfg::A_BYTES + a * 8192, &map_p2, p0 + a * 64, row, &bars.raw_full[s]);
                         }
                     } else
 #pragma unroll
@@ -984,7 +995,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
 #pragma unroll
                         for (int a = 0; a < BN / 64; ++a) {   // bf16 hi / lo atoms of 64 columns, final layout
                             tma_load_2d(st + 2 * Cfg::A_BYTES + a * 8192, &map_q, q0 + a * 64, row, &bars.raw_full[s]);
-                            tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + a * 8192, &map_q2, q0 + a * 64, row, &bars.raw_full[s]);
+                            if (!fast) tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + a * 8192, &map_q2, q0 + a * 64, row, &bars.raw_full[s]);
                         }
                     } else {
 #pragma unroll
@@ -1027,7 +1038,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
                        const __grid_constant__ CUtensorMap map_q2, int Pw, int Qw, float* __restrict__ C, int ldc, int64_t R,
                        int64_t rows_per_split, int splits, int chunk_kb, TcGather ga, int anchors_per_item,
-                       const __grid_constant__ CUtensorMap map_p2) {
+                       const __grid_constant__ CUtensorMap map_p2, int fast) {
     using Cfg = TnPairCfg<BN_>;
     constexpr int STAGES = Cfg::STAGES, BN = Cfg::BN, KR = 64, UK = 16;
     constexpr uint32_t MN_LBO = 8192, K_SBO = 1024, KSTEP_BYTES = 2048;
@@ -1171,9 +1182,13 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
                             const uint64_t dp_lo = make_smem_desc(p_lo + koff, MN_LBO, K_SBO, 2);
                             const uint64_t dq_lo = make_smem_desc(q_lo + koff, MN_LBO, K_SBO, 2);
                             const uint32_t first = ((kb - kb0) | ks) != 0;
-                            umma_bf16_pair(d_tmem, dp_lo, dq_hi, idesc, first);
-                            umma_bf16_pair(d_tmem, dp_hi, dq_lo, idesc, 1);
-                            umma_bf16_pair(d_tmem, dp_hi, dq_hi, idesc, 1);
+                            if (fast) {
+                                umma_bf16_pair(d_tmem, dp_hi, dq_hi, idesc, first);
+                            } else {
+                                umma_bf16_pair(d_tmem, dp_lo, dq_hi, idesc, first);
+                                umma_bf16_pair(d_tmem, dp_hi, dq_lo, idesc, 1);
+                                umma_bf16_pair(d_tmem, dp_hi, dq_hi, idesc, 1);
+                            }
                         }
                         umma_commit_pair(&bars.empty[s]);
                     }
@@ -1189,7 +1204,7 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
             tma_prefetch_desc(&map_p);
             tma_prefetch_desc(&map_q);
             tma_prefetch_desc(&map_q2);
-            const uint32_t tx = 2u * (uint32_t)Cfg::A_BYTES + 2u * (uint32_t)Cfg::QH_BYTES;
+            const uint32_t tx = ((PRE && fast) ? 1u : 2u) * (uint32_t)Cfg::A_BYTES + (fast ? 1u : 2u) * (uint32_t)Cfg::QH_BYTES;
             int it = 0;
             for (int item = pair; item < items; item += npairs) {
                 const int tile = item % tiles;
@@ -1216,7 +1231,7 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
                                 const int c0 = cc < Pw ? cc - kk * ga.c : ga.c;                 // out of bounds: zeros
                                 const int mid = cc < Pw ? __ldg(ga.table + an * ga.kk_n + kk) : 0;
                                 tma_load_3d(st + a * 8192, &map_p, c0, mid, row, &bars.raw_full[s]);
-                                tma_load_3d(st + Cfg::A_BYTES + a * 8192, &map_p2, c0, mid, row, &bars.raw_full[s]);
+                                if (!fast) tma_load_3d(st + Cfg::A_BYTES + a * 8192, &map_p2, c0, mid, row, &bars.raw_full[s]);
                             }
                         } else
 #pragma unroll
@@ -1232,7 +1247,7 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
 #pragma unroll
                         for (int a = 0; a < BN / 128; ++a) {
                             tma_load_3d(sq + a * 8192, &map_q, q0 + a * 64, an, row, &bars.raw_full[s]);
-                            tma_load_3d(sq + Cfg::QH_BYTES + a * 8192, &map_q2, q0 + a * 64, an, row, &bars.raw_full[s]);
+                            if (!fast) tma_load_3d(sq + Cfg::QH_BYTES + a * 8192, &map_q2, q0 + a * 64, an, row, &bars.raw_full[s]);
                         }
                         continue;
                     }
@@ -1240,7 +1255,7 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
 #pragma unroll
                         for (int a = 0; a < TC_BM / 64; ++a) {
                             tma_load_2d(st + a * 8192, &map_p, p0 + a * 64, row, &bars.raw_full[s]);
-                            tma_load_2d(st + Cfg::A_BYTES + a * 8192, &map_p2, p0 + a * 64, row, &bars.raw_full[s]);
+                            if (!fast) tma_load_2d(st + Cfg::A_BYTES + a * 8192, &map_p2, p0 + a * 64, row, &bars.raw_full[s]);
                         }
                     } else
 #pragma unroll
@@ -1249,7 +1264,7 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
 #pragma unroll
                     for (int a = 0; a < BN / 128; ++a) {
                         tma_load_2d(sq + a * 8192, &map_q, q0 + a * 64, row, &bars.raw_full[s]);
-                        tma_load_2d(sq + Cfg::QH_BYTES + a * 8192, &map_q2, q0 + a * 64, row, &bars.raw_full[s]);
+                        if (!fast) tma_load_2d(sq + Cfg::QH_BYTES + a * 8192, &map_q2, q0 + a * 64, row, &bars.raw_full[s]);
                     }
                 }
             }
@@ -1366,7 +1381,8 @@ static int num_sms() {
     return n;
 }
 
-static int default_chunk(int passes, bool bf = false) {
+static int default_chunk(int passes, bool bf = false, bool fast = false) {
+    if (fast) return 16;   // one MMA per k-step and no fp32-parity claim: long chunks, few epilogue drains
     // k-blocks the tensor core accumulates in TMEM before the epilogue folds the chunk into registers (experiments:
     // VGTKB_CHUNK_KB).  Draining a 128 x 256 fp32 chunk costs about as much as the MMAs of one k-block, so the chunk
     // must span several k-blocks; the round-toward-zero drift grows with the MMAs per chunk (12 per k-block).
@@ -1403,14 +1419,14 @@ static int tc_gemm_nt_impl(int64_t M, int N, int K, const float* A, const float*
 // CTA-pair launch (bf16x3, N > 128): clusters of two CTAs, one pair per two SMs
 template <int BN_, bool PRE = false>
 static int launch_nt_pair(int64_t M, int N, int K, const void* A, const void* Bhi, const void* Blo, const float* bias, float* C,
-                          cudaStream_t st, TcGather ga, const void* A_lo = nullptr) {
+                          cudaStream_t st, TcGather ga, const void* A_lo = nullptr, int fast = 0) {
     using Cfg = PairCfg<BN_>;
     CUtensorMap ma, mhi, mlo, mc, ma2;
     int rc = ga.anchors > 0 ? make_map_3d(&ma, A, M, ga.anchors, ga.c, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B, PRE)
                             : make_map_2d(&ma, A, M, K, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B, PRE);
     if (rc) return rc;
     ma2 = ma;
-    if (PRE) {
+    if (PRE && A_lo != nullptr) {
         rc = ga.anchors > 0 ? make_map_3d(&ma2, A_lo, M, ga.anchors, ga.c, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B, true)
                             : make_map_2d(&ma2, A_lo, M, K, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B, true);
         if (rc) return rc;
@@ -1446,7 +1462,8 @@ static int launch_nt_pair(int64_t M, int N, int K, const void* A, const void* Bh
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VGTKB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mhi, mlo, mc, tma_out, bias, C, M, N, K, default_chunk(3, true), ga, ma2));
+    VGTKB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mhi, mlo, mc, tma_out, bias, C, M, N, K, default_chunk(3, true, fast != 0), ga, ma2,
+                                  fast));
     return check_launch("gemm_nt(tcgen05, cta pairs)");
 }
 
@@ -1474,6 +1491,8 @@ static int tc_gemm_nt_impl(int64_t M, int N, int K, const float* A, const float*
     float* owned = nullptr;
     const float* Bhi = B;
     const float* Blo = B;
+    const int fast = passes == 7;                 // 7 = bf16 single pass (mode 4)
+    if (fast) passes = 6;
     const bool bf = passes == 6 && K % 8 == 0;   // 6 = bf16x3 (needs 16-byte aligned bf16 rows)
     if (passes == 6) passes = 3;                  // K % 8 != 0: 3xTF32 instead
     if (passes == 3) {
@@ -1491,10 +1510,10 @@ static int tc_gemm_nt_impl(int64_t M, int N, int K, const float* A, const float*
     int rc;
     // CTA pairs (cta_group::2) are the default for the bf16x3 mode; VGTKB_CTA_PAIRS=0 selects the single-CTA kernels
     static const int use_pairs = getenv("VGTKB_CTA_PAIRS") ? atoi(getenv("VGTKB_CTA_PAIRS")) : 1;
-    if (bf && use_pairs) {
-        if (N <= 64) rc = launch_nt_pair<64>(M, N, K, A, Bhi, Blo, bias, C, st, ga);
-        else if (N <= 128) rc = launch_nt_pair<128>(M, N, K, A, Bhi, Blo, bias, C, st, ga);
-        else rc = launch_nt_pair<256>(M, N, K, A, Bhi, Blo, bias, C, st, ga);
+    if (bf && (use_pairs || fast)) {
+        if (N <= 64) rc = launch_nt_pair<64>(M, N, K, A, Bhi, Blo, bias, C, st, ga, nullptr, fast);
+        else if (N <= 128) rc = launch_nt_pair<128>(M, N, K, A, Bhi, Blo, bias, C, st, ga, nullptr, fast);
+        else rc = launch_nt_pair<256>(M, N, K, A, Bhi, Blo, bias, C, st, ga, nullptr, fast);
     } else if (bf) {
         if (N <= 64) rc = launch_nt<64, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st, ga);
         else if (N <= 128) rc = launch_nt<128, true>(M, N, K, A, Bhi, Blo, bias, C, passes, st, ga);
@@ -1508,7 +1527,7 @@ static int tc_gemm_nt_impl(int64_t M, int N, int K, const float* A, const float*
 
 template <int BN, bool BF, bool PRE = false>
 static int launch_tn(const void* P, int Pw, const void* Q, const void* Q2, int Qw, float* C, int ldc, int64_t R, int passes,
-                     cudaStream_t st, TcGather ga = TcGather{0, 0, 0, nullptr}, const void* P_lo = nullptr) {
+                     cudaStream_t st, TcGather ga = TcGather{0, 0, 0, nullptr}, const void* P_lo = nullptr, int fast = 0) {
     using Cfg = TcCfg<BN>;
     constexpr int KR = BF ? 64 : TC_BK;
     CUtensorMap mp, mq, mq2, mp2;
@@ -1517,7 +1536,7 @@ static int launch_tn(const void* P, int Pw, const void* Q, const void* Q2, int Q
     if (ga.anchors > 0) {   // R = points; P = X [points, anchors, c]; Q = Y [points, anchors, Qw]
         rc = make_map_3d(&mp, P, R, ga.anchors, ga.c, KR, swz, PRE);
         if (rc) return rc;
-        if (PRE) {
+        if (PRE && P_lo != nullptr) {
             rc = make_map_3d(&mp2, P_lo, R, ga.anchors, ga.c, KR, swz, true);
             if (rc) return rc;
         }
@@ -1528,7 +1547,7 @@ static int launch_tn(const void* P, int Pw, const void* Q, const void* Q2, int Q
     } else {
         rc = make_map_2d(&mp, P, R, Pw, KR, swz, PRE);
         if (rc) return rc;
-        if (PRE) {
+        if (PRE && P_lo != nullptr) {
             rc = make_map_2d(&mp2, P_lo, R, Pw, KR, swz, true);
             if (rc) return rc;
         }
@@ -1553,19 +1572,19 @@ static int launch_tn(const void* P, int Pw, const void* Q, const void* Q2, int Q
     splits = ceil_div64(R, rps);
     const int64_t items = splits * tiles * n_groups;
     const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024;
-    if (!PRE) mp2 = mp;
+    if (!PRE || P_lo == nullptr) mp2 = mp;
     auto kern = tc_gemm_tn_kernel<BN, BF, PRE>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)(items < num_sms() ? items : num_sms());
-    kern<<<grid, TC_THREADS, smem, st>>>(mp, mq, mq2, Pw, Qw, C, ldc, R, rps, (int)splits, passes, default_chunk(passes, BF),
-                                         ga, ag, mp2);
+    kern<<<grid, TC_THREADS, smem, st>>>(mp, mq, mq2, Pw, Qw, C, ldc, R, rps, (int)splits, passes, default_chunk(passes, BF, fast != 0),
+                                         ga, ag, mp2, fast);
     return check_launch("gemm_tn(tcgen05)");
 }
 
 // CTA-pair launch of the bf16x3 weight-gradient kernel (Q tile 128 or 256)
 template <int BN_, bool PRE = false>
 static int launch_tn_pair(const void* P, int Pw, const void* Q, const void* Q2, int Qw, float* C, int ldc, int64_t R,
-                          cudaStream_t st, TcGather ga = TcGather{0, 0, 0, nullptr}, const void* P_lo = nullptr) {
+                          cudaStream_t st, TcGather ga = TcGather{0, 0, 0, nullptr}, const void* P_lo = nullptr, int fast = 0) {
     using Cfg = TnPairCfg<BN_>;
     constexpr int KR = 64;
     CUtensorMap mp, mq, mq2, mp2;
@@ -1574,7 +1593,7 @@ static int launch_tn_pair(const void* P, int Pw, const void* Q, const void* Q2, 
     if (ga.anchors > 0) {
         rc = make_map_3d(&mp, P, R, ga.anchors, ga.c, KR, swz, PRE);
         if (rc) return rc;
-        if (PRE) {
+        if (PRE && P_lo != nullptr) {
             rc = make_map_3d(&mp2, P_lo, R, ga.anchors, ga.c, KR, swz, true);
             if (rc) return rc;
         }
@@ -1585,7 +1604,7 @@ static int launch_tn_pair(const void* P, int Pw, const void* Q, const void* Q2, 
     } else {
         rc = make_map_2d(&mp, P, R, Pw, KR, swz, PRE);
         if (rc) return rc;
-        if (PRE) {
+        if (PRE && P_lo != nullptr) {
             rc = make_map_2d(&mp2, P_lo, R, Pw, KR, swz, true);
             if (rc) return rc;
         }
@@ -1611,7 +1630,7 @@ static int launch_tn_pair(const void* P, int Pw, const void* Q, const void* Q2, 
     splits = ceil_div64(R, rps);
     const int64_t items = splits * tiles * n_groups;
     const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024;
-    if (!PRE) mp2 = mp;
+    if (!PRE || P_lo == nullptr) mp2 = mp;
     auto kern = tc_gemm_tn_pair_kernel<BN_, PRE>;
     VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int pairs = (int)(items < max_pairs ? items : max_pairs);
@@ -1627,7 +1646,8 @@ static int launch_tn_pair(const void* P, int Pw, const void* Q, const void* Q2, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VGTKB_CUDA(cudaLaunchKernelEx(&cfg, kern, mp, mq, mq2, Pw, Qw, C, ldc, R, rps, (int)splits, default_chunk(3, true), ga, ag, mp2));
+    VGTKB_CUDA(cudaLaunchKernelEx(&cfg, kern, mp, mq, mq2, Pw, Qw, C, ldc, R, rps, (int)splits, default_chunk(3, true, fast != 0), ga, ag,
+                                  mp2, fast));
     return check_launch("gemm_tn(tcgen05, cta pairs)");
 }
 
@@ -1645,20 +1665,24 @@ int tc_gemm_tn(int M, int N, int64_t R, const float* A, const float* B, float* C
         ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) != 0)
         return VGTKB_EUNSUP;
     if ((int64_t)M * N < 64 * 64 / 4) return VGTKB_EUNSUP;   // tiny outputs: the FFMA split-R kernel is fine
+    const int fast = passes == 7;                             // 7 = bf16 single pass (mode 4)
+    if (fast) passes = 6;
     if (passes == 6 && (M % 8 != 0 || workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0))
         passes = 3;                                           // bf16 rows must be 16-byte aligned: 3xTF32 instead
     if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
-    if (passes == 6) {   // bf16x3
+    if (passes == 6) {   // bf16x3 / bf16
         const int64_t na = R * (int64_t)M;
         uint16_t* hi = reinterpret_cast<uint16_t*>(workspace);
         uint16_t* lo = hi + na;
         const int blocks = (int)(ceil_div64(na, 256) < 2368 ? ceil_div64(na, 256) : 2368);
         split_bf16_kernel<<<blocks, 256, 0, st>>>(na, A, hi, lo);
-        if (M <= 64) return launch_tn<64, true>(B, N, hi, lo, M, C, N, R, 3, st);
+        const TcGather none{0, 0, 0, nullptr};
+        if (M <= 64) return launch_tn<64, true>(B, N, hi, lo, M, C, N, R, 3, st, none, nullptr, fast);
         if (tn_pairs_enabled() && N > TC_BM)
-            return M <= 128 ? launch_tn_pair<128>(B, N, hi, lo, M, C, N, R, st) : launch_tn_pair<256>(B, N, hi, lo, M, C, N, R, st);
-        if (M <= 128) return launch_tn<128, true>(B, N, hi, lo, M, C, N, R, 3, st);
-        return launch_tn<256, true>(B, N, hi, lo, M, C, N, R, 3, st);
+            return M <= 128 ? launch_tn_pair<128>(B, N, hi, lo, M, C, N, R, st, none, nullptr, fast)
+                            : launch_tn_pair<256>(B, N, hi, lo, M, C, N, R, st, none, nullptr, fast);
+        if (M <= 128) return launch_tn<128, true>(B, N, hi, lo, M, C, N, R, 3, st, none, nullptr, fast);
+        return launch_tn<256, true>(B, N, hi, lo, M, C, N, R, 3, st, none, nullptr, fast);
     }
     if (M <= 64) return launch_tn<64, false>(B, N, A, A, M, C, N, R, passes, st);
     if (M <= 128) return launch_tn<128, false>(B, N, A, A, M, C, N, R, passes, st);
@@ -1673,6 +1697,8 @@ int tc_gemm_tn_gather(int64_t points, int anchors, int kk_n, int c_n, int M, con
     if (c_n % 32 != 0 || M % 4 != 0 || points < 64 || points >= ((int64_t)1 << 31) ||
         ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) != 0)
         return VGTKB_EUNSUP;
+    const int fast = passes == 7;
+    if (fast) passes = 6;
     if (passes == 6 && (M % 8 != 0 || workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0)) passes = 3;
     if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
     const TcGather ga{anchors, kk_n, c_n, table};
@@ -1682,12 +1708,12 @@ int tc_gemm_tn_gather(int64_t points, int anchors, int kk_n, int c_n, int M, con
         uint16_t* lo = hi + na;
         const int blocks = (int)(ceil_div64(na, 256) < 2368 ? ceil_div64(na, 256) : 2368);
         split_bf16_kernel<<<blocks, 256, 0, st>>>(na, Y, hi, lo);
-        if (M <= 64) return launch_tn<64, true>(X, N, hi, lo, M, C, N, points, 3, st, ga);
+        if (M <= 64) return launch_tn<64, true>(X, N, hi, lo, M, C, N, points, 3, st, ga, nullptr, fast);
         if (tn_pairs_enabled() && N > TC_BM)
-            return M <= 128 ? launch_tn_pair<128>(X, N, hi, lo, M, C, N, points, st, ga)
-                            : launch_tn_pair<256>(X, N, hi, lo, M, C, N, points, st, ga);
-        if (M <= 128) return launch_tn<128, true>(X, N, hi, lo, M, C, N, points, 3, st, ga);
-        return launch_tn<256, true>(X, N, hi, lo, M, C, N, points, 3, st, ga);
+            return M <= 128 ? launch_tn_pair<128>(X, N, hi, lo, M, C, N, points, st, ga, nullptr, fast)
+                            : launch_tn_pair<256>(X, N, hi, lo, M, C, N, points, st, ga, nullptr, fast);
+        if (M <= 128) return launch_tn<128, true>(X, N, hi, lo, M, C, N, points, 3, st, ga, nullptr, fast);
+        return launch_tn<256, true>(X, N, hi, lo, M, C, N, points, 3, st, ga, nullptr, fast);
     }
     if (M <= 64) return launch_tn<64, false>(X, N, Y, Y, M, C, N, points, passes, st, ga);
     if (M <= 128) return launch_tn<128, false>(X, N, Y, Y, M, C, N, points, passes, st, ga);
@@ -1714,8 +1740,9 @@ namespace vgtkb {
 // C[M,N] = (a_hi + a_lo)[M,K] * B[N,K]^T (+ bias); workspace: N*K floats (bf16 hi/lo split of B).  VGTKB_EUNSUP for
 // shapes the CTA-pair kernel does not take.
 int tc_gemm_nt_planes(int64_t M, int N, int K, const void* a_hi, const void* a_lo, const float* B, const float* bias, float* C,
-                      float* workspace, cudaStream_t st) {
-    if (M < 1 || N < 1 || K < 64 || K % 8 != 0 || M >= ((int64_t)1 << 31) || workspace == nullptr ||
+                      float* workspace, cudaStream_t st, int fast) {
+    if (M < 1 || N < 1 || K < 64 || K % 8 != 0 || M >= ((int64_t)1 << 31) || workspace == nullptr || a_hi == nullptr ||
+        (a_lo == nullptr && !fast) ||
         ((reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) | reinterpret_cast<uintptr_t>(B) |
           reinterpret_cast<uintptr_t>(workspace)) & 15) != 0)
         return VGTKB_EUNSUP;
@@ -1725,15 +1752,15 @@ int tc_gemm_nt_planes(int64_t M, int N, int K, const void* a_hi, const void* a_l
     uint16_t* blo = bhi + nb;
     split_bf16_kernel<<<blocks, 256, 0, st>>>(nb, B, bhi, blo);
     const TcGather none{0, 0, 0, nullptr};
-    if (N <= 64) return launch_nt_pair<64, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo);
-    if (N <= 128) return launch_nt_pair<128, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo);
-    return launch_nt_pair<256, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo);
+    if (N <= 64) return launch_nt_pair<64, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo, fast);
+    if (N <= 128) return launch_nt_pair<128, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo, fast);
+    return launch_nt_pair<256, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo, fast);
 }
 
 // split `n` floats into bf16 hi / lo planes at the start of `workspace` unless the planes are given
 static int planes_or_split(const float* x, const void* x_hi, const void* x_lo, int64_t n, float* workspace, const void** hi,
-                           const void** lo, cudaStream_t st) {
-    if (x_hi != nullptr && x_lo != nullptr) {
+                           const void** lo, cudaStream_t st, int fast = 0) {
+    if (x_hi != nullptr && (x_lo != nullptr || fast)) {
         *hi = x_hi;
         *lo = x_lo;
         return VGTKB_OK;
@@ -1751,31 +1778,33 @@ static int planes_or_split(const float* x, const void* x_hi, const void* x_lo, i
 // C[M,N] (+)= A[R,M]^T * B[R,N]; the narrow operand A as planes (a_hi / a_lo) or fp32 (split into workspace: R*M floats);
 // the wide operand B as planes (b_hi / b_lo: pure TMA -> MMA stream) or fp32 (B: converted in the kernel)
 int tc_gemm_tn_planes(int M, int N, int64_t R, const float* A, const void* a_hi, const void* a_lo, const float* B,
-                      const void* b_hi, const void* b_lo, float* C, int accumulate, float* workspace, cudaStream_t st) {
-    const bool bpl = b_hi != nullptr && b_lo != nullptr;
-    if (M < 8 || M % 8 != 0 || M > 256 || N < 64 || N % 8 != 0 || R < 64 || R >= ((int64_t)1 << 31) ||
+                      const void* b_hi, const void* b_lo, float* C, int accumulate, float* workspace, cudaStream_t st, int fast) {
+    const bool bpl = b_hi != nullptr && (b_lo != nullptr || fast);
+    if (M < 8 || M % 8 != 0 || N < 64 || N % 8 != 0 || R < 64 || R >= ((int64_t)1 << 31) ||
         ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) |
           reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo)) & 15) != 0 ||
         (!bpl && B == nullptr))
         return VGTKB_EUNSUP;
     const void *hi, *lo;
-    const int rc = planes_or_split(A, a_hi, a_lo, R * (int64_t)M, workspace, &hi, &lo, st);
+    const int rc = planes_or_split(A, a_hi, a_lo, R * (int64_t)M, workspace, &hi, &lo, st, fast);
     if (rc) return rc;
+    if (lo == nullptr) lo = hi;                       // fast: never loaded, only a valid tensor map is needed
     if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
     const TcGather none{0, 0, 0, nullptr};
     if (bpl) {
-        if (M <= 64) return launch_tn<64, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
+        if (M <= 64) return launch_tn<64, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo, fast);
         if (N > TC_BM)
-            return M <= 128 ? launch_tn_pair<128, true>(b_hi, N, hi, lo, M, C, N, R, st, none, b_lo)
-                            : launch_tn_pair<256, true>(b_hi, N, hi, lo, M, C, N, R, st, none, b_lo);
-        if (M <= 128) return launch_tn<128, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
-        return launch_tn<256, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo);
+            return M <= 128 ? launch_tn_pair<128, true>(b_hi, N, hi, lo, M, C, N, R, st, none, b_lo, fast)
+                            : launch_tn_pair<256, true>(b_hi, N, hi, lo, M, C, N, R, st, none, b_lo, fast);
+        if (M <= 128) return launch_tn<128, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo, fast);
+        return launch_tn<256, true, true>(b_hi, N, hi, lo, M, C, N, R, 3, st, none, b_lo, fast);
     }
-    if (M <= 64) return launch_tn<64, true>(B, N, hi, lo, M, C, N, R, 3, st);
+    if (M <= 64) return launch_tn<64, true>(B, N, hi, lo, M, C, N, R, 3, st, none, nullptr, fast);
     if (tn_pairs_enabled() && N > TC_BM)
-        return M <= 128 ? launch_tn_pair<128>(B, N, hi, lo, M, C, N, R, st) : launch_tn_pair<256>(B, N, hi, lo, M, C, N, R, st);
-    if (M <= 128) return launch_tn<128, true>(B, N, hi, lo, M, C, N, R, 3, st);
-    return launch_tn<256, true>(B, N, hi, lo, M, C, N, R, 3, st);
+        return M <= 128 ? launch_tn_pair<128>(B, N, hi, lo, M, C, N, R, st, none, nullptr, fast)
+                        : launch_tn_pair<256>(B, N, hi, lo, M, C, N, R, st, none, nullptr, fast);
+    if (M <= 128) return launch_tn<128, true>(B, N, hi, lo, M, C, N, R, 3, st, none, nullptr, fast);
+    return launch_tn<256, true>(B, N, hi, lo, M, C, N, R, 3, st, none, nullptr, fast);
 }
 
 // gather-GEMM (intra conv) with the activation operand X [points, anchors, c_n] as bf16 planes; workspace: N*kk_n*c_n floats
@@ -1803,7 +1832,7 @@ int tc_gemm_tn_gather_planes(int64_t points, int anchors, int kk_n, int c_n, int
                              const void* x_lo, const float* Y, const void* y_hi, const void* y_lo, float* C, int accumulate,
                              float* workspace, cudaStream_t st) {
     const int N = kk_n * c_n;
-    if (c_n % 64 != 0 || M % 8 != 0 || M < 8 || M > 256 || points < 64 || points >= ((int64_t)1 << 31) ||
+    if (c_n % 64 != 0 || M % 8 != 0 || M < 8 || points < 64 || points >= ((int64_t)1 << 31) ||
         ((reinterpret_cast<uintptr_t>(x_hi) | reinterpret_cast<uintptr_t>(x_lo) | reinterpret_cast<uintptr_t>(Y) |
           reinterpret_cast<uintptr_t>(y_hi) | reinterpret_cast<uintptr_t>(y_lo)) & 15) != 0)
         return VGTKB_EUNSUP;
@@ -1825,7 +1854,7 @@ extern "C" int vgtkb_gemm_nt_presplit(int64_t M, int N, int K, const void* a_hi,
                                       const float* bias, float* C, float* workspace, void* stream) {
     using namespace vgtkb;
     VGTKB_REQUIRE(M >= 1 && N >= 1 && K >= 64, "gemm_nt_presplit: bad size");
-    const int rc = tc_gemm_nt_planes(M, N, K, a_hi, a_lo, B, bias, C, workspace, (cudaStream_t)stream);
+    const int rc = tc_gemm_nt_planes(M, N, K, a_hi, a_lo, B, bias, C, workspace, (cudaStream_t)stream, 0);
     if (rc == VGTKB_EUNSUP)
         set_error("gemm_nt_presplit: needs K %% 8 == 0, M < 2^31, 16-byte aligned operands and a workspace of N*K floats");
     return rc;
@@ -1841,9 +1870,9 @@ extern "C" int vgtkb_gemm_tn_presplit(int M, int N, int64_t R, const float* A, c
 extern "C" int vgtkb_gemm_tn_planes(int M, int N, int64_t R, const float* A, const void* a_hi, const void* a_lo, const float* B,
                                     const void* b_hi, const void* b_lo, float* C, int accumulate, float* workspace, void* stream) {
     using namespace vgtkb;
-    const int rc = tc_gemm_tn_planes(M, N, R, A, a_hi, a_lo, B, b_hi, b_lo, C, accumulate, workspace, (cudaStream_t)stream);
+    const int rc = tc_gemm_tn_planes(M, N, R, A, a_hi, a_lo, B, b_hi, b_lo, C, accumulate, workspace, (cudaStream_t)stream, 0);
     if (rc == VGTKB_EUNSUP)
-        set_error("gemm_tn_planes: needs M %% 8 == 0, 8 <= M <= 256, N %% 8 == 0, N >= 64, R >= 64, 16-byte aligned operands, "
+        set_error("gemm_tn_planes: needs M %% 8 == 0, M >= 8, N %% 8 == 0, N >= 64, R >= 64, 16-byte aligned operands, "
                   "and either planes or fp32 + a workspace of R*M floats for the narrow operand");
     return rc;
 }
@@ -1868,6 +1897,6 @@ extern "C" int vgtkb_gather_gemm_tn_planes(int64_t points, int anchors, int kk, 
     const int rc = tc_gemm_tn_gather_planes(points, anchors, kk, c, m, table, x_hi, x_lo, y, y_hi, y_lo, out, accumulate, workspace,
                                             (cudaStream_t)stream);
     if (rc == VGTKB_EUNSUP)
-        set_error("gather_gemm_tn_planes: unsupported shape (needs c %% 64 == 0, m %% 8 == 0, m <= 256, points >= 64, aligned operands)");
+        set_error("gather_gemm_tn_planes: unsupported shape (needs c %% 64 == 0, m %% 8 == 0, points >= 64, aligned operands)");
     return rc;
 }

@@ -1067,6 +1067,302 @@ inter_group_bwd_mma_tl_kernel(const __grid_constant__ TmaMap map_dg, int n, int 
     }
 }
 
+// ---------------------------------------------------------------------------------- general warp-MMA variants
+// KS = 1..4 k-steps of 16 neighbours (nn <= 64: model 38 builds every layer with 64 neighbours,
+// SPConvNets/models/unsup_seg_so3_pose_conv_pn_38_multi_stage.py:2174-2191) and FAST = single-pass bf16 (contraction mode
+// 4, BASELINE config 3: operands rounded to bf16 once, one MMA per product instead of three, G leaves as ONE bf16 plane).
+// Same fragment scheme as inter_group_fwd_mma_ts_kernel / inter_group_bwd_mma_tl_kernel, written for register economy
+// instead of prefetch depth: the weight fragments of the anchor stay in registers (KS x 6 words per plane), the neighbour
+// offsets are re-read from shared memory while the weights are computed, and the feature fragments of one k-step live
+// only until its MMAs are issued.  The tuned kernels above keep the KS <= 2, fp32-parity shapes of the classic backbone.
+template <int KS, bool FAST>
+__global__ void __launch_bounds__(IG_WARPS * 32, KS <= 2 ? 2 : 1)
+inter_group_fwd_mma_gen_kernel(const __grid_constant__ TmaMap map_hi, const __grid_constant__ TmaMap map_lo, int n, int p, int nn,
+                               int a, int k, int ci, const float* __restrict__ xyz, const float* __restrict__ sxyz,
+                               const int32_t* __restrict__ idx, const float* __restrict__ rk, float inv_sigma,
+                               const float* __restrict__ feats) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ float s_g[16 * KS * 3];
+    __shared__ uint32_t s_off[16 * KS];
+    const int pi = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    // per warp: two staging buffers, each hi tile [24][64 B] + lo tile [24][64 B]
+    unsigned char* stage = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) + warp * (2 * 24 * 128);
+    igt_neighbourhood<KS>(b, pi, n, p, nn, a, ci, xyz, sxyz, idx, s_g, s_off);
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_hi);
+        if (!FAST) tma_prefetch_desc(&map_lo);
+    }
+    __syncthreads();
+    uint32_t off[KS][4];
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) off[s][j] = s_off[16 * s + 2 * tig + (j & 1) + 8 * (j >> 1)];
+    const float* fb = feats + (size_t)b * n * a * ci + 4 * gid;
+    int sb = 0;
+    for (int ai = warp; ai < a; ai += IG_WARPS) {
+        uint32_t bh[KS][3][2], bl[FAST ? 1 : KS][3][2];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int kp = 8 * t + gid;
+            const bool live = kp < k;
+            float kx = 0.f, ky = 0.f, kz = 0.f;
+            if (live) {
+                const float* q = rk + (ai * k + kp) * 3;
+                kx = __ldg(q);
+                ky = __ldg(q + 1);
+                kz = __ldg(q + 2);
+            }
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                float w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ni = 16 * s + 2 * tig + (j & 1) + 8 * (j >> 1);
+                    const float dx = s_g[ni * 3] - kx, dy = s_g[ni * 3 + 1] - ky, dz = s_g[ni * 3 + 2] - kz;
+                    const float v = fmaxf(0.f, 1.f - (dx * dx + dy * dy + dz * dz) * inv_sigma);
+                    w[j] = live ? v : 0.f;
+                }
+                if (FAST) {
+                    bh[s][t][0] = ig_pack_bf16x2(w[0], w[1]);
+                    bh[s][t][1] = ig_pack_bf16x2(w[2], w[3]);
+                } else {
+                    ig_split2(w[0], w[1], bh[s][t][0], bl[s][t][0]);
+                    ig_split2(w[2], w[3], bh[s][t][1], bl[s][t][1]);
+                }
+            }
+        }
+        const int row0 = (((b * p + pi) * a) + ai) * k;
+        const float* fa = fb + (size_t)ai * ci;
+        for (int c0 = 0; c0 < ci; c0 += 32, sb ^= 1) {
+            float d[2][3][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) d[m][t][e] = 0.f;
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                float4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(fa + off[s][j] + c0));
+                uint32_t ah[2][4], al[2][4];
+                if (FAST) {
+                    ah[0][0] = ig_pack_bf16x2(v[0].x, v[1].x);
+                    ah[0][1] = ig_pack_bf16x2(v[0].y, v[1].y);
+                    ah[0][2] = ig_pack_bf16x2(v[2].x, v[3].x);
+                    ah[0][3] = ig_pack_bf16x2(v[2].y, v[3].y);
+                    ah[1][0] = ig_pack_bf16x2(v[0].z, v[1].z);
+                    ah[1][1] = ig_pack_bf16x2(v[0].w, v[1].w);
+                    ah[1][2] = ig_pack_bf16x2(v[2].z, v[3].z);
+                    ah[1][3] = ig_pack_bf16x2(v[2].w, v[3].w);
+                } else {
+                    ig_split2(v[0].x, v[1].x, ah[0][0], al[0][0]);
+                    ig_split2(v[0].y, v[1].y, ah[0][1], al[0][1]);
+                    ig_split2(v[2].x, v[3].x, ah[0][2], al[0][2]);
+                    ig_split2(v[2].y, v[3].y, ah[0][3], al[0][3]);
+                    ig_split2(v[0].z, v[1].z, ah[1][0], al[1][0]);
+                    ig_split2(v[0].w, v[1].w, ah[1][1], al[1][1]);
+                    ig_split2(v[2].z, v[3].z, ah[1][2], al[1][2]);
+                    ig_split2(v[2].w, v[3].w, ah[1][3], al[1][3]);
+                }
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        if (!FAST) {
+                            ig_mma(d[m][t], al[m], bh[s][t][0], bh[s][t][1]);
+                            ig_mma(d[m][t], ah[m], bl[s][t][0], bl[s][t][1]);
+                        }
+                        ig_mma(d[m][t], ah[m], bh[s][t][0], bh[s][t][1]);
+                    }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+            const uint32_t sh = smem_u32(stage + sb * (24 * 128)), sl = sh + 24 * 64;
+            const int flip = tig >> 1;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int kp = 8 * t + 2 * tig;
+                uint32_t h[2][2], l[2][2];
+                if (FAST) {
+                    h[0][0] = ig_pack_bf16x2(d[0][t][0], d[0][t][2]);
+                    h[0][1] = ig_pack_bf16x2(d[1][t][0], d[1][t][2]);
+                    h[1][0] = ig_pack_bf16x2(d[0][t][1], d[0][t][3]);
+                    h[1][1] = ig_pack_bf16x2(d[1][t][1], d[1][t][3]);
+                } else {
+                    ig_split2(d[0][t][0], d[0][t][2], h[0][0], l[0][0]);
+                    ig_split2(d[1][t][0], d[1][t][2], h[0][1], l[0][1]);
+                    ig_split2(d[0][t][1], d[0][t][3], h[1][0], l[1][0]);
+                    ig_split2(d[1][t][1], d[1][t][3], h[1][1], l[1][1]);
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int par = q ^ flip;
+                    const uint32_t o = (uint32_t)((kp + par) * 64 + gid * 8);
+                    st_shared_u2(sh + o, par ? h[1][0] : h[0][0], par ? h[1][1] : h[0][1]);
+                    if (!FAST) st_shared_u2(sl + o, par ? l[1][0] : l[0][0], par ? l[1][1] : l[0][1]);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&map_hi, stage + sb * (24 * 128), c0, row0);
+                if (!FAST) tma_store_2d(&map_lo, stage + sb * (24 * 128) + 24 * 64, c0, row0);
+                bulk_commit();
+            }
+        }
+    }
+    if (lane == 0) bulk_wait_all();
+}
+
+template <int KS, bool FAST>
+__global__ void __launch_bounds__(IG_WARPS * 32, (KS <= 2 || FAST) ? 2 : 1)
+inter_group_bwd_mma_gen_kernel(const __grid_constant__ TmaMap map_dg, int n, int p, int nn, int a, int k, int ci,
+                               const float* __restrict__ xyz, const float* __restrict__ sxyz, const int32_t* __restrict__ idx,
+                               const float* __restrict__ rk, float inv_sigma, float* __restrict__ gfeats) {
+    constexpr int NT = 2 * KS;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ float s_g[16 * KS * 3];
+    __shared__ uint32_t s_off[16 * KS];
+    __shared__ __align__(8) uint64_t s_bar[IG_WARPS][2];
+    const int pi = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    float* stage = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)) + warp * (2 * 24 * 32);
+    igt_neighbourhood<KS>(b, pi, n, p, nn, a, ci, xyz, sxyz, idx, s_g, s_off);
+    for (int i = lane; i < 2 * 24 * 32; i += 32) stage[i] = 0.f;    // rows >= k are never loaded
+    if (lane == 0) {
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
+        fence_barrier_init();
+    }
+    if (threadIdx.x == 0) tma_prefetch_desc(&map_dg);
+    fence_proxy_async();
+    __syncthreads();
+    uint32_t off[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        off[t][0] = s_off[8 * t + 2 * tig];
+        off[t][1] = s_off[8 * t + 2 * tig + 1];
+    }
+    int kps[6];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) kps[j] = 2 * tig + (j & 1) + 8 * (j >> 1);
+    kps[4] = 16 + 2 * tig;
+    kps[5] = 17 + 2 * tig;
+    float* gb = gfeats + (size_t)b * n * a * ci + 4 * gid;
+    const int chunks = ci / 32;
+    const int my_anchors = (a - warp + IG_WARPS - 1) / IG_WARPS;
+    const int items = my_anchors * chunks;
+    auto issue = [&](int item) {
+        if (lane == 0) {
+            const int ai = warp + (item / chunks) * IG_WARPS, c0 = (item % chunks) * 32, buf = item & 1;
+            mbar_arrive_expect_tx(&s_bar[warp][buf], (uint32_t)k * 128u);
+            tma_load_2d(stage + buf * (24 * 32), &map_dg, c0, (((b * p + pi) * a) + ai) * k, &s_bar[warp][buf]);
+        }
+    };
+    if (items > 0) issue(0);
+    uint32_t bh[NT][3], bl[FAST ? 1 : NT][3];
+    for (int item = 0; item < items; ++item) {
+        const int ai = warp + (item / chunks) * IG_WARPS, c0 = (item % chunks) * 32, buf = item & 1;
+        __syncwarp();
+        if (item + 1 < items) issue(item + 1);
+        if (c0 == 0) {
+            float kx[6], ky[6], kz[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                kx[j] = ky[j] = kz[j] = 1e12f;
+                if (kps[j] < k) {
+                    const float* q = rk + (ai * k + kps[j]) * 3;
+                    kx[j] = __ldg(q);
+                    ky[j] = __ldg(q + 1);
+                    kz[j] = __ldg(q + 2);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const float gx = s_g[(8 * t + gid) * 3], gy = s_g[(8 * t + gid) * 3 + 1], gz = s_g[(8 * t + gid) * 3 + 2];
+                float w[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const float dx = gx - kx[j], dy = gy - ky[j], dz = gz - kz[j];
+                    const float v = fmaxf(0.f, 1.f - (dx * dx + dy * dy + dz * dz) * inv_sigma);
+                    w[j] = (kps[j] < k && 8 * t + gid < nn) ? v : 0.f;
+                }
+                if (FAST) {
+                    bh[t][0] = ig_pack_bf16x2(w[0], w[1]);
+                    bh[t][1] = ig_pack_bf16x2(w[2], w[3]);
+                    bh[t][2] = ig_pack_bf16x2(w[4], w[5]);
+                } else {
+                    ig_split2(w[0], w[1], bh[t][0], bl[t][0]);
+                    ig_split2(w[2], w[3], bh[t][1], bl[t][1]);
+                    ig_split2(w[4], w[5], bh[t][2], bl[t][2]);
+                }
+            }
+        }
+        mbar_wait(&s_bar[warp][buf], (uint32_t)(item >> 1) & 1u);
+        const float* in = stage + buf * (24 * 32);
+        float4 v[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v[j] = lds128(in + kps[j] * 32 + ((gid ^ (kps[j] & 7)) << 2));
+        uint32_t ah[2][6], al[2][6];
+        if (FAST) {
+            ah[0][0] = ig_pack_bf16x2(v[0].x, v[1].x);
+            ah[0][1] = ig_pack_bf16x2(v[0].y, v[1].y);
+            ah[0][2] = ig_pack_bf16x2(v[2].x, v[3].x);
+            ah[0][3] = ig_pack_bf16x2(v[2].y, v[3].y);
+            ah[0][4] = ig_pack_bf16x2(v[4].x, v[5].x);
+            ah[0][5] = ig_pack_bf16x2(v[4].y, v[5].y);
+            ah[1][0] = ig_pack_bf16x2(v[0].z, v[1].z);
+            ah[1][1] = ig_pack_bf16x2(v[0].w, v[1].w);
+            ah[1][2] = ig_pack_bf16x2(v[2].z, v[3].z);
+            ah[1][3] = ig_pack_bf16x2(v[2].w, v[3].w);
+            ah[1][4] = ig_pack_bf16x2(v[4].z, v[5].z);
+            ah[1][5] = ig_pack_bf16x2(v[4].w, v[5].w);
+        } else {
+            ig_split2(v[0].x, v[1].x, ah[0][0], al[0][0]);
+            ig_split2(v[0].y, v[1].y, ah[0][1], al[0][1]);
+            ig_split2(v[2].x, v[3].x, ah[0][2], al[0][2]);
+            ig_split2(v[2].y, v[3].y, ah[0][3], al[0][3]);
+            ig_split2(v[4].x, v[5].x, ah[0][4], al[0][4]);
+            ig_split2(v[4].y, v[5].y, ah[0][5], al[0][5]);
+            ig_split2(v[0].z, v[1].z, ah[1][0], al[1][0]);
+            ig_split2(v[0].w, v[1].w, ah[1][1], al[1][1]);
+            ig_split2(v[2].z, v[3].z, ah[1][2], al[1][2]);
+            ig_split2(v[2].w, v[3].w, ah[1][3], al[1][3]);
+            ig_split2(v[4].z, v[5].z, ah[1][4], al[1][4]);
+            ig_split2(v[4].w, v[5].w, ah[1][5], al[1][5]);
+        }
+        float* ga = gb + (size_t)ai * ci + c0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            float d[2][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) d[m][e] = 0.f;
+                const uint32_t h16[4] = {ah[m][0], ah[m][1], ah[m][2], ah[m][3]};
+                if (!FAST) {
+                    const uint32_t l16[4] = {al[m][0], al[m][1], al[m][2], al[m][3]};
+                    ig_mma(d[m], l16, bh[t][0], bh[t][1]);
+                    ig_mma(d[m], h16, bl[t][0], bl[t][1]);
+                    ig_mma_k8(d[m], al[m][4], al[m][5], bh[t][2]);
+                    ig_mma_k8(d[m], ah[m][4], ah[m][5], bl[t][2]);
+                }
+                ig_mma(d[m], h16, bh[t][0], bh[t][1]);
+                ig_mma_k8(d[m], ah[m][4], ah[m][5], bh[t][2]);
+            }
+            const int n0 = 8 * t + 2 * tig;
+            if (n0 < nn) atomicAdd(reinterpret_cast<float4*>(ga + off[t][0]), make_float4(d[0][0], d[0][2], d[1][0], d[1][2]));
+            if (n0 + 1 < nn) atomicAdd(reinterpret_cast<float4*>(ga + off[t][1]), make_float4(d[0][1], d[0][3], d[1][1], d[1][3]));
+        }
+    }
+}
+
 // backward of the fast path: dX[b, j_n, a, c] += sum_k w[n][k] dG[b,p,a,k,c]
 // (bound by the red.global.add traffic: the 16-byte vector atomics of CPL = 4 beat higher occupancy with
 // CPL = 2 -- measured 2.9 ms vs 3.4 ms per step)
@@ -1331,31 +1627,97 @@ static int launch_inter(bool fwd, int b, int n, int p, int nn, int a, int k, int
 }
 
 namespace vgtkb {
-// G as two bf16 planes [b*p*a, k*ci] (hi, lo): the forward grouping of vgtkb_inter_conv_forward.  VGTKB_EUNSUP for shapes
-// the warp-MMA kernel does not take (k > 24, nn > 32, ci % 32 != 0, misaligned / too large tensors).
+template <int KS, bool FAST>
+static int launch_group_fwd_gen(const TmaMap& mh, const TmaMap& ml, int b, int n, int p, int nn, int a, int k, int ci, const float* xyz,
+                                const float* sxyz, const int32_t* idx, const float* rk, float sigma, const float* feats,
+                                cudaStream_t st) {
+    const size_t smem = (size_t)IG_WARPS * 2 * 24 * 128 + 1024;
+    auto kern = inter_group_fwd_mma_gen_kernel<KS, FAST>;
+    VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(p, b), IG_WARPS * 32, smem, st>>>(mh, ml, n, p, nn, a, k, ci, xyz, sxyz, idx, rk, 1.0f / sigma, feats);
+    return check_launch("inter_group_forward(mma, general)");
+}
+
+// G as bf16 planes [b*p*a, k*ci]: hi and lo (fast = 0, the bf16x3 operand format) or hi only (fast = 1, single-pass bf16;
+// g_lo unused) -- the forward grouping of vgtkb_inter_conv_forward.  VGTKB_EUNSUP for shapes the warp-MMA kernels do not
+// take (k > 24, nn > 64, ci % 32 != 0, misaligned / too large tensors).
 int inter_group_forward_planes(int b, int n, int p, int nn, int a, int k, int ci, const float* xyz, const float* sample_xyz,
                                const int32_t* idx, const float* rot_kernels, float sigma, const float* feats, void* g_hi,
-                               void* g_lo, cudaStream_t st) {
+                               void* g_lo, int fast, cudaStream_t st) {
     const int64_t g_rows = (int64_t)b * p * a * k;
-    if (k > 24 || nn > 32 || ci % 32 != 0 || !aligned16(feats) || !aligned16(g_hi) || !aligned16(g_lo) ||
+    if (k > 24 || nn > 64 || ci % 32 != 0 || !aligned16(feats) || !aligned16(g_hi) || (!fast && !aligned16(g_lo)) ||
         (int64_t)n * a * ci >= ((int64_t)1 << 32) || g_rows >= ((int64_t)1 << 31) || b > 65535)
         return VGTKB_EUNSUP;
     TmaMap mh, ml;
     int rc = make_plane_map(&mh, g_hi, g_rows, ci, k);
     if (rc) return rc;
-    rc = make_plane_map(&ml, g_lo, g_rows, ci, k);
-    if (rc) return rc;
-    const size_t smem = (size_t)IG_WARPS * 2 * 24 * 128 + 1024;
-    if (nn <= 16) {
-        VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_mma_ts_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        inter_group_fwd_mma_ts_kernel<1, true><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(mh, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
-                                                                                        rot_kernels, 1.0f / sigma, feats, ml);
-    } else {
-        VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_mma_ts_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        inter_group_fwd_mma_ts_kernel<2, true><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(mh, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
-                                                                                        rot_kernels, 1.0f / sigma, feats, ml);
+    ml = mh;
+    if (!fast) {
+        rc = make_plane_map(&ml, g_lo, g_rows, ci, k);
+        if (rc) return rc;
     }
-    return check_launch("inter_group_forward(mma, bf16 planes)");
+    const int ks = (nn + 15) / 16;
+    if (!fast && ks <= 2) {       // the tuned kernels (prefetch, two CTAs per SM)
+        const size_t smem = (size_t)IG_WARPS * 2 * 24 * 128 + 1024;
+        if (ks == 1) {
+            VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_mma_ts_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            inter_group_fwd_mma_ts_kernel<1, true><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(mh, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
+                                                                                            rot_kernels, 1.0f / sigma, feats, ml);
+        } else {
+            VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_mma_ts_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            inter_group_fwd_mma_ts_kernel<2, true><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(mh, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
+                                                                                            rot_kernels, 1.0f / sigma, feats, ml);
+        }
+        return check_launch("inter_group_forward(mma, bf16 planes)");
+    }
+#define VGTKB_GEN_FWD(KS_, F_) \
+    return launch_group_fwd_gen<KS_, F_>(mh, ml, b, n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels, sigma, feats, st)
+    if (fast) {
+        if (ks == 1) VGTKB_GEN_FWD(1, true);
+        if (ks == 2) VGTKB_GEN_FWD(2, true);
+        if (ks == 3) VGTKB_GEN_FWD(3, true);
+        VGTKB_GEN_FWD(4, true);
+    }
+    if (ks == 3) VGTKB_GEN_FWD(3, false);
+    VGTKB_GEN_FWD(4, false);
+#undef VGTKB_GEN_FWD
+}
+
+template <int KS, bool FAST>
+static int launch_group_bwd_gen(const TmaMap& map, int b, int n, int p, int nn, int a, int k, int ci, const float* xyz,
+                                const float* sxyz, const int32_t* idx, const float* rk, float sigma, float* gfeats, cudaStream_t st) {
+    const size_t smem = (size_t)IG_WARPS * 2 * 24 * 128 + 1024;
+    auto kern = inter_group_bwd_mma_gen_kernel<KS, FAST>;
+    VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(p, b), IG_WARPS * 32, smem, st>>>(map, n, p, nn, a, k, ci, xyz, sxyz, idx, rk, 1.0f / sigma, gfeats);
+    return check_launch("inter_group_backward(mma, general)");
+}
+
+// scatter of the fp32 dG through the neighbourhoods for the shapes the tuned kernel does not take (33..64 neighbours) and for
+// the single-pass bf16 mode; grad_feats is accumulated into.  VGTKB_EUNSUP: caller falls back to vgtkb_inter_group_backward.
+int inter_group_backward_gen(int b, int n, int p, int nn, int a, int k, int ci, const float* xyz, const float* sample_xyz,
+                             const int32_t* idx, const float* rot_kernels, float sigma, const float* grad_grouped,
+                             float* grad_feats, int fast, cudaStream_t st) {
+    const int64_t g_rows = (int64_t)b * p * a * k;
+    if (k > 24 || nn > 64 || ci % 32 != 0 || !aligned16(grad_feats) || !aligned16(grad_grouped) ||
+        (int64_t)n * a * ci >= ((int64_t)1 << 32) || g_rows >= ((int64_t)1 << 31) || b > 65535)
+        return VGTKB_EUNSUP;
+    TmaMap map;
+    const int rc = make_rows_map(&map, grad_grouped, g_rows, ci, k);
+    if (rc) return rc;
+    const int ks = (nn + 15) / 16;
+#define VGTKB_GEN_BWD(KS_, F_) \
+    return launch_group_bwd_gen<KS_, F_>(map, b, n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels, sigma, grad_feats, st)
+    if (fast) {
+        if (ks == 1) VGTKB_GEN_BWD(1, true);
+        if (ks == 2) VGTKB_GEN_BWD(2, true);
+        if (ks == 3) VGTKB_GEN_BWD(3, true);
+        VGTKB_GEN_BWD(4, true);
+    }
+    if (ks <= 2) return VGTKB_EUNSUP;      // the tuned kernels behind vgtkb_inter_group_backward take these
+    if (ks == 3) VGTKB_GEN_BWD(3, false);
+    VGTKB_GEN_BWD(4, false);
+#undef VGTKB_GEN_BWD
 }
 }  // namespace vgtkb
 

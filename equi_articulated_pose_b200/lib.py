@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgtkb200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _lib = None
 _device_ok = set()
@@ -60,8 +60,8 @@ SIGNATURES = {
     "vgtkb_split_bf16": [c_i64, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_gemm_nt_presplit": [c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_gemm_tn_presplit": [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp],
-    "vgtkb_inter_conv_forward": [c_int] * 8 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
-    "vgtkb_inter_conv_backward": [c_int] * 8 + [c_vp, c_vp, c_vp, c_vp, c_f32] + [c_vp] * 11,
+    "vgtkb_inter_conv_forward": [c_int] * 8 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
+    "vgtkb_inter_conv_backward": [c_int] * 8 + [c_vp, c_vp, c_vp, c_vp, c_f32] + [c_vp] * 10 + [c_int, c_vp],
     "vgtkb_gemm_tn_planes": [c_int, c_int, c_i64] + [c_vp] * 7 + [c_int, c_vp, c_vp],
     "vgtkb_gather_gemm_nt_planes": [c_i64, c_int, c_int, c_int, c_int] + [c_vp] * 8,
     "vgtkb_gather_gemm_tn_planes": [c_i64, c_int, c_int, c_int, c_int] + [c_vp] * 7 + [c_int, c_vp, c_vp],

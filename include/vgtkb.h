@@ -303,7 +303,7 @@ int vgtkb_split_bf16(int64_t n, const float* x, void* hi, void* lo, void* stream
 int vgtkb_gemm_nt_presplit(int64_t M, int N, int K, const void* a_hi, const void* a_lo, const float* B, const float* bias,
                            float* C, float* workspace, void* stream);
 /*   gemm_tn_presplit:  C [M, N] (+)= A [R, M]^T * (b_hi + b_lo) [R, N] (weight gradient with the wide operand as planes);
- *                      M % 8 == 0, M <= 256, N % 8 == 0, R >= 64; workspace: R*M floats (split of the narrow operand) */
+ *                      M % 8 == 0, N % 8 == 0, R >= 64; workspace: R*M floats (split of the narrow operand) */
 int vgtkb_gemm_tn_presplit(int M, int N, int64_t R, const float* A, const void* b_hi, const void* b_lo, float* C, int accumulate,
                            float* workspace, void* stream);
 
@@ -342,18 +342,20 @@ int vgtkb_norm_act_backward_planes(int groups, int64_t rows, int c, const float*
  *             NULL = skip; needs the scratch grad_grouped [b*p*a, k*ci] fp32).  workspace: max(b*p*a*co, 2*k*ci*co) floats.
  *             grad_out_hi / grad_out_lo: optional bf16 planes of grad_out (vgtkb_norm_bwd_apply_planes writes them); NULL =
  *             grad_out is split / converted here.
- *   supported: 1 iff the shape is taken (k <= 24, nn <= 32, ci % 32 == 0, co % 8 == 0, co <= 256, b*p*a >= 64, 32-bit offsets);
+ *   mode:     3 = bf16x3 (fp32-parity: both planes), 4 = single-pass bf16 (BASELINE config 3 "bf16": operands rounded to bf16
+ *             once, one tensor-core pass, ~2e-3 of the output maximum per conv; g_lo / grad_out_lo unused, may be NULL).
+ *   supported: 1 iff the shape is taken (k <= 24, nn <= 64, ci % 32 == 0, co % 8 == 0, co <= 1024, b*p*a >= 64, 32-bit offsets);
  *             other shapes run vgtkb_inter_group_* + vgtkb_gemm_*. */
 int vgtkb_inter_conv_supported(int b, int n, int p, int nn, int a, int k, int ci, int co);
 int vgtkb_inter_conv_forward(int b, int n, int p, int nn, int a, int k, int ci, int co, const float* xyz,
                              const float* sample_xyz, const int32_t* idx, const float* rot_kernels, float sigma,
                              const float* feats, const float* w_kc, void* g_hi, void* g_lo, float* workspace, float* out,
-                             void* stream);
+                             int mode, void* stream);
 int vgtkb_inter_conv_backward(int b, int n, int p, int nn, int a, int k, int ci, int co, const float* xyz,
                               const float* sample_xyz, const int32_t* idx, const float* rot_kernels, float sigma,
                               const float* w_kc, const void* g_hi, const void* g_lo, const float* grad_out,
                               const void* grad_out_hi, const void* grad_out_lo, float* grad_grouped, float* grad_feats,
-                              float* grad_w, float* workspace, void* stream);
+                              float* grad_w, float* workspace, int mode, void* stream);
 
 /* column sums of a row-major [rows, c] matrix (bias gradient of the skip conv) */
 int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream);

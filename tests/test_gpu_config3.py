@@ -1,8 +1,9 @@
 """BASELINE config 3 / 5 shape on the GPU: the equivariant backbone model 38 (`--use-equi=38`, kanchor 60) builds -- three
 stride-1 separable blocks 64 / 128 / 512 with 64-neighbour balls (blocks.model38_backbone_params, checked against the
 reference's own builder in tests/test_reference_compat.py) -- on synthetic 'oven' / 'laptop' clouds, fwd + bwd against the
-CPU oracle.  n_neighbor = 64 is beyond the 32-neighbour tensor-core grouping kernels, so this also covers the exact fp32
-grouping kernels inside a full block stack."""
+CPU oracle.  n_neighbor = 64 runs the general warp-MMA grouping kernels (four k-steps of 16 neighbours,
+csrc/grouping.cu inter_group_*_mma_gen_kernel<4, .>) behind vgtkb_inter_conv_forward / _backward; the last test runs the same
+stack in the single-pass bf16 "fast" mode BASELINE config 3 names (contraction mode 4) at N = 512, B = 8."""
 import pytest
 import torch
 
@@ -71,3 +72,51 @@ def test_model38_backbone_on_articulated_clouds_vs_oracle(dev, kind, seed):
         else:                            # same bar as the classic backbone test: as close to fp64 as the fp32 reference
             assert e_gpu <= max(5 * e_ref, 5e-2 * scale), (name, e_gpu / scale, e_ref / scale)
     print(kind, "fwd rel err", rel_err(out.feats, of), "worst grad err / scale", max(r[2] / r[1] for r in rows if r[1] >= 1e-6 * gmax))
+
+
+def test_model38_backbone_bf16_fast_mode_n512_b8(dev):
+    """BASELINE config 3 arithmetic ("bf16"): contraction mode 4 = operands rounded to bf16 once, one tensor-core pass, fp32
+    accumulation, on the model-38 backbone at N = 512, B = 8 (the size bench.py --config 3 times).  The reference has no
+    reduced-precision mode, so the tolerance is OURS and stated here: forward within 2e-2 of the fp32 oracle (max|d| / max|ref|;
+    measured ~5e-3), loss within 1e-2, and every non-negligible parameter gradient within 25 % (relative L2) of the fp32-parity
+    mode's gradient with a cosine above 0.97."""
+    from equi_articulated_pose_b200 import blocks, synthetic, ops, lib
+    n, b = 512, 8
+    params = blocks.model38_backbone_params(input_num=n)
+    sd = synthetic.init_backbone_state(params, seed=21)
+    pts = synthetic.articulated_cloud("oven", b, n, 3000)
+    sdo, of, oxyz, loss, w = _oracle(params, sd, pts, torch.float32)
+    grads = {}
+    for mode in (3, 4):
+        prev = ops.get_gemm_mode()
+        ops.set_gemm_mode(mode)
+        try:
+            net = build_backbone(params, sd, dev).train()
+            lib.PROFILE = []
+            out = net(pts.to(dev))
+            names = {r[0] for r in lib.PROFILE}
+            lib.PROFILE = None
+            l2 = (out.feats * w.to(dev)).mean()
+            l2.backward()
+        finally:
+            ops.set_gemm_mode(prev)
+            lib.PROFILE = None
+        assert "vgtkb_inter_conv_forward" in names and "vgtkb_inter_group_forward" in names   # (the latter: first layer, ci = 1)
+        assert torch.equal(out.xyz.cpu(), oxyz)
+        e = rel_err(out.feats, of)
+        assert e < (1e-4 if mode == 3 else 2e-2), (mode, e)
+        if mode == 4:
+            assert abs(float(l2.detach()) - float(loss)) < 1e-2 * max(abs(float(loss)), 1e-3)
+            print("bf16 fast mode: forward rel err", e)
+        grads[mode] = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    omax = max(float(sdo[k].grad.abs().max()) for k in grads[3])
+    for k, g3 in grads[3].items():
+        # structurally zero in exact arithmetic: both sides hold rounding noise.  (The first skip branch normalises a constant
+        # tensor, every skip-conv bias sits in front of a BatchNorm: tests/golden/bench_config2_b8.npz gmax64 ~ 1e-16.)
+        if k.endswith("skip_conv.bias") or k.startswith("backbone.0.blocks.0.skip_conv") or k == "backbone.0.blocks.0.norm.weight" \
+                or float(sdo[k].grad.abs().max()) < 1e-4 * omax:
+            continue
+        g4 = grads[4][k]
+        rel = float((g4 - g3).norm() / g3.norm())
+        cos = float((g4 * g3).sum() / (g4.norm() * g3.norm()))
+        assert rel < 0.25 and cos > 0.97, (k, rel, cos)
