@@ -468,7 +468,7 @@ def run_ours(args):
     # gradient all-reduce stays an eager call between two graphs (forward + backward + bucket | Adam) -- the SyncBatchNorm
     # exchanges inside the first graph are plain kernels over peer memory with a device-side sequence counter, so they
     # replay; an NCCL-based SyncBatchNorm (no peer mailboxes) keeps the step eager.
-    use_graph = not args.no_graph and (world == 1 or not sync_bn or ops._PEER_MAILBOX is not None)
+    use_graph = not args.no_graph and (world == 1 or not sync_bn or ops.peer_mailbox_for(None) is not None)
     graph_note = "eager launches" + (" (--no-graph)" if args.no_graph else "")
     run_step = step
     log(f"rank {rank}: capturing the step (graph={use_graph})")

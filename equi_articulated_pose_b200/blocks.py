@@ -69,7 +69,10 @@ class FusedBatchNorm2d(nn.BatchNorm2d):
         training = self.training or not self.track_running_stats
         if training and self.track_running_stats and self.num_batches_tracked is not None:
             self.num_batches_tracked += 1
-        mom = 0.1 if self.momentum is None else self.momentum
+        if self.momentum is None:       # torch: cumulative moving average when momentum is None
+            mom = 1.0 / max(float(self.num_batches_tracked), 1.0) if training and self.num_batches_tracked is not None else 0.0
+        else:
+            mom = self.momentum
         return _ops.norm_act(rows.unsqueeze(0), self.weight, self.bias, None if residual is None else residual.unsqueeze(0),
                              self.running_mean if training else self.running_mean,
                              self.running_var if training else self.running_var,
@@ -101,14 +104,14 @@ def convert_sync_batchnorm(module, process_group=None, peer_memory=True):
         if isinstance(m, FusedBatchNorm2d):
             m.sync_group = True if process_group is None else process_group
     if peer_memory and dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1 \
-            and dist.get_backend(process_group) == "nccl" and _ops._PEER_MAILBOX is None \
-            and os.environ.get("VGTKB_PEER_SYNCBN", "1") != "0":
+            and dist.get_backend(process_group) == "nccl" and _ops.peer_mailbox_for(process_group) is None \
+            and os.environ.get("VGTKB_PEER_SYNCBN", "1") != "0":        # VGTKB_PEER_SYNCBN=0: NCCL all-reduces instead
         from . import dataparallel as _dp
         dev = next(module.parameters()).device
         try:
-            _ops.set_peer_mailbox(_dp.PeerMailbox(dev, process_group))
+            _ops.set_peer_mailbox(_dp.PeerMailbox(dev, process_group), process_group)   # one mailbox per process group
         except RuntimeError:
-            _ops.set_peer_mailbox(None)              # every rank raised (agreed outcome): NCCL path
+            _ops.set_peer_mailbox(None, process_group)   # every rank raised (agreed outcome): NCCL path
     return module
 
 
@@ -140,9 +143,14 @@ class IntraSO3ConvBlock(nn.Module):
     def forward(self, x, residual_rows=None):
         y = self.conv(x)
         rows, (b, p, a, _) = _rows(y.feats)
-        rows = _apply_norm(self.norm, rows, b, self.slope, residual_rows)
         if self.training and self.dropout is not None:
-            rows = self.dropout(rows)
+            # the reference drops out relu(norm(intra)) and only THEN adds the skip branch (base_so3conv.py:59-64,210-217):
+            # the residual must not ride through the fused pass, or dropout would zero / rescale the skip path too
+            rows = self.dropout(_apply_norm(self.norm, rows, b, self.slope))
+            if residual_rows is not None:
+                rows = rows + residual_rows
+        else:
+            rows = _apply_norm(self.norm, rows, b, self.slope, residual_rows)
         return zptk.SphericalPointCloud(y.xyz, _unrows(rows, b, p, a), y.anchors)
 
 

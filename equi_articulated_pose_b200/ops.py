@@ -172,10 +172,11 @@ class InterGroupFn(torch.autograd.Function):
         p, nn = idx.shape[1], idx.shape[2]
         k = rot_kernels.shape[1]
         g = torch.empty((b, p, a, k * ci), dtype=torch.float32, device=feats.device)
+        mode = 3 if _GEMM_MODE == 3 else 0          # fixed here: backward uses the arithmetic the forward ran in
         call("vgtkb_inter_group_forward", feats.device, b, n, p, nn, a, k, ci, ptr(xyz), ptr(sample_xyz), ptr(idx),
-             ptr(rot_kernels), float(sigma), ptr(feats), ptr(g), 3 if _GEMM_MODE == 3 else 0)
+             ptr(rot_kernels), float(sigma), ptr(feats), ptr(g), mode)
         ctx.save_for_backward(xyz, sample_xyz, idx, rot_kernels)
-        ctx.meta = (b, n, p, nn, a, k, ci, float(sigma))
+        ctx.meta = (b, n, p, nn, a, k, ci, float(sigma), mode)
         return g
 
     @staticmethod
@@ -183,11 +184,11 @@ class InterGroupFn(torch.autograd.Function):
         if not ctx.needs_input_grad[0]:
             return (None,) * 6
         xyz, sample_xyz, idx, rot_kernels = ctx.saved_tensors
-        b, n, p, nn, a, k, ci, sigma = ctx.meta
+        b, n, p, nn, a, k, ci, sigma, mode = ctx.meta
         grad_g = _f32(grad_g)
         gx = torch.zeros((b, n, a, ci), dtype=torch.float32, device=grad_g.device)
         call("vgtkb_inter_group_backward", grad_g.device, b, n, p, nn, a, k, ci, ptr(xyz), ptr(sample_xyz), ptr(idx),
-             ptr(rot_kernels), sigma, ptr(grad_g), ptr(gx), 3 if _GEMM_MODE == 3 else 0)
+             ptr(rot_kernels), sigma, ptr(grad_g), ptr(gx), mode)
         return gx, None, None, None, None, None
 
 
@@ -414,6 +415,7 @@ class IntraConvFn(torch.autograd.Function):
         x, w_kc = _f32(x), _f32(w_kc)
         x_hi, x_lo = take_planes(x) if planes_enabled() and x.shape[2] % 64 == 0 else (None, None)
         ctx.planes = x_hi is not None
+        ctx.mode = _GEMM_MODE                        # backward runs in the arithmetic of the forward
         if ctx.planes:
             x_hi, x_lo = x_hi.view(x.shape), x_lo.view(x.shape)
             ctx.save_for_backward(x_hi, x_lo, w_kc, table, table_inv)
@@ -431,7 +433,7 @@ class IntraConvFn(torch.autograd.Function):
             pts, a, c = x.shape
         kk, co = table.shape[1], w_kc.shape[0]
         gy = _f32(gy)
-        gy_hi, gy_lo = take_planes(gy) if planes_enabled() and co % 64 == 0 else (None, None)
+        gy_hi, gy_lo = take_planes(gy) if ctx.mode == 3 and planes_enabled() and co % 64 == 0 else (None, None)
         gx = gw = None
         if ctx.needs_input_grad[0]:
             # gx[(pt,a'), c] = sum_{kk,o} gy[pt, inv[a',kk], o] * w_kc[o, kk*C + c]
@@ -439,12 +441,12 @@ class IntraConvFn(torch.autograd.Function):
             if gy_hi is not None:
                 gx = gather_gemm_nt_planes(gy_hi.view(pts, a, co), gy_lo.view(pts, a, co), table_inv, wt).view(pts, a, c)
             else:
-                gx = gather_gemm_nt(gy.view(pts, a, co), table_inv, wt).view(pts, a, c)
+                gx = gather_gemm_nt(gy.view(pts, a, co), table_inv, wt, mode=ctx.mode).view(pts, a, c)
         if ctx.needs_input_grad[1]:
             if ctx.planes:
                 gw = gather_gemm_tn_planes(x_hi, x_lo, table, gy, gy_hi, gy_lo)
             else:
-                gw = gather_gemm_tn(x, table, gy)
+                gw = gather_gemm_tn(x, table, gy, mode=ctx.mode)
         return gx, gw, None, None
 
 
@@ -456,8 +458,8 @@ class LinearFn(torch.autograd.Function):
         x, w = _f32(x), _f32(w)
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
-        ctx.mode = mode
-        return gemm_nt(x, w, bias, mode)
+        ctx.mode = _GEMM_MODE if mode is None else mode      # fixed here: backward uses the arithmetic of the forward
+        return gemm_nt(x, w, bias, ctx.mode)
 
     @staticmethod
     def backward(ctx, gy):
@@ -552,17 +554,36 @@ def _sync_world(group):
     return dist.get_world_size(None if group is True else group)
 
 
-_PEER_MAILBOX = None     # dataparallel.PeerMailbox: SyncBatchNorm exchanges over NVLink peer memory instead of NCCL
+# dataparallel.PeerMailbox per process group: SyncBatchNorm exchanges over NVLink peer memory instead of NCCL.  A mailbox
+# only serves the group it was built for (its rank / world / peer pointers / exchange counter are that group's); a
+# BatchNorm synchronised over another group takes the NCCL path.
+_PEER_MAILBOXES = {}
+_PEER_MAILBOX = None     # mailbox of the default group (kept as a plain attribute for callers that test `is not None`)
 
 
-def set_peer_mailbox(mailbox):
+def _group_key(group):
+    return "default" if group is None or group is True else id(group)
+
+
+def set_peer_mailbox(mailbox, group=None):
+    """Register (or, with None, remove) the peer mailbox serving `group` (None / True = the default process group)."""
     global _PEER_MAILBOX
-    _PEER_MAILBOX = mailbox
+    key = _group_key(group if mailbox is None else getattr(mailbox, "group", group))
+    if mailbox is None:
+        _PEER_MAILBOXES.pop(key, None)
+    else:
+        _PEER_MAILBOXES[key] = mailbox
+    _PEER_MAILBOX = _PEER_MAILBOXES.get("default")
+
+
+def peer_mailbox_for(group):
+    return _PEER_MAILBOXES.get(_group_key(group))
 
 
 def _all_reduce_sums(scratch, group):
-    if _PEER_MAILBOX is not None and scratch.is_cuda:
-        _PEER_MAILBOX.all_reduce_sums(scratch)
+    mb = peer_mailbox_for(group)
+    if mb is not None and scratch.is_cuda:
+        mb.all_reduce_sums(scratch)
         return
     import torch.distributed as dist
     dist.all_reduce(scratch, op=dist.ReduceOp.SUM, group=None if group is True else group)
@@ -595,7 +616,7 @@ class NormActFn(torch.autograd.Function):
             scratch = torch.empty(2 * c + 1, dtype=torch.float64, device=dev)
             scratch[2 * c:].fill_(float(rows))
             call("vgtkb_norm_sums", dev, 1, rows, c, ptr(x), ptr(scratch))
-            mb = _PEER_MAILBOX
+            mb = peer_mailbox_for(sync_group)
             if mb is not None:      # exchange + finalize in one kernel over peer memory
                 call("vgtkb_norm_finalize_peer", dev, c, float(eps), ptr(scratch), ptr(stats), rm, rv, float(momentum),
                      mb.rank, mb.world, mb.ptrs, mb.next_seq())
@@ -627,15 +648,23 @@ class NormActFn(torch.autograd.Function):
     def backward(ctx, gy):
         x, stats, gam, bet = ctx.saved_tensors
         g, rows, c, slope, use_running, has_res, sync_group = ctx.meta
-        if use_running:
-            raise NotImplementedError("backward through eval-mode BatchNorm is not part of the hot path")
         gy = _f32(gy)
         dev = gy.device
         gx = torch.empty_like(x)
         ggam = torch.empty(c, dtype=torch.float32, device=dev) if gam is not None else None
         gbet = torch.empty(c, dtype=torch.float32, device=dev) if bet is not None else None
         gx_hi, gx_lo = _alloc_planes(gx) if ctx.planes_bwd else (None, None)
-        if sync_group is not None:
+        if use_running:
+            # eval-mode BatchNorm (frozen statistics, e.g. fine-tuning with bn.eval()): the statistics do not depend on x, so
+            # gx = gamma * invstd * dyp, ggamma = sum dyp * xhat, gbeta = sum dyp -- the sums kernel as is, and the apply
+            # kernel with the two mean terms zeroed
+            scratch = torch.empty((g, 2, c), dtype=torch.float64, device=dev)
+            call("vgtkb_norm_bwd_sums", dev, g, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), slope, ptr(gy),
+                 ptr(scratch), ptr(ggam), ptr(gbet))
+            scratch.zero_()
+            call("vgtkb_norm_bwd_apply_planes", dev, g, rows, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), slope, ptr(gy),
+                 ptr(scratch), ptr(gx), ptr(gx_hi), ptr(gx_lo))
+        elif sync_group is not None:
             scratch = torch.empty(2 * c + 1, dtype=torch.float64, device=dev)
             scratch[2 * c:].fill_(float(rows))
             call("vgtkb_norm_bwd_sums", dev, 1, rows, c, ptr(x), ptr(stats), ptr(gam), ptr(bet), slope, ptr(gy),

@@ -74,6 +74,10 @@ class InterSO3Conv(nn.Module):
             self._rk = L.rotated_kernels(self.anchors, self.kernels)
         return self._rk
 
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._rk = None                  # `anchors` / `kernels` may be overwritten in place: recompute the (tiny) cache
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def forward(self, x, inter_idx=None, inter_w=None):
         fused = L.inter_so3conv(x.xyz, x.feats, self.basic_conv.weight_kc(), self.stride, self.n_neighbor, self.anchors,
                                 self.kernels, self.radius, self.sigma, inter_idx, inter_w, self.lazy_sample,
@@ -154,6 +158,10 @@ class IntraSO3Conv(nn.Module):
             is_perm = bool((torch.sort(t, dim=0)[0] == torch.arange(na, device=t.device, dtype=torch.int32).view(na, 1)).all())
             self._tables = (t, inv.contiguous(), is_perm)
         return self._tables
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._tables = None              # `intra_idx` may be overwritten in place
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def forward(self, x):
         nb, c, npt, na = x.feats.shape

@@ -595,10 +595,21 @@ def test_pose_conv_module_non_identity(dev):
     _, _, _, o_id = conv(zptk.SphericalPointCloudPose(xyz, feats, None, eye))
     _, _, _, o_pl = plain(zptk.SphericalPointCloud(xyz, feats, None))
     assert torch.equal(o_id.feats, o_pl.feats)
-    _, _, _, o_rot = conv(zptk.SphericalPointCloudPose(xyz, feats, None, torch.from_numpy(g["pose"]).to(dev)))
-    assert tuple(o_rot.feats.shape) == tuple(o_pl.feats.shape) and torch.isfinite(o_rot.feats).all()
-    assert not torch.allclose(o_rot.feats, o_pl.feats)
+    idx_rot, _, _, o_rot = conv(zptk.SphericalPointCloudPose(xyz, feats, None, torch.from_numpy(g["pose"]).to(dev)))
     assert torch.equal(o_rot.pose, torch.from_numpy(g["pose"]).to(dev))
+    # non-identity pose: the module output equals the oracle's pose grouping (pinned on the reference fixture by the test
+    # above: rotated offsets R_p R_j^T (x_j - x_p), nearest-anchor permutation) followed by BasicSO3Conv with the same W
+    from oracle import so3 as O, cops
+    from equi_articulated_pose_b200 import so3_constants as C
+    xyz_c, pose_c, feats_c = torch.from_numpy(g["xyz"]), torch.from_numpy(g["pose"]), torch.from_numpy(g["feats"])
+    idx = torch.from_numpy(cops.ball_query(xyz_c.numpy(), xyz_c.numpy(), float(g["radius"]), int(g["nn"])))
+    assert torch.equal(idx_rot.cpu(), idx)
+    G_ref, _, _ = O.pose_inter_group_feats(xyz_c, pose_c, feats_c, idx, torch.from_numpy(C.anchors_all()), conv.kernels.cpu(),
+                                           float(g["sigma"]), 1)
+    want = O.basic_conv(conv.basic_conv.W.detach().cpu().double(), G_ref.double())
+    assert tuple(o_rot.feats.shape) == tuple(want.shape)
+    assert rel_err(o_rot.feats, want.float()) < 1e-4
+    assert not torch.allclose(o_rot.feats, o_pl.feats)
 
 
 # ------------------------------------------------------------------------------ anchor-orbit chamfer (model 38 loss)
