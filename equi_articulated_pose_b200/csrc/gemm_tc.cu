@@ -381,7 +381,7 @@ struct PairCfg {
     static_assert(STAGES >= 3 && BN % 64 == 0, "pair configuration");
 };
 
-// PRE = true (EXPERIMENTAL, round-2 groundwork, not on any default path): the activation operand arrives ALREADY split
+// PRE = true (the default path of vgtkb_inter_conv_* and of the intra-conv gather-GEMMs): the activation operand arrives ALREADY split
 // into bf16 hi / lo planes in global memory (map_a = hi plane, map_a2 = lo plane; same shape as the fp32 operand), so the
 // stage is filled by TMA in its final layout and the converter warps only forward the barrier -- the operand-conversion
 // work that bounds the narrow layers (profiles/r1_ncu_gemm_tn_stall_hotspots.txt) disappears from the kernel.
@@ -743,7 +743,7 @@ __device__ __forceinline__ void convert_tn_rows4_bf16(uint32_t region, int k0, i
 // BF = false: kind::tf32 (k-block = 32 rows of R).  BF = true: bf16x3, kind::f16, k-block = 64 rows of R,
 // operands in the canonical 128B-swizzled MN-major bf16 layout: stage = [mn-atom of 64 columns][64 k-rows x 128 B],
 // LBO (next MN atom) = 8192 B, SBO (next 8 k-rows) = 1024 B, one MMA (K = 16) starts 2048 B after the previous.
-// PRE = true (EXPERIMENTAL, with BF; round-2 groundwork, not on any default path): the wide operand P arrives as two
+// PRE = true (with BF; the weight gradients of vgtkb_inter_conv_backward and of the intra conv): the wide operand P arrives as two
 // bf16 planes (map_p = hi, map_p2 = lo) and is loaded by TMA in the MMA's layout, like Q; the converters only forward the barrier.
 template <int BN, bool BF, bool PRE = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -1033,7 +1033,7 @@ struct TnPairCfg {
     static_assert(STAGES >= 3 && BN % 128 == 0, "pair configuration");
 };
 
-template <int BN_, bool PRE = false>       // PRE: see tc_gemm_tn_kernel (experimental pre-split P operand)
+template <int BN_, bool PRE = false>       // PRE: see tc_gemm_tn_kernel (wide operand P as bf16 planes)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
                        const __grid_constant__ CUtensorMap map_q2, int Pw, int Qw, float* __restrict__ C, int ldc, int64_t R,

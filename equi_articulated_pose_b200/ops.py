@@ -876,7 +876,7 @@ def three_interpolate(feat, idx, w):
     return ThreeInterpolateFn.apply(feat, idx, w)
 
 
-# ----------------------------------------------------------------------------- experimental (round-2 groundwork)
+# ----------------------------------------------------------------------------- plane-operand contractions (raw form)
 def split_bf16(x):
     """fp32 tensor -> (hi, lo) bf16 planes with hi = bf16_rn(x), lo = bf16_rn(x - hi) (the operand split of gemm mode 3)."""
     x = _f32(x)
@@ -888,7 +888,7 @@ def split_bf16(x):
 
 def gemm_nt_presplit(a_hi, a_lo, b, bias=None):
     """C[M,N] = (a_hi + a_lo)[M,K] @ b[N,K]^T (+ bias): the bf16x3 contraction with its activation operand already stored
-    as bf16 planes (no in-kernel conversion).  EXPERIMENTAL: not used by any module; see include/vgtkb.h."""
+    as bf16 planes (no in-kernel conversion); the raw form of what InterConvFn / IntraConvFn use."""
     if a_hi.dtype != torch.bfloat16 or a_lo.dtype != torch.bfloat16 or a_hi.shape != a_lo.shape:
         raise _lib.VgtkbError("gemm_nt_presplit: two bf16 planes of the same shape expected")
     b = _f32(b)
@@ -904,7 +904,7 @@ def gemm_nt_presplit(a_hi, a_lo, b, bias=None):
 
 def gemm_tn_presplit(a, b_hi, b_lo):
     """C[M,N] = a[R,M]^T @ (b_hi + b_lo)[R,N]: the bf16x3 weight-gradient contraction with its wide operand stored as bf16
-    planes.  EXPERIMENTAL: not used by any module; see include/vgtkb.h."""
+    planes; the raw form of what InterConvFn's weight gradient uses."""
     if b_hi.dtype != torch.bfloat16 or b_lo.dtype != torch.bfloat16 or b_hi.shape != b_lo.shape:
         raise _lib.VgtkbError("gemm_tn_presplit: two bf16 planes of the same shape expected")
     a = _f32(a)

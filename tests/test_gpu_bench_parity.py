@@ -81,13 +81,14 @@ def test_config2_b8_forward_and_gradients_vs_oracle(dev, gold):
              "gradients": [dict(r, e_gpu_over_scale=r["e_gpu"] / r["scale"] if r["scale"] > 0 else None,
                                 e_ref_over_scale=r["e_ref"] / r["scale"] if r["scale"] > 0 else None) for r in rows],
              "bar": "e_gpu <= max(5 e_ref, 1e-2 scale) per tensor (same sampled entries, fp64 ground truth); structurally zero "
-                    "tensors: |g| < 1e-4 of the largest gradient maximum"}
+                    "tensors (true gradient 0): e_gpu <= max(5 e_ref, 1e-6 of the largest gradient maximum)"}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(table, open(os.path.join(ROOT, "gpurun_out", "r2_grad_parity_b8.json"), "w"), indent=1)
     bad = []
     for r in rows:
-        if r["scale"] < 1e-6 * gmax:          # bias in front of BatchNorm, constant first skip branch: true gradient 0
-            if r["e_gpu"] >= 1e-4 * gmax:
+        if r["scale"] < 1e-6 * gmax:          # bias in front of BatchNorm, constant first skip branch: true gradient 0,
+            # both implementations hold rounding noise (the first skip BatchNorm divides by sqrt(eps)): same 5x rule
+            if r["e_gpu"] > max(5.0 * r["e_ref"], 1e-6 * gmax):
                 bad.append((r["tensor"], "zero", r["e_gpu"]))
         elif r["e_gpu"] > max(5.0 * r["e_ref"], 1e-2 * r["scale"]):
             bad.append((r["tensor"], r["e_gpu"] / r["scale"], r["e_ref"] / r["scale"]))

@@ -1,14 +1,12 @@
-"""Round-2 groundwork, NOT part of the default suite: parity of the pre-split-operand contraction
-(vgtkb_split_bf16 + vgtkb_gemm_nt_presplit, csrc/gemm_tc.cu template PRE) against mode 3 of vgtkb_gemm_nt, whose arithmetic it
-reproduces (bit-identical results expected: same operand split, same MMA order, same chunked accumulation).
-The path was written after the GPU budget of round 1 was spent; run with VGTKB_EXPERIMENTAL=1 on a B200."""
-import os
-
+"""Plane-operand contractions (vgtkb_split_bf16 + vgtkb_gemm_nt_presplit / vgtkb_gemm_tn_presplit, csrc/gemm_tc.cu template PRE:
+the activation operand arrives as bf16 hi / lo planes and is loaded by TMA in the MMA's layout) against mode 3 of
+vgtkb_gemm_nt / vgtkb_gemm_tn, whose arithmetic they reproduce (NT: bit-identical -- same operand split, same MMA order,
+same chunked accumulation; TN: identical up to the order of the red.global.add partial sums).  These kernels are the
+default path of vgtkb_inter_conv_* and of the intra-conv gather-GEMMs."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("VGTKB_EXPERIMENTAL", "0") != "1", reason="experimental path: set VGTKB_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("M,N,K", [(4096, 64, 1536), (1000, 128, 3072), (61440, 256, 6144), (300, 256, 64), (129, 72, 128)])
