@@ -1525,6 +1525,52 @@ static int tc_gemm_nt_impl(int64_t M, int N, int K, const float* A, const float*
     return rc;
 }
 
+// Work decomposition of the weight-gradient kernels: items = tiles x anchor groups x R splits are dealt round-robin to
+// `units` persistent CTAs (or CTA pairs).  The first version took ceil(2 units / tiles) splits, which lands just ABOVE two
+// full waves for the shapes of the backbone (e.g. 6 tiles x 25 splits = 150 items on 74 pairs: a third wave with two
+// items, 68 % efficiency; ncu: tensor pipe 37-74 % on kernels whose operands stream at half the fabric rate).  Pick the
+// (groups, splits) pair that fills whole waves best, at most ~3 waves, every split at least 512 rows long.
+static void tn_decompose(int tiles, int units, int anchors, int64_t R, int KR, int& n_groups, int& ag, int64_t& splits, int64_t& rps) {
+    const int64_t max_splits = ceil_div64(R, 512) > 0 ? ceil_div64(R, 512) : 1;
+    const char* legacy = getenv("VGTKB_TN_DECOMP");
+    if (legacy != nullptr && legacy[0] == '0') {      // the first version (comparison runs)
+        n_groups = 1, ag = 1;
+        if (anchors > 0) {
+            n_groups = (int)ceil_div64((int64_t)2 * units, tiles);
+            if (n_groups > anchors) n_groups = anchors;
+            ag = ceil_div(anchors, n_groups);
+            n_groups = ceil_div(anchors, ag);
+        }
+        splits = ceil_div64((int64_t)2 * units, (int64_t)tiles * n_groups);
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+        rps = ceil_div64(ceil_div64(R, splits), KR) * KR;
+        splits = ceil_div64(R, rps);
+        return;
+    }
+    double best = -1.0;
+    n_groups = 1, ag = anchors > 0 ? anchors : 1, splits = 1, rps = ceil_div64(R, KR) * KR;
+    const int ng_max = anchors > 0 ? anchors : 1;
+    for (int ng = 1; ng <= ng_max; ++ng) {
+        const int a_per = anchors > 0 ? ceil_div(anchors, ng) : 1;
+        const int ng_eff = anchors > 0 ? ceil_div(anchors, a_per) : 1;
+        if (ng_eff != ng) continue;                                   // same decomposition as a smaller ng
+        for (int64_t sp = 1; sp <= max_splits && (int64_t)tiles * ng * sp <= (int64_t)3 * units + tiles; ++sp) {
+            const int64_t r = ceil_div64(ceil_div64(R, sp), KR) * KR;
+            const int64_t sp_eff = ceil_div64(R, r);
+            if (sp_eff != sp) continue;
+            const int64_t items = (int64_t)tiles * ng * sp;
+            const int64_t waves = ceil_div64(items, units);
+            // efficiency of the last wave, with a mild preference for more (shorter) items: better balance, shorter tails
+            const double eff = (double)items / (double)(waves * units) - (items < units ? 0.0 : 0.02 / (double)waves);
+            if (eff > best + 1e-9) {
+                best = eff;
+                n_groups = ng, ag = a_per, splits = sp, rps = r;
+            }
+        }
+    }
+}
+
 template <int BN, bool BF, bool PRE = false>
 static int launch_tn(const void* P, int Pw, const void* Q, const void* Q2, int Qw, float* C, int ldc, int64_t R, int passes,
                      cudaStream_t st, TcGather ga = TcGather{0, 0, 0, nullptr}, const void* P_lo = nullptr, int fast = 0) {
@@ -1558,18 +1604,8 @@ static int launch_tn(const void* P, int Pw, const void* Q, const void* Q2, int Q
     }
     const int tiles = ceil_div(Pw, TC_BM) * ceil_div(Qw, BN);
     int n_groups = 1, ag = 1;
-    if (ga.anchors > 0) {   // parallelism first from anchor groups, then from point splits
-        n_groups = (int)ceil_div64((int64_t)2 * num_sms(), tiles);
-        if (n_groups > ga.anchors) n_groups = ga.anchors;
-        ag = ceil_div(ga.anchors, n_groups);
-        n_groups = ceil_div(ga.anchors, ag);
-    }
-    int64_t splits = ceil_div64((int64_t)2 * num_sms(), (int64_t)tiles * n_groups);
-    const int64_t max_splits = ceil_div64(R, 512);
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    int64_t rps = ceil_div64(ceil_div64(R, splits), KR) * KR;
-    splits = ceil_div64(R, rps);
+    int64_t splits = 1, rps = R;
+    tn_decompose(tiles, num_sms(), ga.anchors, R, KR, n_groups, ag, splits, rps);
     const int64_t items = splits * tiles * n_groups;
     const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024;
     if (!PRE || P_lo == nullptr) mp2 = mp;
@@ -1616,18 +1652,8 @@ static int launch_tn_pair(const void* P, int Pw, const void* Q, const void* Q2, 
     const int max_pairs = num_sms() / 2;
     const int tiles = ceil_div(ceil_div(Pw, TC_BM), 2) * ceil_div(Qw, Cfg::BN);
     int n_groups = 1, ag = 1;
-    if (ga.anchors > 0) {
-        n_groups = (int)ceil_div64((int64_t)2 * max_pairs, tiles);
-        if (n_groups > ga.anchors) n_groups = ga.anchors;
-        ag = ceil_div(ga.anchors, n_groups);
-        n_groups = ceil_div(ga.anchors, ag);
-    }
-    int64_t splits = ceil_div64((int64_t)2 * max_pairs, (int64_t)tiles * n_groups);
-    const int64_t max_splits = ceil_div64(R, 512);
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    int64_t rps = ceil_div64(ceil_div64(R, splits), KR) * KR;
-    splits = ceil_div64(R, rps);
+    int64_t splits = 1, rps = R;
+    tn_decompose(tiles, max_pairs, ga.anchors, R, KR, n_groups, ag, splits, rps);
     const int64_t items = splits * tiles * n_groups;
     const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024;
     if (!PRE || P_lo == nullptr) mp2 = mp;
