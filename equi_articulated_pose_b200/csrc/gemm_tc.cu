@@ -94,9 +94,9 @@ struct TcBarriers {
 };
 
 template <int STAGES>
-__device__ __forceinline__ void tc_init_barriers(TcBarriers& b) {
+__device__ __forceinline__ void tc_init_barriers(TcBarriers& b, int raw_count = 1) {
     for (int s = 0; s < STAGES; ++s) {
-        mbar_init(&b.raw_full[s], 1);            // the TMA issuer's expect_tx arrive
+        mbar_init(&b.raw_full[s], raw_count);    // the TMA issuers' expect_tx arrives (one per issuing warp)
         mbar_init(&b.full[s], TC_CONV_WARPS);    // one elected arrive per converter warp
         mbar_init(&b.empty[s], 1);               // tcgen05.commit
     }
@@ -266,8 +266,9 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
     } else if (warp == TC_MMA_WARP) {
         // ============================ MMA issuer ============================
+        // whole warp in the loop, one elected lane issues (uniform-register operands: see tc_gemm_nt_pair_kernel)
         reg_dec_other();
-        if (lane == 0) {
+        {
             const uint32_t idesc = BF ? make_idesc_bf16(TC_BM, BN, 0, 0) : make_idesc_tf32(TC_BM, BN, 0, 0);
             int it = 0, ci = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -289,30 +290,34 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         const int kba = (kb + krot) % nkb;
                         const int krem = K - kba * KBE;
                         const int ksteps = krem >= KBE ? KBE / UK : (krem + UK - 1) / UK;
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint32_t koff = ks * 32;  // 8 tf32 / 16 bf16 = 32 bytes inside the 128 B swizzle row
-                            const uint64_t da_hi = make_smem_desc(a_hi + koff, 16, 1024);
-                            const uint64_t db_hi = make_smem_desc(b_hi + koff, 16, 1024);
-                            const uint32_t first = ((kb - kb0) | ks) != 0;
-                            if (BF) {
-                                const uint64_t da_lo = make_smem_desc(a_lo + koff, 16, 1024);
-                                const uint64_t db_lo = make_smem_desc(b_lo + koff, 16, 1024);
-                                umma_bf16(d_tmem, da_lo, db_hi, idesc, first);
-                                umma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
-                                umma_bf16(d_tmem, da_hi, db_hi, idesc, 1);
-                            } else if (passes == 3) {
-                                const uint64_t da_lo = make_smem_desc(a_lo + koff, 16, 1024);
-                                const uint64_t db_lo = make_smem_desc(b_lo + koff, 16, 1024);
-                                umma_tf32(d_tmem, da_lo, db_hi, idesc, first);   // small terms first
-                                umma_tf32(d_tmem, da_hi, db_lo, idesc, 1);
-                                umma_tf32(d_tmem, da_hi, db_hi, idesc, 1);
-                            } else {
-                                umma_tf32(d_tmem, da_hi, db_hi, idesc, first);
+                        const uint64_t da_hi0 = make_smem_desc(a_hi, 16, 1024), db_hi0 = make_smem_desc(b_hi, 16, 1024);
+                        const uint64_t da_lo0 = make_smem_desc(a_lo, 16, 1024), db_lo0 = make_smem_desc(b_lo, 16, 1024);
+                        const bool first_kb = kb == kb0;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < KBE / UK; ++ks) {
+                                if (ks < ksteps) {
+                                    const uint64_t o = (uint64_t)(ks * 2);  // 8 tf32 / 16 bf16 = 32 bytes inside the 128 B swizzle row
+                                    const uint32_t acc = (first_kb && ks == 0) ? 0u : 1u;
+                                    if (BF) {
+                                        umma_bf16(d_tmem, da_lo0 + o, db_hi0 + o, idesc, acc);
+                                        umma_bf16(d_tmem, da_hi0 + o, db_lo0 + o, idesc, 1);
+                                        umma_bf16(d_tmem, da_hi0 + o, db_hi0 + o, idesc, 1);
+                                    } else if (passes == 3) {
+                                        umma_tf32(d_tmem, da_lo0 + o, db_hi0 + o, idesc, acc);   // small terms first
+                                        umma_tf32(d_tmem, da_hi0 + o, db_lo0 + o, idesc, 1);
+                                        umma_tf32(d_tmem, da_hi0 + o, db_hi0 + o, idesc, 1);
+                                    } else {
+                                        umma_tf32(d_tmem, da_hi0 + o, db_hi0 + o, idesc, acc);
+                                    }
+                                }
                             }
+                            umma_commit(&bars.empty[s]);   // smem stage reusable once these MMAs have read it
                         }
-                        umma_commit(&bars.empty[s]);   // smem stage reusable once these MMAs have read it
+                        __syncwarp();
                     }
-                    umma_commit(&bars.tfull[buf]);     // chunk complete
+                    if (elect_one()) umma_commit(&bars.tfull[buf]);     // chunk complete
+                    __syncwarp();
                 }
             }
         }
@@ -390,7 +395,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                        const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c, int tma_out,
                        const float* __restrict__ bias, float* __restrict__ C, int64_t M, int N, int K, int chunk_kb, TcGather ga,
-                       const __grid_constant__ CUtensorMap map_a2, int fast) {
+                       const __grid_constant__ CUtensorMap map_a2, int fast_in) {
+    // bits 4.. of fast_in: timing experiments (VGTKB_DBG; results are garbage): 1 = no MMAs are issued, 2 = no TMA loads
+    const int fast = fast_in & 15, dbg = fast_in >> 4;
     // fast != 0: single-pass bf16 (contraction mode 4, BASELINE config 3): only the hi planes take part -- one MMA per k-step
     // instead of three, and the lo planes are neither loaded (PRE) nor used
     using Cfg = PairCfg<BN_>;
@@ -412,8 +419,10 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&bars.raw_full[s], 1);                  // local TMA
-            mbar_init(&bars.full[s], 2 * TC_CONV_WARPS);      // converter warps of BOTH CTAs (used in the leader)
+            // PRE: the stage's boxes are issued by up to four different warps (one expect_tx arrive each), see below
+            mbar_init(&bars.raw_full[s], PRE ? (fast ? 2 : 4) : 1);
+            // converter warps of BOTH CTAs (PRE: one forwarding warp per CTA); used in the leader
+            mbar_init(&bars.full[s], PRE ? 2 : 2 * TC_CONV_WARPS);
             mbar_init(&bars.empty[s], 1);                     // multicast tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -427,6 +436,62 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = bars.tmem_base;
+
+    // TMA issue loop of one thread.  which = -1: all boxes of every stage (raw fp32 operand, converter path);
+    // which = 0..3 (PRE): only box `which` of every stage -- 0: A hi, 1: A lo, 2: weights hi, 3: weights lo
+    auto issue_loads = [&](int which) {
+        if (which < 0 || which == 0) tma_prefetch_desc(&map_a);
+        if (PRE && which == 1) tma_prefetch_desc(&map_a2);
+        if (which < 0 || which == 2) tma_prefetch_desc(&map_bhi);
+        if (which < 0 || which == 3) tma_prefetch_desc(&map_blo);
+        if (fast && (which == 1 || which == 3)) return;          // single-pass bf16: the lo planes are not loaded
+        const uint32_t tx = which < 0 ? 2u * (uint32_t)Cfg::A_BYTES + (fast ? 1u : 2u) * (uint32_t)Cfg::BH_BYTES
+                                      : (which < 2 ? (uint32_t)Cfg::A_BYTES : (uint32_t)Cfg::BH_BYTES);
+        int it = 0;
+        for (int tile = pair; tile < total_tiles; tile += npairs) {
+            const int nt = tile % n_tiles, an = (tile / n_tiles) % a_cnt, mt = 2 * (tile / (n_tiles * a_cnt)) + (int)rank;
+            const int brow = nt * BN + (int)rank * (BN / 2);
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
+                if (!elect_one()) continue;      // the warp runs the loop, one lane issues (uniform-register operands)
+                unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
+                if (dbg & 2) {
+                    mbar_arrive(&bars.raw_full[s]);
+                    continue;
+                }
+                mbar_arrive_expect_tx(&bars.raw_full[s], tx);
+                if (PRE) {          // bf16 planes: one box of 64 columns per plane, already the MMA's layout
+                    if (which < 2) {
+                        const CUtensorMap* mp = which == 0 ? &map_a : &map_a2;
+                        if (ga.anchors > 0) {
+                            const int kcol = kb * KBE, kk = kcol / ga.c, c0 = kcol - kk * ga.c;
+                            const int mid = __ldg(ga.table + an * ga.kk_n + kk);
+                            tma_load_3d(st + which * Cfg::A_BYTES, mp, c0, mid, mt * TC_BM, &bars.raw_full[s]);
+                        } else {
+                            tma_load_2d(st + which * Cfg::A_BYTES, mp, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
+                        }
+                    } else if (which == 2) {
+                        tma_load_2d(st + 2 * Cfg::A_BYTES, &map_bhi, kb * KBE, brow, &bars.raw_full[s]);
+                    } else {
+                        tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::BH_BYTES, &map_blo, kb * KBE, brow, &bars.raw_full[s]);
+                    }
+                    continue;
+                }
+                if (ga.anchors > 0) {
+                    const int kcol = kb * KBE, kk = kcol / ga.c, c0 = kcol - kk * ga.c;
+                    const int mid = __ldg(ga.table + an * ga.kk_n + kk);
+                    tma_load_3d(st, &map_a, c0, mid, mt * TC_BM, &bars.raw_full[s]);
+                    tma_load_3d(st + Cfg::A_BYTES, &map_a, c0 + 32, mid, mt * TC_BM, &bars.raw_full[s]);
+                } else {
+                    tma_load_2d(st, &map_a, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
+                    tma_load_2d(st + Cfg::A_BYTES, &map_a, kb * KBE + 32, mt * TC_BM, &bars.raw_full[s]);
+                }
+                tma_load_2d(st + 2 * Cfg::A_BYTES, &map_bhi, kb * KBE, brow, &bars.raw_full[s]);
+                if (!fast) tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::BH_BYTES, &map_blo, kb * KBE, brow, &bars.raw_full[s]);
+            }
+        }
+    };
 
     if (warp < TC_EPI_WARPS) {
         // ============================ epilogue ============================
@@ -533,23 +598,46 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         // ============================ converters ============================
         reg_dec_other();
         const int ct = warp < TC_MMA_WARP ? threadIdx.x - TC_EPI_WARPS * 32 : threadIdx.x - (TC_TMA_WARP + 1) * 32 + 128;
-        int it = 0;
-        for (int tile = pair; tile < total_tiles; tile += npairs) {
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int s = it % STAGES;
-                mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
-                if (!PRE) {
+        if (PRE) {
+            // nothing to convert.  Measured (scripts/tma_rate.cu, profiles/r2_tma_issue_rate.csv): ONE issuing thread gets at
+            // most one 128-byte-row box through the TMA unit per ~700 cycles whatever its height (21 B/clk/SM for 128-row
+            // boxes: the 3.3-4.5 TB/s every plane-fed contraction was stuck at), and the rate scales with the number of
+            // issuing WARPS.  So the four boxes of a stage are issued by four warps: the TMA warp (A hi) and converter
+            // warps 0..2 (A lo, B hi, B lo); converter warp 3 forwards "stage landed" to the leader CTA.
+            const int cw = ct >> 5;
+            if (cw < 3) {
+                issue_loads(cw + 1);
+            } else if (cw == 3) {
+                int it = 0;
+                for (int tile = pair; tile < total_tiles; tile += npairs)
+                    for (int kb = 0; kb < nkb; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
+                        if (lane == 0) mbar_arrive_remote(&bars.full[s], 0);
+                    }
+            }
+            __syncwarp();
+        } else {
+            int it = 0;
+            for (int tile = pair; tile < total_tiles; tile += npairs) {
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
                     convert_rows_bf16(smem_base + s * Cfg::STAGE_BYTES, ct >> 5, lane);
                     fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(&bars.full[s], 0);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(&bars.full[s], 0);
             }
         }
     } else if (warp == TC_MMA_WARP) {
         // ============================ MMA issuer (leader CTA only) ============================
+        // The WHOLE warp runs the loop (waits, descriptor arithmetic: warp-uniform, kept in uniform registers) and one
+        // elected lane issues the tcgen05 instructions.  The first version ran everything under `lane == 0`: every MMA
+        // then needed an ELECT + 5 x R2UR + branch sequence to move its operands into uniform registers, ~100 cycles per
+        // MMA -- with the loads switched off (VGTKB_DBG=2) the N = 64 / 128 launches took as long as with them.
         reg_dec_other();
-        if (rank == 0 && lane == 0) {
+        if (rank == 0) {
             const uint32_t idesc = make_idesc_bf16(2 * TC_BM, BN, 0, 0);
             int it = 0, ci = 0;
             for (int tile = pair; tile < total_tiles; tile += npairs) {
@@ -568,25 +656,32 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                         const uint32_t b_hi = a_lo + Cfg::A_BYTES;
                         const uint32_t b_lo = b_hi + Cfg::BH_BYTES;
                         const int krem = K - kb * KBE;
-                        const int ksteps = krem >= KBE ? KBE / UK : (krem + UK - 1) / UK;
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint32_t koff = ks * 32;
-                            const uint64_t da_hi = make_smem_desc(a_hi + koff, 16, 1024);
-                            const uint64_t db_hi = make_smem_desc(b_hi + koff, 16, 1024);
-                            const uint64_t da_lo = make_smem_desc(a_lo + koff, 16, 1024);
-                            const uint64_t db_lo = make_smem_desc(b_lo + koff, 16, 1024);
-                            const uint32_t first = ((kb - kb0) | ks) != 0;
-                            if (fast) {
-                                umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, first);
-                            } else {
-                                umma_bf16_pair(d_tmem, da_lo, db_hi, idesc, first);
-                                umma_bf16_pair(d_tmem, da_hi, db_lo, idesc, 1);
-                                umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, 1);
+                        const int ksteps = (dbg & 1) ? 0 : (krem >= KBE ? KBE / UK : (krem + UK - 1) / UK);
+                        // descriptors of k-step 0; a k-step advances the start-address field (bits 0-13, address >> 4) by 2
+                        const uint64_t da_hi0 = make_smem_desc(a_hi, 16, 1024), db_hi0 = make_smem_desc(b_hi, 16, 1024);
+                        const uint64_t da_lo0 = make_smem_desc(a_lo, 16, 1024), db_lo0 = make_smem_desc(b_lo, 16, 1024);
+                        const bool first_kb = kb == kb0;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < KBE / UK; ++ks) {
+                                if (ks < ksteps) {
+                                    const uint64_t o = (uint64_t)(ks * 2);
+                                    const uint32_t acc = (first_kb && ks == 0) ? 0u : 1u;
+                                    if (fast) {
+                                        umma_bf16_pair(d_tmem, da_hi0 + o, db_hi0 + o, idesc, acc);
+                                    } else {
+                                        umma_bf16_pair(d_tmem, da_lo0 + o, db_hi0 + o, idesc, acc);
+                                        umma_bf16_pair(d_tmem, da_hi0 + o, db_lo0 + o, idesc, 1);
+                                        umma_bf16_pair(d_tmem, da_hi0 + o, db_hi0 + o, idesc, 1);
+                                    }
+                                }
                             }
+                            umma_commit_pair(&bars.empty[s]);
                         }
-                        umma_commit_pair(&bars.empty[s]);
+                        __syncwarp();
                     }
-                    umma_commit_pair(&bars.tfull[buf]);
+                    if (elect_one()) umma_commit_pair(&bars.tfull[buf]);
+                    __syncwarp();
                 }
             }
         }
@@ -594,46 +689,7 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     } else {
         // ============================ TMA producer (both CTAs: own rows, own half of the weights) =========
         reg_dec_other();
-        if (lane == 0) {
-            tma_prefetch_desc(&map_a);
-            if (PRE) tma_prefetch_desc(&map_a2);
-            tma_prefetch_desc(&map_bhi);
-            tma_prefetch_desc(&map_blo);
-            const bool skip_alo = PRE && fast;       // raw fp32 operands always arrive as two boxes
-            const uint32_t tx = (skip_alo ? 1u : 2u) * (uint32_t)Cfg::A_BYTES + (fast ? 1u : 2u) * (uint32_t)Cfg::BH_BYTES;
-            int it = 0;
-            for (int tile = pair; tile < total_tiles; tile += npairs) {
-                const int nt = tile % n_tiles, an = (tile / n_tiles) % a_cnt, mt = 2 * (tile / (n_tiles * a_cnt)) + (int)rank;
-                const int brow = nt * BN + (int)rank * (BN / 2);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
-                    unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&bars.raw_full[s], tx);
-                    if (PRE) {          // bf16 planes: one box of 64 columns per plane, already the MMA's layout
-                        if (ga.anchors > 0) {
-                            const int kcol = kb * KBE, kk = kcol / ga.c, c0 = kcol - kk * ga.c;
-                            const int mid = __ldg(ga.table + an * ga.kk_n + kk);
-                            tma_load_3d(st, &map_a, c0, mid, mt * TC_BM, &bars.raw_full[s]);
-                            if (!fast) tma_load_3d(st + Cfg::A_BYTES, &map_a2, c0, mid, mt * TC_BM, &bars.raw_full[s]);
-                        } else {
-                            tma_load_2d(st, &map_a, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
-                            if (!fast) tma_load_2d(st + Cfg::A_BYTES, &map_a2, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
-                        }
-                    } else if (ga.anchors > 0) {
-                        const int kcol = kb * KBE, kk = kcol / ga.c, c0 = kcol - kk * ga.c;
-                        const int mid = __ldg(ga.table + an * ga.kk_n + kk);
-                        tma_load_3d(st, &map_a, c0, mid, mt * TC_BM, &bars.raw_full[s]);
-                        tma_load_3d(st + Cfg::A_BYTES, &map_a, c0 + 32, mid, mt * TC_BM, &bars.raw_full[s]);
-                    } else {
-                        tma_load_2d(st, &map_a, kb * KBE, mt * TC_BM, &bars.raw_full[s]);
-                        tma_load_2d(st + Cfg::A_BYTES, &map_a, kb * KBE + 32, mt * TC_BM, &bars.raw_full[s]);
-                    }
-                    tma_load_2d(st + 2 * Cfg::A_BYTES, &map_bhi, kb * KBE, brow, &bars.raw_full[s]);
-                    if (!fast) tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::BH_BYTES, &map_blo, kb * KBE, brow, &bars.raw_full[s]);
-                }
-            }
-        }
+        issue_loads(PRE ? 0 : -1);
         __syncwarp();
     }
 
@@ -771,7 +827,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
     const int n_groups = ga.anchors > 0 ? (ga.anchors + anchors_per_item - 1) / anchors_per_item : 1;
     const int items = tiles * n_groups * splits;        // item -> (sp, grp, tile), tile fastest
 
-    if (threadIdx.x == 0) tc_init_barriers<STAGES>(bars);
+    if (threadIdx.x == 0) tc_init_barriers<STAGES>(bars, (BF && PRE) ? (fast ? 2 : 4) : 1);   // PRE: four issuing warps
     if (warp == TC_MMA_WARP) tmem_alloc(&bars.tmem_base, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
@@ -790,6 +846,108 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
         const int grp = (item / tiles) % n_groups;
         a0 = grp * anchors_per_item;
         return min(anchors_per_item, ga.anchors - a0);
+    };
+
+    // TMA issue loop of one thread: which = -1 every box of every stage; BF && PRE: 0 = P hi, 1 = P lo, 2 = Q hi, 3 = Q lo
+    auto issue_loads = [&](int which) {
+        if (which <= 0) tma_prefetch_desc(&map_p);
+        if (PRE && which == 1) tma_prefetch_desc(&map_p2);
+        if (which < 0 || which == 2) tma_prefetch_desc(&map_q);
+        if (BF && (which < 0 || which == 3)) tma_prefetch_desc(&map_q2);
+        if (fast && (which == 1 || which == 3)) return;
+        // fast (bf16 single pass): the lo planes of Q, and of P when it arrives as planes, are not loaded
+        const uint32_t tx = which >= 0 ? (which < 2 ? (uint32_t)Cfg::A_BYTES : (uint32_t)Cfg::B_BYTES)
+                            : BF     ? 2u * (uint32_t)Cfg::A_BYTES + (fast ? 1u : 2u) * (uint32_t)Cfg::B_BYTES
+                                     : (uint32_t)Cfg::A_BYTES + (uint32_t)Cfg::B_BYTES;
+        constexpr uint32_t BOX_BYTES = BF ? 8192 : 4096;
+        int it = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int tile = item % tiles;
+            const int p0 = (tile / q_tiles) * TC_BM, q0 = (tile % q_tiles) * BN;
+            int64_t r0;
+            int a0;
+            const int nkb = item_nkb(item, r0);
+            const int nblk = nkb * item_anchors(item, a0);
+            for (int kb = 0; kb < nblk; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
+                if (!elect_one()) continue;      // the warp runs the loop, one lane issues (uniform-register operands)
+                unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
+                const int row = (int)(r0 + (int64_t)(kb % nkb) * KR);
+                mbar_arrive_expect_tx(&bars.raw_full[s], tx);
+                if (ga.anchors > 0) {
+                    // gathered P: column (kk, c) of anchor `an` lives at X[point, table[an, kk], c]
+                    const int an = a0 + kb / nkb;
+                    if (PRE) {
+                        if (which < 2) {
+#pragma unroll
+                            for (int a = 0; a < TC_BM / 64; ++a) {       // bf16 planes: atoms of 64 columns, final layout
+                                const int cc = p0 + a * 64;
+                                const int kk = cc < Pw ? cc / ga.c : 0;
+                                const int c0 = cc < Pw ? cc - kk * ga.c : ga.c;                 // out of bounds: zeros
+                                const int mid = cc < Pw ? __ldg(ga.table + an * ga.kk_n + kk) : 0;
+                                tma_load_3d(st + which * Cfg::A_BYTES + a * 8192, which == 0 ? &map_p : &map_p2, c0, mid, row, &bars.raw_full[s]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < BN / 64; ++a)
+                                tma_load_3d(st + 2 * Cfg::A_BYTES + (which - 2) * Cfg::B_BYTES + a * 8192, which == 2 ? &map_q : &map_q2,
+                                            q0 + a * 64, an, row, &bars.raw_full[s]);
+                        }
+                        continue;
+                    } else
+#pragma unroll
+                    for (int a = 0; a < TC_BM / 32; ++a) {
+                        const int cc = p0 + a * 32;
+                        if (cc < Pw) {
+                            const int kk = cc / ga.c;
+                            tma_load_3d(st + a * BOX_BYTES, &map_p, cc - kk * ga.c, __ldg(ga.table + an * ga.kk_n + kk), row, &bars.raw_full[s]);
+                        } else {
+                            tma_load_3d(st + a * BOX_BYTES, &map_p, ga.c, 0, row, &bars.raw_full[s]);   // out of bounds: zeros
+                        }
+                    }
+                    if (BF) {
+#pragma unroll
+                        for (int a = 0; a < BN / 64; ++a) {
+                            tma_load_3d(st + 2 * Cfg::A_BYTES + a * 8192, &map_q, q0 + a * 64, an, row, &bars.raw_full[s]);
+                            if (!fast) tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + a * 8192, &map_q2, q0 + a * 64, an, row, &bars.raw_full[s]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < BN / 32; ++a)
+                            tma_load_3d(st + 2 * Cfg::A_BYTES + a * BOX_BYTES, &map_q, q0 + a * 32, an, row, &bars.raw_full[s]);
+                    }
+                    continue;
+                }
+                if (PRE) {
+                    if (which < 2) {
+#pragma unroll
+                        for (int a = 0; a < TC_BM / 64; ++a)
+                            tma_load_2d(st + which * Cfg::A_BYTES + a * 8192, which == 0 ? &map_p : &map_p2, p0 + a * 64, row, &bars.raw_full[s]);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < BN / 64; ++a)
+                            tma_load_2d(st + 2 * Cfg::A_BYTES + (which - 2) * Cfg::B_BYTES + a * 8192, which == 2 ? &map_q : &map_q2,
+                                        q0 + a * 64, row, &bars.raw_full[s]);
+                    }
+                    continue;
+                } else
+#pragma unroll
+                for (int a = 0; a < TC_BM / 32; ++a)
+                    tma_load_2d(st + a * BOX_BYTES, &map_p, p0 + a * 32, row, &bars.raw_full[s]);
+                if (BF) {
+#pragma unroll
+                    for (int a = 0; a < BN / 64; ++a) {   // bf16 hi / lo atoms of 64 columns, final layout
+                        tma_load_2d(st + 2 * Cfg::A_BYTES + a * 8192, &map_q, q0 + a * 64, row, &bars.raw_full[s]);
+                        if (!fast) tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + a * 8192, &map_q2, q0 + a * 64, row, &bars.raw_full[s]);
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < BN / 32; ++a)
+                        tma_load_2d(st + 2 * Cfg::A_BYTES + a * BOX_BYTES, &map_q, q0 + a * 32, row, &bars.raw_full[s]);
+                }
+            }
+        }
     };
 
     if (warp < TC_EPI_WARPS) {
@@ -834,36 +992,43 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
         // ============================ converters (both operands) ============================
         reg_dec_other();
         const int ct = warp < TC_MMA_WARP ? threadIdx.x - TC_EPI_WARPS * 32 : threadIdx.x - (TC_TMA_WARP + 1) * 32 + 128;
-        int it = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            int64_t r0;
-            int a0;
-            const int nblk = item_nkb(item, r0) * item_anchors(item, a0);
-            for (int kb = 0; kb < nblk; ++kb, ++it) {
-                const int s = it % STAGES;
-                mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
-                if (BF && PRE) {
-                    // both operands arrived in their final layout
-                } else if (BF) {
-                    const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
-                    // only P is converted here: Q (the narrow operand every P tile re-reads) was split to bf16
-                    // hi/lo once in global memory and arrives in its final layout through TMA
-                    for (int task = ct >> 5; task < KR / 4; task += TC_CONV_WARPS) convert_tn_rows4_bf16(st, task * 4, lane);
-                    fence_proxy_async();
-                } else if (passes == 3) {
-                    const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
-                    convert_region(st, Cfg::A_BYTES, Cfg::A_BYTES / 16, ct);
-                    convert_region(st + 2 * Cfg::A_BYTES, Cfg::B_BYTES, Cfg::B_BYTES / 16, ct);
-                    fence_proxy_async();
+        if (BF && PRE) {
+            // both operands arrive in their final layout: converter warps 0..2 are TMA issuers (P lo, Q hi, Q lo; the TMA
+            // warp issues P hi -- one issuing thread moves ~21 B/clk/SM, see tc_gemm_nt_pair_kernel), the MMA warp waits
+            // on raw_full alone
+            if ((ct >> 5) < 3) issue_loads((ct >> 5) + 1);
+            __syncwarp();
+        } else {
+            int it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                int64_t r0;
+                int a0;
+                const int nblk = item_nkb(item, r0) * item_anchors(item, a0);
+                for (int kb = 0; kb < nblk; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
+                    if (BF) {
+                        const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+                        // only P is converted here: Q (the narrow operand every P tile re-reads) was split to bf16
+                        // hi/lo once in global memory and arrives in its final layout through TMA
+                        for (int task = ct >> 5; task < KR / 4; task += TC_CONV_WARPS) convert_tn_rows4_bf16(st, task * 4, lane);
+                        fence_proxy_async();
+                    } else if (passes == 3) {
+                        const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+                        convert_region(st, Cfg::A_BYTES, Cfg::A_BYTES / 16, ct);
+                        convert_region(st + 2 * Cfg::A_BYTES, Cfg::B_BYTES, Cfg::B_BYTES / 16, ct);
+                        fence_proxy_async();
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.full[s]);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars.full[s]);
             }
         }
     } else if (warp == TC_MMA_WARP) {
         // ============================ MMA issuer ============================
+        // whole warp in the loop, one elected lane issues (uniform-register operands: see tc_gemm_nt_pair_kernel)
         reg_dec_other();
-        if (lane == 0) {
+        {
             const uint32_t idesc = BF ? make_idesc_bf16(TC_BM, BN, 1, 1) : make_idesc_tf32(TC_BM, BN, 1, 1);   // MN-major
             int it = 0, ci = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -881,7 +1046,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
                     for (int kb = kb0; kb < kb1; ++kb, ++it) {
                         const int s = it % STAGES;
                         mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
-                        mbar_wait_guard(&bars.full[s], (it / STAGES) & 1);
+                        if (!(BF && PRE)) mbar_wait_guard(&bars.full[s], (it / STAGES) & 1);
                         tc_fence_after();
                         const uint32_t p_hi = smem_base + s * Cfg::STAGE_BYTES;
                         const uint32_t p_lo = p_hi + Cfg::A_BYTES;
@@ -889,32 +1054,36 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
                         const uint32_t q_lo = q_hi + Cfg::B_BYTES;
                         const int64_t rrem = rows - (int64_t)(kb % nkb) * KR;
                         const int ksteps = rrem >= KR ? KR / UK : (int)((rrem + UK - 1) / UK);
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint32_t koff = ks * KSTEP_BYTES;   // one MMA's rows of R
-                            const uint64_t dp_hi = make_smem_desc(p_hi + koff, MN_LBO, K_SBO, L32);
-                            const uint64_t dq_hi = make_smem_desc(q_hi + koff, MN_LBO, K_SBO, L32);
-                            const uint32_t first = ((kb - kb0) | ks) != 0;
-                            if (BF && fast) {
-                                umma_bf16(d_tmem, dp_hi, dq_hi, idesc, first);
-                            } else if (BF) {
-                                const uint64_t dp_lo = make_smem_desc(p_lo + koff, MN_LBO, K_SBO, L32);
-                                const uint64_t dq_lo = make_smem_desc(q_lo + koff, MN_LBO, K_SBO, L32);
-                                umma_bf16(d_tmem, dp_lo, dq_hi, idesc, first);
-                                umma_bf16(d_tmem, dp_hi, dq_lo, idesc, 1);
-                                umma_bf16(d_tmem, dp_hi, dq_hi, idesc, 1);
-                            } else if (passes == 3) {
-                                const uint64_t dp_lo = make_smem_desc(p_lo + koff, MN_LBO, K_SBO, L32);
-                                const uint64_t dq_lo = make_smem_desc(q_lo + koff, MN_LBO, K_SBO, L32);
-                                umma_tf32(d_tmem, dp_lo, dq_hi, idesc, first);
-                                umma_tf32(d_tmem, dp_hi, dq_lo, idesc, 1);
-                                umma_tf32(d_tmem, dp_hi, dq_hi, idesc, 1);
-                            } else {
-                                umma_tf32(d_tmem, dp_hi, dq_hi, idesc, first);
+                        const uint64_t dp_hi0 = make_smem_desc(p_hi, MN_LBO, K_SBO, L32), dq_hi0 = make_smem_desc(q_hi, MN_LBO, K_SBO, L32);
+                        const uint64_t dp_lo0 = make_smem_desc(p_lo, MN_LBO, K_SBO, L32), dq_lo0 = make_smem_desc(q_lo, MN_LBO, K_SBO, L32);
+                        const bool first_kb = kb == kb0;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < KR / UK; ++ks) {
+                                if (ks < ksteps) {
+                                    const uint64_t o = (uint64_t)(ks * (KSTEP_BYTES >> 4));   // one MMA's rows of R
+                                    const uint32_t acc = (first_kb && ks == 0) ? 0u : 1u;
+                                    if (BF && fast) {
+                                        umma_bf16(d_tmem, dp_hi0 + o, dq_hi0 + o, idesc, acc);
+                                    } else if (BF) {
+                                        umma_bf16(d_tmem, dp_lo0 + o, dq_hi0 + o, idesc, acc);
+                                        umma_bf16(d_tmem, dp_hi0 + o, dq_lo0 + o, idesc, 1);
+                                        umma_bf16(d_tmem, dp_hi0 + o, dq_hi0 + o, idesc, 1);
+                                    } else if (passes == 3) {
+                                        umma_tf32(d_tmem, dp_lo0 + o, dq_hi0 + o, idesc, acc);
+                                        umma_tf32(d_tmem, dp_hi0 + o, dq_lo0 + o, idesc, 1);
+                                        umma_tf32(d_tmem, dp_hi0 + o, dq_hi0 + o, idesc, 1);
+                                    } else {
+                                        umma_tf32(d_tmem, dp_hi0 + o, dq_hi0 + o, idesc, acc);
+                                    }
+                                }
                             }
+                            umma_commit(&bars.empty[s]);
                         }
-                        umma_commit(&bars.empty[s]);
+                        __syncwarp();
                     }
-                    umma_commit(&bars.tfull[buf]);
+                    if (elect_one()) umma_commit(&bars.tfull[buf]);
+                    __syncwarp();
                 }
             }
         }
@@ -922,89 +1091,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
     } else {
         // ============================ TMA producer ============================
         reg_dec_other();
-        if (lane == 0) {
-            tma_prefetch_desc(&map_p);
-            tma_prefetch_desc(&map_q);
-            if (BF) tma_prefetch_desc(&map_q2);
-            // fast (bf16 single pass): the lo planes of Q, and of P when it arrives as planes, are not loaded
-            const uint32_t tx = BF ? ((PRE && fast) ? 1u : 2u) * (uint32_t)Cfg::A_BYTES + (fast ? 1u : 2u) * (uint32_t)Cfg::B_BYTES
-                                   : (uint32_t)Cfg::A_BYTES + (uint32_t)Cfg::B_BYTES;
-            constexpr uint32_t BOX_BYTES = BF ? 8192 : 4096;
-            int it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int tile = item % tiles;
-                const int p0 = (tile / q_tiles) * TC_BM, q0 = (tile % q_tiles) * BN;
-                int64_t r0;
-                int a0;
-                const int nkb = item_nkb(item, r0);
-                const int nblk = nkb * item_anchors(item, a0);
-                for (int kb = 0; kb < nblk; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
-                    unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
-                    const int row = (int)(r0 + (int64_t)(kb % nkb) * KR);
-                    mbar_arrive_expect_tx(&bars.raw_full[s], tx);
-                    if (ga.anchors > 0) {
-                        // gathered P: column (kk, c) of anchor `an` lives at X[point, table[an, kk], c]
-                        const int an = a0 + kb / nkb;
-                        if (PRE) {
-#pragma unroll
-                            for (int a = 0; a < TC_BM / 64; ++a) {       // bf16 planes: atoms of 64 columns, final layout
-                                const int cc = p0 + a * 64;
-                                const int kk = cc < Pw ? cc / ga.c : 0;
-                                const int c0 = cc < Pw ? cc - kk * ga.c : ga.c;                 // out of bounds: zeros
-                                const int mid = cc < Pw ? __ldg(ga.table + an * ga.kk_n + kk) : 0;
-                                tma_load_3d(st + a * 8192, &map_p, c0, mid, row, &bars.raw_full[s]);
-                                if (!fast) tma_load_3d(st + Cfg::A_BYTES + a * 8192, &map_p2, c0, mid, row, &bars.raw_full[s]);
-                            }
-                        } else
-#pragma unroll
-                        for (int a = 0; a < TC_BM / 32; ++a) {
-                            const int cc = p0 + a * 32;
-                            if (cc < Pw) {
-                                const int kk = cc / ga.c;
-                                tma_load_3d(st + a * BOX_BYTES, &map_p, cc - kk * ga.c, __ldg(ga.table + an * ga.kk_n + kk), row, &bars.raw_full[s]);
-                            } else {
-                                tma_load_3d(st + a * BOX_BYTES, &map_p, ga.c, 0, row, &bars.raw_full[s]);   // out of bounds: zeros
-                            }
-                        }
-                        if (BF) {
-#pragma unroll
-                            for (int a = 0; a < BN / 64; ++a) {
-                                tma_load_3d(st + 2 * Cfg::A_BYTES + a * 8192, &map_q, q0 + a * 64, an, row, &bars.raw_full[s]);
-                                if (!fast) tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + a * 8192, &map_q2, q0 + a * 64, an, row, &bars.raw_full[s]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int a = 0; a < BN / 32; ++a)
-                                tma_load_3d(st + 2 * Cfg::A_BYTES + a * BOX_BYTES, &map_q, q0 + a * 32, an, row, &bars.raw_full[s]);
-                        }
-                        continue;
-                    }
-                    if (PRE) {
-#pragma unroll
-                        for (int a = 0; a < TC_BM / 64; ++a) {
-                            tma_load_2d(st + a * 8192, &map_p, p0 + a * 64, row, &bars.raw_full[s]);
-                            if (!fast) tma_load_2d(st + Cfg::A_BYTES + a * 8192, &map_p2, p0 + a * 64, row, &bars.raw_full[s]);
-                        }
-                    } else
-#pragma unroll
-                    for (int a = 0; a < TC_BM / 32; ++a)
-                        tma_load_2d(st + a * BOX_BYTES, &map_p, p0 + a * 32, row, &bars.raw_full[s]);
-                    if (BF) {
-#pragma unroll
-                        for (int a = 0; a < BN / 64; ++a) {   // bf16 hi / lo atoms of 64 columns, final layout
-                            tma_load_2d(st + 2 * Cfg::A_BYTES + a * 8192, &map_q, q0 + a * 64, row, &bars.raw_full[s]);
-                            if (!fast) tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + a * 8192, &map_q2, q0 + a * 64, row, &bars.raw_full[s]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int a = 0; a < BN / 32; ++a)
-                            tma_load_2d(st + 2 * Cfg::A_BYTES + a * BOX_BYTES, &map_q, q0 + a * 32, row, &bars.raw_full[s]);
-                    }
-                }
-            }
-        }
+        issue_loads((BF && PRE) ? 0 : -1);
         __syncwarp();
     }
 
@@ -1058,8 +1145,8 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&bars.raw_full[s], 1);
-            mbar_init(&bars.full[s], 2 * TC_CONV_WARPS);
+            mbar_init(&bars.raw_full[s], PRE ? (fast ? 2 : 4) : 1);      // PRE: four issuing warps (see the NT pair kernel)
+            mbar_init(&bars.full[s], PRE ? 2 : 2 * TC_CONV_WARPS);
             mbar_init(&bars.empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -1085,6 +1172,90 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
         const int grp = (item / tiles) % n_groups;
         a0 = grp * anchors_per_item;
         return min(anchors_per_item, ga.anchors - a0);
+    };
+
+    // TMA issue loop of one thread.  which = -1: every box of every stage (raw fp32 P, converter path); PRE: which = 0: P hi,
+    // 1: P lo, 2: Q hi, 3: Q lo -- four issuing warps, see the NT pair kernel
+    auto issue_loads = [&](int which) {
+        if (which <= 0) tma_prefetch_desc(&map_p);
+        if (PRE && which == 1) tma_prefetch_desc(&map_p2);
+        if (which < 0 || which == 2) tma_prefetch_desc(&map_q);
+        if (which < 0 || which == 3) tma_prefetch_desc(&map_q2);
+        if (fast && (which == 1 || which == 3)) return;
+        const uint32_t tx = which < 0 ? 2u * (uint32_t)Cfg::A_BYTES + (fast ? 1u : 2u) * (uint32_t)Cfg::QH_BYTES
+                                      : (which < 2 ? (uint32_t)Cfg::A_BYTES : (uint32_t)Cfg::QH_BYTES);
+        int it = 0;
+        for (int item = pair; item < items; item += npairs) {
+            const int tile = item % tiles;
+            const int p0 = (2 * (tile / q_tiles) + (int)rank) * TC_BM;
+            const int q0 = (tile % q_tiles) * BN + (int)rank * (BN / 2);
+            int64_t r0;
+            int a0;
+            const int nkb = item_nkb(item, r0);
+            const int nblk = nkb * item_anchors(item, a0);
+            for (int kb = 0; kb < nblk; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
+                if (!elect_one()) continue;      // the warp runs the loop, one lane issues (uniform-register operands)
+                unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
+                unsigned char* sq = st + 2 * Cfg::A_BYTES;
+                const int row = (int)(r0 + (int64_t)(kb % nkb) * KR);
+                mbar_arrive_expect_tx(&bars.raw_full[s], tx);
+                const int an = ga.anchors > 0 ? a0 + kb / nkb : 0;
+                if (PRE) {
+                    if (which < 2) {
+                        const CUtensorMap* mp = which == 0 ? &map_p : &map_p2;
+                        unsigned char* dst = st + which * Cfg::A_BYTES;
+#pragma unroll
+                        for (int a = 0; a < TC_BM / 64; ++a) {
+                            const int cc = p0 + a * 64;
+                            if (ga.anchors > 0) {
+                                const int kk = cc < Pw ? cc / ga.c : 0;
+                                const int c0 = cc < Pw ? cc - kk * ga.c : ga.c;                 // out of bounds: zeros
+                                const int mid = cc < Pw ? __ldg(ga.table + an * ga.kk_n + kk) : 0;
+                                tma_load_3d(dst + a * 8192, mp, c0, mid, row, &bars.raw_full[s]);
+                            } else {
+                                tma_load_2d(dst + a * 8192, mp, cc, row, &bars.raw_full[s]);
+                            }
+                        }
+                    } else {
+                        const CUtensorMap* mq = which == 2 ? &map_q : &map_q2;
+                        unsigned char* dst = sq + (which - 2) * Cfg::QH_BYTES;
+#pragma unroll
+                        for (int a = 0; a < BN / 128; ++a) {
+                            if (ga.anchors > 0) tma_load_3d(dst + a * 8192, mq, q0 + a * 64, an, row, &bars.raw_full[s]);
+                            else tma_load_2d(dst + a * 8192, mq, q0 + a * 64, row, &bars.raw_full[s]);
+                        }
+                    }
+                    continue;
+                }
+                if (ga.anchors > 0) {
+#pragma unroll
+                    for (int a = 0; a < TC_BM / 32; ++a) {
+                        const int cc = p0 + a * 32;
+                        if (cc < Pw) {
+                            const int kk = cc / ga.c;
+                            tma_load_3d(st + a * 8192, &map_p, cc - kk * ga.c, __ldg(ga.table + an * ga.kk_n + kk), row, &bars.raw_full[s]);
+                        } else {
+                            tma_load_3d(st + a * 8192, &map_p, ga.c, 0, row, &bars.raw_full[s]);   // out of bounds: zeros
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < BN / 128; ++a) {
+                        tma_load_3d(sq + a * 8192, &map_q, q0 + a * 64, an, row, &bars.raw_full[s]);
+                        if (!fast) tma_load_3d(sq + Cfg::QH_BYTES + a * 8192, &map_q2, q0 + a * 64, an, row, &bars.raw_full[s]);
+                    }
+                    continue;
+                }
+#pragma unroll
+                for (int a = 0; a < TC_BM / 32; ++a) tma_load_2d(st + a * 8192, &map_p, p0 + a * 32, row, &bars.raw_full[s]);
+#pragma unroll
+                for (int a = 0; a < BN / 128; ++a) {
+                    tma_load_2d(sq + a * 8192, &map_q, q0 + a * 64, row, &bars.raw_full[s]);
+                    if (!fast) tma_load_2d(sq + Cfg::QH_BYTES + a * 8192, &map_q2, q0 + a * 64, row, &bars.raw_full[s]);
+                }
+            }
+        }
     };
 
     if (warp < TC_EPI_WARPS) {
@@ -1130,27 +1301,46 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
         // ============================ converters (own P columns) ============================
         reg_dec_other();
         const int ct = warp < TC_MMA_WARP ? threadIdx.x - TC_EPI_WARPS * 32 : threadIdx.x - (TC_TMA_WARP + 1) * 32 + 128;
-        int it = 0;
-        for (int item = pair; item < items; item += npairs) {
-            int64_t r0;
-            int a0;
-            const int nblk = item_nkb(item, r0) * item_anchors(item, a0);
-            for (int kb = 0; kb < nblk; ++kb, ++it) {
-                const int s = it % STAGES;
-                mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
-                if (!PRE) {
+        if (PRE) {      // converter warps 0..2 issue boxes (P lo, Q hi, Q lo), warp 3 forwards the barrier, 4 and 5 idle
+            const int cw = ct >> 5;
+            if (cw < 3) {
+                issue_loads(cw + 1);
+            } else if (cw == 3) {
+                int it = 0;
+                for (int item = pair; item < items; item += npairs) {
+                    int64_t r0;
+                    int a0;
+                    const int nblk = item_nkb(item, r0) * item_anchors(item, a0);
+                    for (int kb = 0; kb < nblk; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
+                        if (lane == 0) mbar_arrive_remote(&bars.full[s], 0);
+                    }
+                }
+            }
+            __syncwarp();
+        } else {
+            int it = 0;
+            for (int item = pair; item < items; item += npairs) {
+                int64_t r0;
+                int a0;
+                const int nblk = item_nkb(item, r0) * item_anchors(item, a0);
+                for (int kb = 0; kb < nblk; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait_guard(&bars.raw_full[s], (it / STAGES) & 1);
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
                     for (int task = ct >> 5; task < KR / 4; task += TC_CONV_WARPS) convert_tn_rows4_bf16(st, task * 4, lane);
                     fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(&bars.full[s], 0);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(&bars.full[s], 0);
             }
         }
     } else if (warp == TC_MMA_WARP) {
         // ============================ MMA issuer (leader CTA only) ============================
+        // whole warp in the loop, one elected lane issues (uniform-register operands: see tc_gemm_nt_pair_kernel)
         reg_dec_other();
-        if (rank == 0 && lane == 0) {
+        if (rank == 0) {
             const uint32_t idesc = make_idesc_bf16(2 * TC_BM, BN, 1, 1);   // MN-major
             int it = 0, ci = 0;
             for (int item = pair; item < items; item += npairs) {
@@ -1175,24 +1365,30 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
                         const uint32_t q_lo = q_hi + Cfg::QH_BYTES;
                         const int64_t rrem = rows - (int64_t)(kb % nkb) * KR;
                         const int ksteps = rrem >= KR ? KR / UK : (int)((rrem + UK - 1) / UK);
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint32_t koff = ks * KSTEP_BYTES;
-                            const uint64_t dp_hi = make_smem_desc(p_hi + koff, MN_LBO, K_SBO, 2);
-                            const uint64_t dq_hi = make_smem_desc(q_hi + koff, MN_LBO, K_SBO, 2);
-                            const uint64_t dp_lo = make_smem_desc(p_lo + koff, MN_LBO, K_SBO, 2);
-                            const uint64_t dq_lo = make_smem_desc(q_lo + koff, MN_LBO, K_SBO, 2);
-                            const uint32_t first = ((kb - kb0) | ks) != 0;
-                            if (fast) {
-                                umma_bf16_pair(d_tmem, dp_hi, dq_hi, idesc, first);
-                            } else {
-                                umma_bf16_pair(d_tmem, dp_lo, dq_hi, idesc, first);
-                                umma_bf16_pair(d_tmem, dp_hi, dq_lo, idesc, 1);
-                                umma_bf16_pair(d_tmem, dp_hi, dq_hi, idesc, 1);
+                        const uint64_t dp_hi0 = make_smem_desc(p_hi, MN_LBO, K_SBO, 2), dq_hi0 = make_smem_desc(q_hi, MN_LBO, K_SBO, 2);
+                        const uint64_t dp_lo0 = make_smem_desc(p_lo, MN_LBO, K_SBO, 2), dq_lo0 = make_smem_desc(q_lo, MN_LBO, K_SBO, 2);
+                        const bool first_kb = kb == kb0;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < KR / UK; ++ks) {
+                                if (ks < ksteps) {
+                                    const uint64_t o = (uint64_t)(ks * (KSTEP_BYTES >> 4));   // start-address field: address >> 4
+                                    const uint32_t acc = (first_kb && ks == 0) ? 0u : 1u;
+                                    if (fast) {
+                                        umma_bf16_pair(d_tmem, dp_hi0 + o, dq_hi0 + o, idesc, acc);
+                                    } else {
+                                        umma_bf16_pair(d_tmem, dp_lo0 + o, dq_hi0 + o, idesc, acc);
+                                        umma_bf16_pair(d_tmem, dp_hi0 + o, dq_lo0 + o, idesc, 1);
+                                        umma_bf16_pair(d_tmem, dp_hi0 + o, dq_hi0 + o, idesc, 1);
+                                    }
+                                }
                             }
+                            umma_commit_pair(&bars.empty[s]);
                         }
-                        umma_commit_pair(&bars.empty[s]);
+                        __syncwarp();
                     }
-                    umma_commit_pair(&bars.tfull[buf]);
+                    if (elect_one()) umma_commit_pair(&bars.tfull[buf]);
+                    __syncwarp();
                 }
             }
         }
@@ -1200,75 +1396,7 @@ tc_gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_c
     } else {
         // ============================ TMA producer (both CTAs: own P columns, own half of Q) ============
         reg_dec_other();
-        if (lane == 0) {
-            tma_prefetch_desc(&map_p);
-            tma_prefetch_desc(&map_q);
-            tma_prefetch_desc(&map_q2);
-            const uint32_t tx = ((PRE && fast) ? 1u : 2u) * (uint32_t)Cfg::A_BYTES + (fast ? 1u : 2u) * (uint32_t)Cfg::QH_BYTES;
-            int it = 0;
-            for (int item = pair; item < items; item += npairs) {
-                const int tile = item % tiles;
-                const int p0 = (2 * (tile / q_tiles) + (int)rank) * TC_BM;
-                const int q0 = (tile % q_tiles) * BN + (int)rank * (BN / 2);
-                int64_t r0;
-                int a0;
-                const int nkb = item_nkb(item, r0);
-                const int nblk = nkb * item_anchors(item, a0);
-                for (int kb = 0; kb < nblk; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait_guard(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
-                    unsigned char* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
-                    unsigned char* sq = st + 2 * Cfg::A_BYTES;
-                    const int row = (int)(r0 + (int64_t)(kb % nkb) * KR);
-                    mbar_arrive_expect_tx(&bars.raw_full[s], tx);
-                    if (ga.anchors > 0) {
-                        const int an = a0 + kb / nkb;
-                        if (PRE) {
-#pragma unroll
-                            for (int a = 0; a < TC_BM / 64; ++a) {
-                                const int cc = p0 + a * 64;
-                                const int kk = cc < Pw ? cc / ga.c : 0;
-                                const int c0 = cc < Pw ? cc - kk * ga.c : ga.c;                 // out of bounds: zeros
-                                const int mid = cc < Pw ? __ldg(ga.table + an * ga.kk_n + kk) : 0;
-                                tma_load_3d(st + a * 8192, &map_p, c0, mid, row, &bars.raw_full[s]);
-                                if (!fast) tma_load_3d(st + Cfg::A_BYTES + a * 8192, &map_p2, c0, mid, row, &bars.raw_full[s]);
-                            }
-                        } else
-#pragma unroll
-                        for (int a = 0; a < TC_BM / 32; ++a) {
-                            const int cc = p0 + a * 32;
-                            if (cc < Pw) {
-                                const int kk = cc / ga.c;
-                                tma_load_3d(st + a * 8192, &map_p, cc - kk * ga.c, __ldg(ga.table + an * ga.kk_n + kk), row, &bars.raw_full[s]);
-                            } else {
-                                tma_load_3d(st + a * 8192, &map_p, ga.c, 0, row, &bars.raw_full[s]);   // out of bounds: zeros
-                            }
-                        }
-#pragma unroll
-                        for (int a = 0; a < BN / 128; ++a) {
-                            tma_load_3d(sq + a * 8192, &map_q, q0 + a * 64, an, row, &bars.raw_full[s]);
-                            if (!fast) tma_load_3d(sq + Cfg::QH_BYTES + a * 8192, &map_q2, q0 + a * 64, an, row, &bars.raw_full[s]);
-                        }
-                        continue;
-                    }
-                    if (PRE) {
-#pragma unroll
-                        for (int a = 0; a < TC_BM / 64; ++a) {
-                            tma_load_2d(st + a * 8192, &map_p, p0 + a * 64, row, &bars.raw_full[s]);
-                            if (!fast) tma_load_2d(st + Cfg::A_BYTES + a * 8192, &map_p2, p0 + a * 64, row, &bars.raw_full[s]);
-                        }
-                    } else
-#pragma unroll
-                    for (int a = 0; a < TC_BM / 32; ++a)
-                        tma_load_2d(st + a * 8192, &map_p, p0 + a * 32, row, &bars.raw_full[s]);
-#pragma unroll
-                    for (int a = 0; a < BN / 128; ++a) {
-                        tma_load_2d(sq + a * 8192, &map_q, q0 + a * 64, row, &bars.raw_full[s]);
-                        if (!fast) tma_load_2d(sq + Cfg::QH_BYTES + a * 8192, &map_q2, q0 + a * 64, row, &bars.raw_full[s]);
-                    }
-                }
-            }
-        }
+        issue_loads(PRE ? 0 : -1);
         __syncwarp();
     }
 
@@ -1462,8 +1590,9 @@ static int launch_nt_pair(int64_t M, int N, int K, const void* A, const void* Bh
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    static const int dbg = getenv("VGTKB_DBG") ? atoi(getenv("VGTKB_DBG")) : 0;      // timing experiments only
     VGTKB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mhi, mlo, mc, tma_out, bias, C, M, N, K, default_chunk(3, true, fast != 0), ga, ma2,
-                                  fast));
+                                  fast | (dbg << 4)));
     return check_launch("gemm_nt(tcgen05, cta pairs)");
 }
 

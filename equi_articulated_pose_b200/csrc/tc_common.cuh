@@ -11,6 +11,18 @@ namespace tc {
 // ---- warp helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// one lane of a converged warp (elect.sync): the code around it stays warp-uniform, so descriptors and addresses live in
+// uniform registers and a tcgen05.mma issues without the per-operand R2UR election loop a `lane == 0` region compiles to
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- tcgen05 fences ---------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
