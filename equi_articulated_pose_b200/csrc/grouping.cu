@@ -14,6 +14,10 @@
 namespace vgtkb {
 using namespace tc;
 
+// timing experiments (VGTKB_DBG_GROUP; results are garbage): fwd 1 = no tensor-map stores, 2 = no gathers, 4 = no MMAs;
+// bwd 1 = no tensor-map loads, 2 = no atomics, 4 = no MMAs
+__constant__ int c_dbg_group;
+
 constexpr int IG_WARPS = 8;
 constexpr int IG_MAXNN = 128;
 constexpr int IG_KP = 24;  // padded kernel-point count handled by the fast path (K <= 24)
@@ -801,7 +805,9 @@ inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p
     __shared__ float s_g[16 * KS * 3];
     __shared__ uint32_t s_off[16 * KS];
     const int pi = blockIdx.x, b = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then treats it (and the staging address, the row coordinate ...) as
+    // warp-uniform, so the tensor-map stores below take their operands from uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int gid = lane >> 2, tig = lane & 3;
     // per warp: two staging tiles [24 rows][128 B], 1024-byte aligned (swizzle atom = 8 rows x 128 B)
     float* stage = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)) + warp * (2 * 24 * 32);
@@ -826,6 +832,13 @@ inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p
     const float* fb = feats + (size_t)b * n * a * ci + 4 * gid;
     int sb = 0;                                                    // staging tile of the next chunk
     float4 v[KS][4];                                               // gathered neighbour rows of the chunk in flight
+    const int dbg = c_dbg_group;
+    if (dbg & 2) {
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[s][j] = make_float4(1.f, 2.f, 3.f, 4.f);
+    }
     for (int ai = warp; ai < a; ai += IG_WARPS) {
         uint32_t bh[KS][3][2], bl[KS][3][2];
 #pragma unroll
@@ -854,7 +867,7 @@ inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p
         }
         const int row0 = (((b * p + pi) * a) + ai) * k;            // first row of this (point, anchor) in G [rows, ci]
         const float* fa = fb + (size_t)ai * ci;
-        if (ai == warp) {                                          // first chunk of the warp; later ones are prefetched
+        if (ai == warp && !(dbg & 2)) {                            // first chunk of the warp; later ones are prefetched
 #pragma unroll
             for (int s = 0; s < KS; ++s)
 #pragma unroll
@@ -877,7 +890,7 @@ inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p
                 // store sequence below would otherwise keep these loads from overlapping it
                 const bool more_c = c0 + 32 < ci;
                 const float* nf = more_c ? fa + c0 + 32 : fa + (size_t)IG_WARPS * ci;
-                if (more_c || ai + IG_WARPS < a) {
+                if ((more_c || ai + IG_WARPS < a) && !(dbg & 2)) {
 #pragma unroll
                     for (int s = 0; s < KS; ++s)
 #pragma unroll
@@ -891,6 +904,7 @@ inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p
                 for (int t = 0; t < 3; ++t)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) d[m][t][e] = 0.f;
+            if (!(dbg & 4))
 #pragma unroll
             for (int s = 0; s < KS; ++s)
 #pragma unroll
@@ -902,7 +916,8 @@ inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p
                         ig_mma(d[m][t], ah[s][m], bh[s][t][0], bh[s][t][1]);
                     }
             // the store that used this staging tile two chunks ago must have read it
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            // (elect.sync names the same lane every time: bulk async-groups belong to the issuing thread)
+            if (!(dbg & 1) && tc::elect_one()) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             __syncwarp();
             float* st = stage + sb * (24 * 32);
             if (PL) {
@@ -933,14 +948,14 @@ inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            if (!(dbg & 1) && tc::elect_one()) {
                 tma_store_2d(&map_g, st, c0, row0);                // k rows x 128 B (box rows = k); PL: k rows x 64 B, hi
                 if (PL) tma_store_2d(&map_lo, reinterpret_cast<unsigned char*>(st) + 24 * 64, c0, row0);
                 bulk_commit();
             }
         }
     }
-    if (lane == 0) bulk_wait_all();
+    if (tc::elect_one()) bulk_wait_all();
 }
 
 template <int KS>
@@ -954,7 +969,7 @@ inter_group_bwd_mma_tl_kernel(const __grid_constant__ TmaMap map_dg, int n, int 
     __shared__ uint32_t s_off[16 * KS];
     __shared__ __align__(8) uint64_t s_bar[IG_WARPS][2];
     const int pi = blockIdx.x, b = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
     const int gid = lane >> 2, tig = lane & 3;
     float* stage = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)) + warp * (2 * 24 * 32);
     igt_neighbourhood<KS>(b, pi, n, p, nn, a, ci, xyz, sxyz, idx, s_g, s_off);
@@ -986,8 +1001,9 @@ inter_group_bwd_mma_tl_kernel(const __grid_constant__ TmaMap map_dg, int n, int 
     const int chunks = ci / 32;
     const int my_anchors = (a - warp + IG_WARPS - 1) / IG_WARPS;
     const int items = my_anchors * chunks;                          // item -> (anchor slot, 32-channel chunk)
+    const int dbg = c_dbg_group;
     auto issue = [&](int item) {
-        if (lane == 0) {
+        if (!(dbg & 1) && tc::elect_one()) {
             const int ai = warp + (item / chunks) * IG_WARPS, c0 = (item % chunks) * 32, buf = item & 1;
             mbar_arrive_expect_tx(&s_bar[warp][buf], (uint32_t)k * 128u);
             tma_load_2d(stage + buf * (24 * 32), &map_dg, c0, (((b * p + pi) * a) + ai) * k, &s_bar[warp][buf]);
@@ -1025,7 +1041,7 @@ inter_group_bwd_mma_tl_kernel(const __grid_constant__ TmaMap map_dg, int n, int 
                 ig_split2(w[4], w[5], bh[t][2], bl[t][2]);
             }
         }
-        mbar_wait(&s_bar[warp][buf], (uint32_t)(item >> 1) & 1u);
+        if (!(dbg & 1)) mbar_wait(&s_bar[warp][buf], (uint32_t)(item >> 1) & 1u);
         const float* in = stage + buf * (24 * 32);
         float4 v[6];
 #pragma unroll
@@ -1053,6 +1069,7 @@ inter_group_bwd_mma_tl_kernel(const __grid_constant__ TmaMap map_dg, int n, int 
                 for (int e = 0; e < 4; ++e) d[m][e] = 0.f;
                 const uint32_t h16[4] = {ah[m][0], ah[m][1], ah[m][2], ah[m][3]};
                 const uint32_t l16[4] = {al[m][0], al[m][1], al[m][2], al[m][3]};
+                if (dbg & 4) continue;
                 ig_mma(d[m], l16, bh[t][0], bh[t][1]);
                 ig_mma(d[m], h16, bl[t][0], bl[t][1]);
                 ig_mma(d[m], h16, bh[t][0], bh[t][1]);
@@ -1061,6 +1078,10 @@ inter_group_bwd_mma_tl_kernel(const __grid_constant__ TmaMap map_dg, int n, int 
                 ig_mma_k8(d[m], ah[m][4], ah[m][5], bh[t][2]);
             }
             const int n0 = 8 * t + 2 * tig;
+            if (dbg & 2) {
+                if (d[0][0] + d[1][1] == 12345.678f) ga[0] = d[0][2];      // keep the MMAs alive
+                continue;
+            }
             if (n0 < nn) atomicAdd(reinterpret_cast<float4*>(ga + off[t][0]), make_float4(d[0][0], d[0][2], d[1][0], d[1][2]));
             if (n0 + 1 < nn) atomicAdd(reinterpret_cast<float4*>(ga + off[t][1]), make_float4(d[0][1], d[0][3], d[1][1], d[1][3]));
         }
@@ -1472,17 +1493,26 @@ inter_group_fwd_c1_kernel(int n, int p, int nn, int a, int k, const float* __res
     __syncthreads();
     const float* fb = feats + (size_t)b * n * a;
     for (int ai = warp; ai < a; ai += IG_WARPS) {
+        float kx = 0.f, ky = 0.f, kz = 0.f;
         if (lane < k) {
             const float* kp = rk + (ai * k + lane) * 3;
-            const float kx = __ldg(kp), ky = __ldg(kp + 1), kz = __ldg(kp + 2);
-            float acc = 0.f;
-            for (int ni = 0; ni < nn; ++ni) {
+            kx = __ldg(kp), ky = __ldg(kp + 1), kz = __ldg(kp + 2);
+        }
+        float acc = 0.f;
+        for (int base = 0; base < nn; base += 32) {
+            // the 32 neighbour features of this anchor in ONE load instruction (lane <-> neighbour), handed to the kernel-
+            // point lanes by shuffles: the first version issued a dependent global load per (kernel point, neighbour)
+            const float f = base + lane < nn ? __ldg(fb + (size_t)s_j[base + lane] * a + ai) : 0.f;
+            const int cnt = nn - base < 32 ? nn - base : 32;
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                const int ni = base + i;
                 const float dx = s_g[ni * 3] - kx, dy = s_g[ni * 3 + 1] - ky, dz = s_g[ni * 3 + 2] - kz;
                 const float w = fmaxf(0.f, 1.f - (dx * dx + dy * dy + dz * dz) * inv_sigma);
-                acc = fmaf(w, __ldg(fb + (size_t)s_j[ni] * a + ai), acc);
+                acc = fmaf(w, __shfl_sync(0xffffffffu, f, i), acc);
             }
-            grouped[(((size_t)b * p + pi) * a + ai) * (size_t)k + lane] = acc;
         }
+        if (lane < k) grouped[(((size_t)b * p + pi) * a + ai) * (size_t)k + lane] = acc;
     }
 }
 
@@ -1641,9 +1671,18 @@ static int launch_group_fwd_gen(const TmaMap& mh, const TmaMap& ml, int b, int n
 // G as bf16 planes [b*p*a, k*ci]: hi and lo (fast = 0, the bf16x3 operand format) or hi only (fast = 1, single-pass bf16;
 // g_lo unused) -- the forward grouping of vgtkb_inter_conv_forward.  VGTKB_EUNSUP for shapes the warp-MMA kernels do not
 // take (k > 24, nn > 64, ci % 32 != 0, misaligned / too large tensors).
+static void set_dbg_group() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const int v = getenv("VGTKB_DBG_GROUP") ? atoi(getenv("VGTKB_DBG_GROUP")) : 0;
+    cudaMemcpyToSymbol(c_dbg_group, &v, sizeof(int));
+}
+
 int inter_group_forward_planes(int b, int n, int p, int nn, int a, int k, int ci, const float* xyz, const float* sample_xyz,
                                const int32_t* idx, const float* rot_kernels, float sigma, const float* feats, void* g_hi,
                                void* g_lo, int fast, cudaStream_t st) {
+    set_dbg_group();
     const int64_t g_rows = (int64_t)b * p * a * k;
     if (k > 24 || nn > 64 || ci % 32 != 0 || !aligned16(feats) || !aligned16(g_hi) || (!fast && !aligned16(g_lo)) ||
         (int64_t)n * a * ci >= ((int64_t)1 << 32) || g_rows >= ((int64_t)1 << 31) || b > 65535)
@@ -1698,6 +1737,7 @@ static int launch_group_bwd_gen(const TmaMap& map, int b, int n, int p, int nn, 
 int inter_group_backward_gen(int b, int n, int p, int nn, int a, int k, int ci, const float* xyz, const float* sample_xyz,
                              const int32_t* idx, const float* rot_kernels, float sigma, const float* grad_grouped,
                              float* grad_feats, int fast, cudaStream_t st) {
+    set_dbg_group();
     const int64_t g_rows = (int64_t)b * p * a * k;
     if (k > 24 || nn > 64 || ci % 32 != 0 || !aligned16(grad_feats) || !aligned16(grad_grouped) ||
         (int64_t)n * a * ci >= ((int64_t)1 << 32) || g_rows >= ((int64_t)1 << 31) || b > 65535)

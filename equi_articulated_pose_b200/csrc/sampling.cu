@@ -160,28 +160,36 @@ fps_kernel(int n, int m, int log2bs, int iters, int plain, const float* __restri
     }
     int old = 0;
     if (tid == 0) out[0] = 0;
+    // rank / iters, rank % iters: iters is 1 or 2 up to 2047 points (a shift and a mask); general division otherwise
+    const bool ip2 = (iters & (iters - 1)) == 0;
+    const uint32_t ilog = 31u - (uint32_t)__clz(iters), imask = (uint32_t)iters - 1u;
     for (int j = 1; j < m; ++j) {
         const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
-        unsigned long long best = 0ull;
+        uint32_t bhi = 0u, blo = 0u;                     // best (distance bits | sign flag, inverted rank) of this thread
 #pragma unroll
         for (int i = 0; i < PPT; ++i) {
             if (valid[i]) {
                 const float d = sq3(px[i] - x1, py[i] - y1, pz[i] - z1);
                 const float d2 = fminf(d, tmp[i]);
                 tmp[i] = d2;
-                const unsigned long long key =
-                    ((unsigned long long)(__float_as_uint(d2) | 0x80000000u) << 32) | inv[i];
-                best = key > best ? key : best;
+                const uint32_t hi = __float_as_uint(d2) | 0x80000000u;
+                const bool better = hi > bhi || (hi == bhi && inv[i] > blo);
+                bhi = better ? hi : bhi;
+                blo = better ? inv[i] : blo;
             }
         }
-        best = warp_max_u64(best);
-        if (lane == 0) red[j & 1][warp] = best;
+        // lexicographic maximum over the warp in two hardware reductions (redux.sync) instead of five 64-bit shuffle steps
+        uint32_t whi = __reduce_max_sync(0xffffffffu, bhi);
+        uint32_t wlo = __reduce_max_sync(0xffffffffu, bhi == whi ? blo : 0u);
+        if (lane == 0) red[j & 1][warp] = ((unsigned long long)whi << 32) | wlo;
         __syncthreads();
-        unsigned long long v = red[j & 1][lane < THREADS / 32 ? lane : 0];
-        v = warp_max_u64(v);
-        if (v >> 63) {
-            const uint32_t rank = 0xffffffffu - (uint32_t)v;
-            const uint32_t br = rank / (uint32_t)iters, it = rank % (uint32_t)iters;
+        const unsigned long long rv = red[j & 1][lane < THREADS / 32 ? lane : 0];
+        const uint32_t rhi = (uint32_t)(rv >> 32), rlo = (uint32_t)rv;
+        whi = __reduce_max_sync(0xffffffffu, rhi);
+        wlo = __reduce_max_sync(0xffffffffu, rhi == whi ? rlo : 0u);
+        if (whi >> 31) {
+            const uint32_t rank = 0xffffffffu - wlo;
+            const uint32_t br = ip2 ? rank >> ilog : rank / (uint32_t)iters, it = ip2 ? rank & imask : rank % (uint32_t)iters;
             const uint32_t tr = log2bs ? (__brev(br) >> (32 - log2bs)) : 0u;
             old = plain ? (int)rank : (int)(it * (uint32_t)bs + tr);
         } else {
@@ -280,9 +288,10 @@ static int fps_dispatch(int b, int n, int m, int plain, const float* xyz, int32_
     while ((2 << log2bs) <= n && log2bs < 10) ++log2bs;
     const int bs = 1 << log2bs;
     const int iters = (n + bs - 1) / bs;
-    if (n <= 512) return launch_fps<1, 512>(b, n, m, log2bs, iters, plain, xyz, idx, st);
-    if (n <= 1024) return launch_fps<2, 512>(b, n, m, log2bs, iters, plain, xyz, idx, st);
-    if (n <= 2048) return launch_fps<4, 512>(b, n, m, log2bs, iters, plain, xyz, idx, st);
+    // few warps per cloud: a round is a latency chain (distance update, two warp reductions, one barrier), not throughput
+    if (n <= 512) return launch_fps<4, 128>(b, n, m, log2bs, iters, plain, xyz, idx, st);
+    if (n <= 1024) return launch_fps<4, 256>(b, n, m, log2bs, iters, plain, xyz, idx, st);
+    if (n <= 2048) return launch_fps<8, 256>(b, n, m, log2bs, iters, plain, xyz, idx, st);
     if (n <= 4096) return launch_fps<8, 512>(b, n, m, log2bs, iters, plain, xyz, idx, st);
     if (n <= 8192) return launch_fps<8, 1024>(b, n, m, log2bs, iters, plain, xyz, idx, st);
     return launch_fps<16, 1024>(b, n, m, log2bs, iters, plain, xyz, idx, st);
