@@ -7,7 +7,7 @@
 
 #include "../../include/vgtkb.h"
 
-#define VGTKB_ABI_VERSION 11
+#define VGTKB_ABI_VERSION 12
 
 namespace vgtkb {
 

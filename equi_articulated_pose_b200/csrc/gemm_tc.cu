@@ -396,7 +396,7 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                        const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c, int tma_out,
                        const float* __restrict__ bias, float* __restrict__ C, int64_t M, int N, int K, int chunk_kb, TcGather ga,
                        const __grid_constant__ CUtensorMap map_a2, int fast_in) {
-    // bits 4.. of fast_in: timing experiments (VGTKB_DBG; results are garbage): 1 = no MMAs are issued, 2 = no TMA loads
+    // bits 4.. of fast_in: timing experiments (VGTKB_DBG; results are garbage): 1 = no MMAs are issued, 2 = no TMA loads, 4 = no output stores
     const int fast = fast_in & 15, dbg = fast_in >> 4;
     // fast != 0: single-pass bf16 (contraction mode 4, BASELINE config 3): only the hi planes take part -- one MMA per k-step
     // instead of three, and the lo planes are neither loaded (PRE) nor used
@@ -546,7 +546,7 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     }
                     fence_proxy_async();                      // generic-proxy writes -> visible to the bulk-copy engine
                     __syncwarp();
-                    if (lane == 0 && colj < N && row0 < M) {  // rows / columns beyond M / N are clipped by the tensor map
+                    if (lane == 0 && colj < N && row0 < M && !(dbg & 4)) {  // rows / columns beyond M / N are clipped by the tensor map
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_c),
                                      "r"(stg), "r"(colj), "r"((int)row0)
                                      : "memory");
@@ -576,7 +576,7 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     float4 o = ld_shared_v4(stg + (uint32_t)(rr * 128 + ((c4 ^ (rr & 7)) << 4)));
                     o.x += bb[0]; o.y += bb[1]; o.z += bb[2]; o.w += bb[3];
                     const int64_t grow = row0 + rr;
-                    if (grow < M) {
+                    if (grow < M && !(dbg & 4)) {
                         float* dst = C + (grow * a_cnt + an) * N + col;
                         if (vec_ok && col + 4 <= N) {
                             *reinterpret_cast<float4*>(dst) = o;

@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgtkb200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _lib = None
 _device_ok = set()
@@ -36,6 +36,9 @@ SIGNATURES = {
     "vgtkb_pose_neighbourhood": [c_int] * 4 + [c_vp] * 7,
     "vgtkb_inter_pose_group_forward": [c_int] * 6 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
     "vgtkb_inter_pose_group_backward": [c_int] * 6 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
+    "vgtkb_pose_neighbourhood_strided": [c_int] * 5 + [c_vp] * 9,
+    "vgtkb_inter_pose_group_forward_strided": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
+    "vgtkb_inter_pose_group_backward_strided": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
     "vgtkb_inter_zpconv_forward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_inter_zpconv_backward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_vp],
     "vgtkb_intra_zpconv_forward": [c_int] * 7 + [c_vp, c_vp, c_vp, c_vp, c_vp],

@@ -283,32 +283,41 @@ class InterConvFn(torch.autograd.Function):
         return gx, gw, None, None, None, None, None
 
 
-def pose_neighbourhood(xyz, pose, idx, anchors, with_perm=True):
-    """xyz [B,3,N], pose [B,N,4,4], idx [B,N,nn] int32, anchors [A,3,3] -> rotated neighbour offsets [B,N,nn,3] and the
-    anchor permutation table [B,N,nn,A] uint8 (None when with_perm is False)."""
+def pose_neighbourhood(xyz, pose, idx, anchors, with_perm=True, sample_xyz=None, sample_idx=None):
+    """xyz [B,3,N], pose [B,N,4,4], idx [B,P,nn] int32, anchors [A,3,3] -> rotated neighbour offsets [B,P,nn,3] and the
+    anchor permutation table [B,P,nn,A] uint8 (None when with_perm is False).  Strided layers pass the P centres:
+    sample_xyz [B,3,P] = xyz[sample_idx], sample_idx [B,P] (their rotations are pose[sample_idx]); default P = N."""
     xyz, pose, idx, anchors = _f32(xyz), _f32(pose), _i32(idx), _f32(anchors)
     b, _, n = xyz.shape
-    nn, a = idx.shape[2], anchors.shape[0]
-    rel = torch.empty((b, n, nn, 3), dtype=torch.float32, device=xyz.device)
-    perm = torch.empty((b, n, nn, a), dtype=torch.uint8, device=xyz.device) if with_perm else None
-    call("vgtkb_pose_neighbourhood", xyz.device, b, n, nn, a, ptr(xyz), ptr(pose), ptr(idx), ptr(anchors), ptr(rel), ptr(perm))
+    p, nn, a = idx.shape[1], idx.shape[2], anchors.shape[0]
+    if sample_idx is None:
+        if p != n:
+            raise _lib.VgtkbError("pose_neighbourhood: idx has P != N centres but no sample_idx / sample_xyz was given")
+        sxyz, sidx = xyz, None
+    else:
+        sxyz, sidx = _f32(sample_xyz), _i32(sample_idx)
+    rel = torch.empty((b, p, nn, 3), dtype=torch.float32, device=xyz.device)
+    perm = torch.empty((b, p, nn, a), dtype=torch.uint8, device=xyz.device) if with_perm else None
+    call("vgtkb_pose_neighbourhood_strided", xyz.device, b, n, p, nn, a, ptr(xyz), ptr(pose), ptr(sxyz), ptr(sidx), ptr(idx),
+         ptr(anchors), ptr(rel), ptr(perm))
     return rel, perm
 
 
 class PoseGroupFn(torch.autograd.Function):
-    """Pose-aware inter grouping: feats X [B,N,A,Ci] -> G [B,N,A,K*Ci] with rotated offsets and anchor permutation."""
+    """Pose-aware inter grouping: feats X [B,N,A,Ci] -> G [B,P,A,K*Ci] with rotated offsets and anchor permutation
+    (P = idx.shape[1] centres; P = N without stride)."""
 
     @staticmethod
     def forward(ctx, feats, idx, rel_xyz, perm, rot_kernels, sigma):
         feats = _f32(feats)
         b, n, a, ci = feats.shape
-        nn, k = idx.shape[2], rot_kernels.shape[1]
-        g = torch.empty((b, n, a, k * ci), dtype=torch.float32, device=feats.device)
-        call("vgtkb_inter_pose_group_forward", feats.device, b, n, nn, a, k, ci, ptr(idx), ptr(rel_xyz), ptr(perm),
+        p, nn, k = idx.shape[1], idx.shape[2], rot_kernels.shape[1]
+        g = torch.empty((b, p, a, k * ci), dtype=torch.float32, device=feats.device)
+        call("vgtkb_inter_pose_group_forward_strided", feats.device, b, n, p, nn, a, k, ci, ptr(idx), ptr(rel_xyz), ptr(perm),
              ptr(rot_kernels), float(sigma), ptr(feats), ptr(g))
         ctx.save_for_backward(idx, rel_xyz, rot_kernels)
         ctx.perm = perm
-        ctx.meta = (b, n, nn, a, k, ci, float(sigma))
+        ctx.meta = (b, n, p, nn, a, k, ci, float(sigma))
         return g
 
     @staticmethod
@@ -316,10 +325,10 @@ class PoseGroupFn(torch.autograd.Function):
         if not ctx.needs_input_grad[0]:
             return (None,) * 6
         idx, rel_xyz, rot_kernels = ctx.saved_tensors
-        b, n, nn, a, k, ci, sigma = ctx.meta
+        b, n, p, nn, a, k, ci, sigma = ctx.meta
         grad_g = _f32(grad_g)
         gx = torch.zeros((b, n, a, ci), dtype=torch.float32, device=grad_g.device)
-        call("vgtkb_inter_pose_group_backward", grad_g.device, b, n, nn, a, k, ci, ptr(idx), ptr(rel_xyz), ptr(ctx.perm),
+        call("vgtkb_inter_pose_group_backward_strided", grad_g.device, b, n, p, nn, a, k, ci, ptr(idx), ptr(rel_xyz), ptr(ctx.perm),
              ptr(rot_kernels), sigma, ptr(grad_g), ptr(gx))
         return gx, None, None, None, None, None
 

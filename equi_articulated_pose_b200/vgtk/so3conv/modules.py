@@ -11,6 +11,7 @@ import torch.nn.functional as F
 from vgtk.spconv import SphericalPointCloud, SphericalPointCloudPose
 import vgtk.pc as pctk
 from . import functional as L
+import vgtk.spconv.functional as zptk_F
 from equi_articulated_pose_b200 import ops as _ops
 
 KERNEL_CONDENSE_RATIO = 0.7
@@ -118,16 +119,27 @@ class InterSO3PoseConv(InterSO3Conv):
             return idx, w, sample_idx, SphericalPointCloudPose(out.xyz, out.feats, self.anchors, sampled_pose)
         if self.use_2d or self.use_art_mode:
             raise NotImplementedError("InterSO3PoseConv: the 2D / articulation-mode groupings are not reached by the shipped flags")
-        if self.stride != 1:
-            raise NotImplementedError("InterSO3PoseConv with a non-identity pose: only stride 1 (what model 38 builds) is implemented")
         xyz = x.xyz.contiguous()
-        idx = pctk.ball_query_index(xyz, xyz, self.radius, self.n_neighbor)
-        rel_xyz, perm = _ops.pose_neighbourhood(xyz, pose, idx, self.anchors, with_perm=self.permute_modes != 0)
+        if self.stride > 1:
+            # strided branch (functional.py:931-1029): FPS / lazy sampling of the centres, ball query of the centres in the
+            # full cloud, centre rotations pose[sample_idx] (spconv/functional.py:468-500)
+            idx, sample_idx, sample_xyz = zptk_F.ball_indices(xyz, self.stride, self.radius, self.n_neighbor, self.lazy_sample)
+            sample_xyz = sample_xyz.contiguous()
+            sampled_pose = torch.gather(pose, 1, sample_idx.long().view(*sample_idx.shape, 1, 1).expand(-1, -1, 4, 4))
+            rel_xyz, perm = _ops.pose_neighbourhood(xyz, pose, idx, self.anchors, with_perm=self.permute_modes != 0,
+                                                    sample_xyz=sample_xyz, sample_idx=sample_idx)
+        else:
+            idx = pctk.ball_query_index(xyz, xyz, self.radius, self.n_neighbor)
+            sample_idx, sample_xyz, sampled_pose = None, xyz, pose
+            rel_xyz, perm = _ops.pose_neighbourhood(xyz, pose, idx, self.anchors, with_perm=self.permute_modes != 0)
         feats_cl = x.feats.permute(0, 2, 3, 1).contiguous()
         g = _ops.PoseGroupFn.apply(feats_cl, idx, rel_xyz, perm, self.rot_kernels(), self.sigma)
-        b, n, a, kc = g.shape
+        b, p, a, kc = g.shape
         k = self.kernel_size
-        feats = self.basic_conv(g.view(b, n, a, k, kc // k).permute(0, 4, 3, 1, 2))
+        feats = self.basic_conv(g.view(b, p, a, k, kc // k).permute(0, 4, 3, 1, 2))
+        if self.stride > 1:
+            # the reference clears inter_idx after a strided layer (:1029)
+            return None, None, sample_idx, SphericalPointCloudPose(sample_xyz, feats, self.anchors, sampled_pose)
         w = L.LazyInterWeights(xyz, xyz, idx, self.rot_kernels(), self.sigma)
         return idx, w, None, SphericalPointCloudPose(xyz, feats, self.anchors, pose)
 

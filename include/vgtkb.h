@@ -141,6 +141,19 @@ int vgtkb_inter_pose_group_forward(int b, int n, int nn, int a, int k, int ci, c
 int vgtkb_inter_pose_group_backward(int b, int n, int nn, int a, int k, int ci, const int32_t* idx, const float* rel_xyz,
                                     const uint8_t* perm, const float* rot_kernels, float sigma, const float* grad_grouped,
                                     float* grad_feats, void* stream);
+/* The strided branch of the same function (so3conv/functional.py:896-1060; sampling and ball query as in
+ * spconv/functional.py:468-500): p = ceil(n / stride) centres sample_xyz [b,3,p] = xyz[sample_idx], centre rotations
+ * pose[sample_idx] (sample_idx [b,p] int32; NULL = the identity map, which needs p == n), idx [b,p,nn] into the n points.
+ * rel_xyz [b,p,nn,3], perm [b,p,nn,a], G [b,p,a,k,c]; X and grad_feats stay [b,n,a,c]. */
+int vgtkb_pose_neighbourhood_strided(int b, int n, int p, int nn, int a, const float* xyz, const float* pose,
+                                     const float* sample_xyz, const int32_t* sample_idx, const int32_t* idx,
+                                     const float* anchors, float* rel_xyz, uint8_t* perm, void* stream);
+int vgtkb_inter_pose_group_forward_strided(int b, int n, int p, int nn, int a, int k, int ci, const int32_t* idx,
+                                           const float* rel_xyz, const uint8_t* perm, const float* rot_kernels, float sigma,
+                                           const float* feats, float* grouped, void* stream);
+int vgtkb_inter_pose_group_backward_strided(int b, int n, int p, int nn, int a, int k, int ci, const int32_t* idx,
+                                            const float* rel_xyz, const uint8_t* perm, const float* rot_kernels, float sigma,
+                                            const float* grad_grouped, float* grad_feats, void* stream);
 
 /* vgtk.cuda.zpconv.{inter,intra}_zpconv_{forward,backward} (zpconv_cuda.cpp:113-118, kernels
  * zpconv_cuda_kernel.cu:33-195), reference layouts, explicit index/weight tensors:

@@ -88,29 +88,36 @@ def intra_group_feats(intra_idx, feats):
     return feats.index_select(3, intra_idx.reshape(-1).long()).view(b, c, p, a, k).permute(0, 1, 4, 2, 3).contiguous()
 
 
-def pose_inter_group_feats(xyz, pose, feats, idx, anchors, kernels, sigma, permute_modes=0):
-    """Pose-aware inter grouping, no-stride branch of inter_so3poseconv_grouping_strided
-    (vgtk/vgtk/so3conv/functional.py:1061-1261).  xyz [B,3,N], pose [B,N,4,4], feats [B,C,N,A], idx [B,N,nn] ->
-    (G [B,C,K,N,A], grouped_xyz [B,3,N,nn], rotated_anchor_idx [B,N,nn,A]).
+def pose_inter_group_feats(xyz, pose, feats, idx, anchors, kernels, sigma, permute_modes=0, sample_xyz=None, sample_idx=None):
+    """Pose-aware inter grouping, both branches of inter_so3poseconv_grouping_strided
+    (vgtk/vgtk/so3conv/functional.py:896-1060 strided, :1061-1261 no stride).  xyz [B,3,N], pose [B,N,4,4],
+    feats [B,C,N,A], idx [B,P,nn] -> (G [B,C,K,P,A], grouped_xyz [B,3,P,nn], rotated_anchor_idx [B,P,nn,A]).
+    Strided: the P centres are sample_xyz [B,3,P] = xyz[sample_idx] with rotations pose[sample_idx]
+    (vgtk/vgtk/spconv/functional.py:468-500); default: every point is a centre.
       R_rel[p,n] = R_p R_{j(p,n)}^T ;  g'[p,n] = R_rel (x_j - x_p) ;  w = relu(1 - |g' - R_a kappa_k|^2 / sigma)
       pi[p,n,a] = argmax_{a'} tr((R_rel^T R_a) R_{a'}^T)      (only applied when permute_modes != 0)
       G[b,c,k,p,a] = sum_n w[b,p,a,k,n] feats[b,c,j(p,n), pi[p,n,a] or a]"""
     b, _, n = xyz.shape
-    nn_ = idx.shape[2]
+    p, nn_ = idx.shape[1], idx.shape[2]
     a = anchors.shape[0]
     R = pose[:, :, :3, :3]
     li = idx.long()
-    Rj = torch.gather(R, 1, li.reshape(b, n * nn_, 1, 1).expand(-1, -1, 3, 3)).view(b, n, nn_, 3, 3)
-    rel = torch.matmul(R.unsqueeze(2), Rj.transpose(3, 4))                               # [B,N,nn,3,3]
-    g = torch.gather(xyz, 2, li.reshape(b, 1, -1).expand(-1, 3, -1)).view(b, 3, n, nn_) - xyz.unsqueeze(-1)
+    if sample_idx is None:
+        Rp, cxyz = R, xyz
+    else:
+        Rp = torch.gather(R, 1, sample_idx.long().view(b, p, 1, 1).expand(-1, -1, 3, 3))
+        cxyz = sample_xyz
+    Rj = torch.gather(R, 1, li.reshape(b, p * nn_, 1, 1).expand(-1, -1, 3, 3)).view(b, p, nn_, 3, 3)
+    rel = torch.matmul(Rp.unsqueeze(2), Rj.transpose(3, 4))                              # [B,P,nn,3,3]
+    g = torch.gather(xyz, 2, li.reshape(b, 1, -1).expand(-1, 3, -1)).view(b, 3, p, nn_) - cxyz.unsqueeze(-1)
     g = torch.matmul(rel, g.permute(0, 2, 3, 1).unsqueeze(-1)).squeeze(-1).permute(0, 3, 1, 2).contiguous()
     w = anchor_weights(g, anchors, kernels, sigma)
-    rot_anchors = torch.matmul(rel.transpose(-1, -2).unsqueeze(3), anchors)              # [B,N,nn,A,3,3]
+    rot_anchors = torch.matmul(rel.transpose(-1, -2).unsqueeze(3), anchors)              # [B,P,nn,A,3,3]
     tr = torch.einsum('bpnaij,cij->bpnac', rot_anchors, anchors)                         # tr(M R_c^T) = <M, R_c>
-    pi = tr.argmax(-1)                                                                   # [B,N,nn,A]
+    pi = tr.argmax(-1)                                                                   # [B,P,nn,A]
     c = feats.shape[1]
     f = feats.permute(0, 2, 3, 1)                                                        # [B,N,A,C]
-    gf = torch.gather(f, 1, li.reshape(b, n * nn_, 1, 1).expand(-1, -1, a, c)).view(b, n, nn_, a, c)
+    gf = torch.gather(f, 1, li.reshape(b, p * nn_, 1, 1).expand(-1, -1, a, c)).view(b, p, nn_, a, c)
     if permute_modes != 0:
         gf = torch.gather(gf, 3, pi.unsqueeze(-1).expand(-1, -1, -1, -1, c))
     G = torch.einsum('bpnac,bpakn->bckpa', gf, w).contiguous()

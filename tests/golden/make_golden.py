@@ -12,6 +12,7 @@ Writes (all small):
   tests/golden/ref_weights_small.npz  inter_so3conv_grouping_anchor + grouping einsum
   tests/golden/ref_intrazp_small.npz, ref_pose_group_small.npz, ref_pointnet_small.npz (`make_golden.py pointnet`)
   tests/golden/ref_pointnet2_small.npz  PointnetPP encoder-decoder (SPConvNets/models/PointNet2.py), fwd (`make_golden.py pointnet2`)
+  tests/golden/ref_pose_group_strided_small.npz  strided branch of inter_so3poseconv_grouping_strided (`make_golden.py pose_strided`)
 """
 import contextlib
 import io
@@ -64,6 +65,36 @@ def make_pointnet():
                     f'a{na}_grad_weight': head.embed.weight.grad.numpy(), f'a{na}_grad_bias': head.embed.bias.grad.numpy()})
     np.savez_compressed(os.path.join(GOLD, "ref_pointnet_small.npz"), **out)
     print("pointnet", out['a60_pooled'].shape, out['a1_pooled'].shape)
+
+
+def make_pose_strided():
+    """Strided branch of inter_so3poseconv_grouping_strided (so3conv/functional.py:931-1029) with random per-point
+    rotations: stride 2, FPS sampling (lazy_sample False) and lazy sampling, permute_modes 0 and 1."""
+    H.import_blocks()
+    import vgtk.so3conv.functional as L
+    from scipy.spatial.transform import Rotation
+    anc = torch.from_numpy(L.get_anchors(60))
+    g = torch.Generator().manual_seed(1005)
+    nb, npt, nnb, cc = 1, 32, 6, 5
+    pxyz = (torch.rand(nb, 3, npt, generator=g) - 0.5)
+    rot = torch.from_numpy(Rotation.random(nb * npt, random_state=11).as_matrix().astype('float32')).view(nb, npt, 3, 3)
+    ppose = torch.eye(4).repeat(nb, npt, 1, 1)
+    ppose[:, :, :3, :3] = rot
+    pfeats = torch.randn(nb, cc, npt, 60, generator=g)
+    pk = torch.from_numpy(L.get_sphereical_kernel_points_from_ply(0.7 * 0.5, 1))
+    outp = {'xyz': pxyz.numpy(), 'pose': ppose.numpy(), 'feats': pfeats.numpy(), 'kernels': pk.numpy(),
+            'radius': np.float32(0.5), 'sigma': np.float32(0.12), 'nn': np.int32(nnb), 'stride': np.int32(2)}
+    for lazy in (0, 1):
+        for pm in ((0, 1) if lazy == 0 else (1,)):
+            with contextlib.redirect_stdout(io.StringIO()):
+                r = L.inter_so3poseconv_grouping_strided(pxyz, ppose, pfeats, 2, nnb, anc, pk, 0.5, 0.12, None, None, bool(lazy),
+                                                         permute_modes=pm)
+            outp[f'grouped_lazy{lazy}_pm{pm}'] = r[3].numpy()
+            outp[f'sample_idx_lazy{lazy}'] = r[4].numpy()
+            outp[f'new_xyz_lazy{lazy}'] = r[2].numpy()
+            outp[f'sampled_pose_lazy{lazy}'] = r[5].numpy()
+    np.savez_compressed(os.path.join(GOLD, "ref_pose_group_strided_small.npz"), **outp)
+    print("pose grouping (strided)", r[3].shape)
 
 
 def make_pointnet2():
@@ -123,6 +154,8 @@ def make_pointnet2():
 
 def main():
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1 and sys.argv[1] == "pose_strided":
+        return make_pose_strided()
     if len(sys.argv) > 1 and sys.argv[1] == "pointnet2":
         return make_pointnet2()
     if len(sys.argv) > 1 and sys.argv[1] == "pointnet":      # only this fixture (the others stay untouched)

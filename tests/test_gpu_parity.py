@@ -612,6 +612,53 @@ def test_pose_conv_module_non_identity(dev):
     assert not torch.allclose(o_rot.feats, o_pl.feats)
 
 
+@pytest.mark.parametrize("lazy,pm", [(0, 0), (0, 1), (1, 1)])
+def test_pose_grouping_strided_matches_reference_fixture(dev, ops, lazy, pm):
+    """Strided branch of the pose grouping (functional.py:931-1029) against the reference's own output
+    (tests/golden/ref_pose_group_strided_small.npz): kernels forward, permutation table bit-exact vs the oracle, backward
+    against the oracle's autograd; and the module (sampling + ball query + kernels + BasicSO3Conv) against oracle + fixture."""
+    from oracle import so3 as O
+    from equi_articulated_pose_b200 import so3_constants as C
+    import equi_articulated_pose_b200 as eap
+    eap.install()
+    import vgtk.so3conv as sptk
+    import vgtk.spconv as zptk
+    import vgtk.so3conv.functional as L
+    g = np.load(os.path.join(GOLD, "ref_pose_group_strided_small.npz"))
+    xyz, pose = torch.from_numpy(g["xyz"]), torch.from_numpy(g["pose"])
+    feats = torch.from_numpy(g["feats"]).requires_grad_(True)
+    anchors, kern = torch.from_numpy(C.anchors_all()), torch.from_numpy(g["kernels"])
+    stride, radius, sigma, nn_ = int(g["stride"]), float(g["radius"]), float(g["sigma"]), int(g["nn"])
+    _, idx, sidx, sxyz = O.ball_grouping(xyz, stride, radius, nn_, bool(lazy))
+    G_ref, _, pi_ref = O.pose_inter_group_feats(xyz, pose, feats, idx, anchors, kern, sigma, pm, sxyz, sidx)
+    go = torch.randn(G_ref.shape, generator=torch.Generator().manual_seed(4))
+    (G_ref * go).sum().backward()
+
+    rel, perm = ops.pose_neighbourhood(xyz.to(dev), pose.to(dev), idx.to(dev).int(), anchors.to(dev), with_perm=pm != 0,
+                                       sample_xyz=sxyz.contiguous().to(dev), sample_idx=sidx.to(dev).int())
+    if pm:
+        assert torch.equal(perm.cpu().long(), pi_ref)
+    rk = L.rotated_kernels(anchors.to(dev), kern.to(dev))
+    x = feats.detach().permute(0, 2, 3, 1).contiguous().to(dev).requires_grad_(True)
+    G = ops.PoseGroupFn.apply(x, idx.to(dev).int(), rel, perm, rk, sigma)
+    b, p, a, kc = G.shape
+    assert p == xyz.shape[2] // stride
+    G_log = G.view(b, p, a, 24, kc // 24).permute(0, 4, 3, 1, 2)
+    assert rel_err(G_log, torch.from_numpy(g[f"grouped_lazy{lazy}_pm{pm}"])) < 1e-5
+    (G_log * go.to(dev)).sum().backward()
+    assert rel_err(x.grad.permute(0, 3, 1, 2), feats.grad) < 1e-5
+
+    # module level: same sampling, same neighbourhoods, pose of the centres, BasicSO3Conv on top
+    torch.manual_seed(0)
+    conv = sptk.InterSO3PoseConv(5, 8, 1, stride, radius, sigma, nn_, lazy_sample=bool(lazy), kanchor=60, permute_modes=pm).to(dev)
+    r_idx, r_w, s_idx, out = conv(zptk.SphericalPointCloudPose(xyz.to(dev), feats.detach().to(dev), None, pose.to(dev)))
+    assert r_idx is None and torch.equal(s_idx.cpu().long(), torch.from_numpy(g[f"sample_idx_lazy{lazy}"]).long())
+    assert torch.equal(out.xyz.cpu(), torch.from_numpy(g[f"new_xyz_lazy{lazy}"]))
+    assert torch.equal(out.pose.cpu(), torch.from_numpy(g[f"sampled_pose_lazy{lazy}"]))
+    want = O.basic_conv(conv.basic_conv.W.detach().cpu().double(), torch.from_numpy(g[f"grouped_lazy{lazy}_pm{pm}"]).double())
+    assert rel_err(out.feats, want.float()) < 1e-4
+
+
 # ------------------------------------------------------------------------------ anchor-orbit chamfer (model 38 loss)
 def _orbit_case(b, a, m, n, seed):
     from oracle import so3 as O

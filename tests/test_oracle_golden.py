@@ -224,6 +224,25 @@ def test_pose_grouping_matches_reference(golden_dir):
     assert torch.allclose(G0, O.inter_group_feats(idx, w, feats), atol=1e-6)
 
 
+def test_pose_grouping_strided_matches_reference(golden_dir):
+    """Strided branch (functional.py:931-1029, stride 2): centres by FPS / lazy sampling, their rotations pose[sample_idx],
+    neighbours from the full cloud -- against the reference's own outputs (sample indices, centre poses, grouped features)."""
+    g = _load(golden_dir, "ref_pose_group_strided_small.npz")
+    xyz, pose, feats = torch.from_numpy(g["xyz"]), torch.from_numpy(g["pose"]), torch.from_numpy(g["feats"])
+    anchors, kern = torch.from_numpy(C.anchors_all()), torch.from_numpy(g["kernels"])
+    for lazy in (0, 1):
+        _, idx, sidx, sxyz = O.ball_grouping(xyz, int(g["stride"]), float(g["radius"]), int(g["nn"]), bool(lazy))
+        assert torch.equal(sidx.long(), torch.from_numpy(g[f"sample_idx_lazy{lazy}"]).long())
+        assert torch.equal(sxyz, torch.from_numpy(g[f"new_xyz_lazy{lazy}"]))
+        sp = torch.gather(pose, 1, sidx.long().view(*sidx.shape, 1, 1).expand(-1, -1, 4, 4))
+        assert torch.equal(sp, torch.from_numpy(g[f"sampled_pose_lazy{lazy}"]))
+        for pm in ((0, 1) if lazy == 0 else (1,)):
+            G, _, _ = O.pose_inter_group_feats(xyz, pose, feats, idx, anchors, kern, float(g["sigma"]), pm, sxyz, sidx)
+            ref = torch.from_numpy(g[f"grouped_lazy{lazy}_pm{pm}"])
+            assert G.shape == ref.shape
+            assert (G - ref).abs().max() / ref.abs().max() < 1e-5, (lazy, pm)
+
+
 def test_anchor_orbit_chamfer_oracle_vs_fp64_bruteforce():
     """oracle.so3.anchor_orbit_chamfer (the unfused reference path of model 38's reconstruction loss, built on the pinned
     chamfer restatement) against a float64 brute-force evaluation."""
