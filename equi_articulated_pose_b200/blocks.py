@@ -64,10 +64,11 @@ class FusedBatchNorm2d(nn.BatchNorm2d):
     sync_group = None
     planes_fwd = False      # the result feeds a tensor-core contraction: also write its bf16 operand planes
     planes_bwd = False      # the input comes from a contraction: write the planes of its gradient in backward
+    counter_managed = False # num_batches_tracked is a view of the owning model's flat counter, bumped once per step there
 
     def forward_rows(self, rows, slope, residual=None):
         training = self.training or not self.track_running_stats
-        if training and self.track_running_stats and self.num_batches_tracked is not None:
+        if training and self.track_running_stats and self.num_batches_tracked is not None and not self.counter_managed:
             self.num_batches_tracked += 1
         if self.momentum is None:       # torch: cumulative moving average when momentum is None
             mom = 1.0 / max(float(self.num_batches_tracked), 1.0) if training and self.num_batches_tracked is not None else 0.0
@@ -341,8 +342,30 @@ class SO3Backbone(nn.Module):
         self.backbone = nn.ModuleList([BasicSO3ConvBlock(p) for p in params])
         self.na_in = na
 
+    def _bump_counters(self):
+        """All `num_batches_tracked` buffers of the fused BatchNorm layers live in ONE int64 tensor (views; state-dict keys and
+        values unchanged) and are incremented by one launch per step instead of one per layer (14 launches in the classic
+        backbone).  Rebuilt when the module moved to another device."""
+        bns = [m for m in self.modules() if isinstance(m, FusedBatchNorm2d) and m.track_running_stats
+               and m.num_batches_tracked is not None]
+        if not bns:
+            return
+        flat = getattr(self, '_nbt_flat', None)
+        dev = bns[0].num_batches_tracked.device
+        ok = flat is not None and flat.device == dev and flat.numel() == len(bns) and all(
+            m.counter_managed and m.num_batches_tracked.data_ptr() == flat[i].data_ptr() for i, m in enumerate(bns))
+        if not ok:
+            flat = torch.stack([m.num_batches_tracked.detach().reshape(()) for m in bns]).to(dev)
+            for i, m in enumerate(bns):
+                m._buffers['num_batches_tracked'] = flat[i]
+                m.counter_managed = True
+            self._nbt_flat = flat
+        flat += 1
+
     def forward(self, points):
         """points [B,N,3] -> SphericalPointCloud (xyz [B,3,P], feats logical [B,C,P,A])."""
+        if self.training:
+            self._bump_counters()
         x = preprocess_input(points, self.na_in, False)
         for block in self.backbone:
             x = block(x)
