@@ -211,7 +211,7 @@ class PointnetSO3Conv(nn.Module):
     def forward(self, x):
         xyz, feats = x.xyz, x.feats
         nb, nc, npt, na = feats.shape
-        xc = (xyz - xyz.mean(2, keepdim=True)).contiguous()
+        xc = (xyz - xyz.mean(2, keepdim=True)).contiguous() if getattr(self, 'center', True) else xyz.contiguous()
         w = self.embed.weight.view(self.dim_out, self.dim_in)
         w_f, w_x = w[:, :nc].contiguous(), w[:, nc:]
         if na == 1:

@@ -13,6 +13,7 @@ Writes (all small):
   tests/golden/ref_intrazp_small.npz, ref_pose_group_small.npz, ref_pointnet_small.npz (`make_golden.py pointnet`)
   tests/golden/ref_pointnet2_small.npz  PointnetPP encoder-decoder (SPConvNets/models/PointNet2.py), fwd (`make_golden.py pointnet2`)
   tests/golden/ref_pose_group_strided_small.npz  strided branch of inter_so3poseconv_grouping_strided (`make_golden.py pose_strided`)
+  tests/golden/ref_heads_small.npz  invariant heads of base_so3conv.py (InvOutBlockR / Pointnet / MVD / Ours / OursWithMask), fwd + bwd (`make_golden.py heads`)
 """
 import contextlib
 import io
@@ -97,6 +98,70 @@ def make_pose_strided():
     print("pose grouping (strided)", r[3].shape)
 
 
+HEAD_CASES = [
+    # name, class, constructor kwargs, params overrides
+    ("r_att", "InvOutBlockR", {}, {"pooling": "attention"}),
+    ("r_max", "InvOutBlockR", {}, {"pooling": "max"}),
+    ("pn_max", "InvOutBlockPointnet", {}, {"pooling": "max"}),
+    ("mvd", "InvOutBlockMVD", {}, {}),
+    ("ours_max", "InvOutBlockOurs", {"pooling_method": "max"}, {}),
+    ("mask_att", "InvOutBlockOursWithMask", {"norm": 1, "pooling_method": "attention", "use_pointnet": True}, {}),
+]
+
+
+def head_inputs():
+    g = torch.Generator().manual_seed(1006)
+    nb, c, npt, na = 2, 16, 16, 60
+    feats = torch.randn(nb, c, npt, na, generator=g)
+    xyz = torch.rand(nb, 3, npt, generator=g) - 0.5
+    mask = (torch.rand(nb, npt, generator=g) > 0.3).float()
+    soft = torch.rand(nb, npt, generator=g)
+    return feats, xyz, mask, soft
+
+
+def head_params(over):
+    p = {"dim_in": 16, "mlp": [32, 64], "fc": [64], "k": 8, "kanchor": 60, "temperature": 3.0}
+    p.update(over)
+    return p
+
+
+def make_heads():
+    """The invariant heads (SPConvNets/utils/base_so3conv.py:481-645, 766-840, 1013-1150), train mode, fwd + bwd on the
+    reference's own modules; every tensor output contributes sum(out * fixed random tensor) to the loss."""
+    M = H.import_blocks()
+    import vgtk.so3conv as sptk
+    feats0, xyz, mask, soft = head_inputs()
+    out = {"feats": feats0.numpy(), "xyz": xyz.numpy(), "mask": mask.numpy(), "soft_mask": soft.numpy()}
+    anc = torch.from_numpy(sptk.get_anchors(60))
+    for name, cls, kw, over in HEAD_CASES:
+        torch.manual_seed(100 + len(name))
+        with contextlib.redirect_stdout(io.StringIO()):
+            head = getattr(M, cls)(head_params(over), **kw)
+        head.train()
+        feats = feats0.clone().requires_grad_(True)
+        if cls == "InvOutBlockR":
+            res = head(feats)
+        elif cls == "InvOutBlockOursWithMask":
+            res = head(sptk.SphericalPointCloud(xyz, feats, anc), mask, soft_mask=soft)
+        else:
+            res = head(sptk.SphericalPointCloud(xyz, feats, anc))
+        res = res if isinstance(res, tuple) else (res,)
+        gg = torch.Generator().manual_seed(7)
+        loss = 0
+        for i, r in enumerate(res):
+            w = torch.randn(r.shape, generator=gg)
+            loss = loss + (r * w).sum()
+            out[f"{name}_out{i}"] = r.detach().numpy()
+        loss.backward()
+        out[f"{name}_grad_feats"] = feats.grad.numpy()
+        for k, v in head.state_dict().items():
+            out[f"{name}_sd_{k}"] = v.numpy()
+        for k, v in head.named_parameters():
+            out[f"{name}_pg_{k}"] = v.grad.numpy() if v.grad is not None else np.zeros(0, np.float32)
+    np.savez_compressed(os.path.join(GOLD, "ref_heads_small.npz"), **out)
+    print("heads", [n for n, *_ in HEAD_CASES])
+
+
 def make_pointnet2():
     """PointnetPP (SPConvNets/models/PointNet2.py:8-196), train-mode forward with return_global=True on two clouds of 600
     points, in_feat_dim = 6 (x = 3 extra channels).  Weights come from oracle.pointnet2.make_state (numpy RandomState, so the
@@ -154,6 +219,8 @@ def make_pointnet2():
 
 def main():
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1 and sys.argv[1] == "heads":
+        return make_heads()
     if len(sys.argv) > 1 and sys.argv[1] == "pose_strided":
         return make_pose_strided()
     if len(sys.argv) > 1 and sys.argv[1] == "pointnet2":
