@@ -200,16 +200,28 @@ class SeparableSO3ConvBlock(nn.Module):
 
     def forward(self, x, inter_idx, inter_w):
         skip = x.feats
-        inter_idx, inter_w, sample_idx, y = self.inter_conv(x, inter_idx, inter_w)
-        # skip branch first, so that its result rides along as the residual of the last fused pass
         b, ci, n, a = skip.shape
+        # the block input feeds the inter conv and the skip branch: in backward the skip branch (recorded later, run first)
+        # deposits its input gradient in the slot and the inter conv's scatter adds onto it (ops.GradSlot)
+        slot = None
+        if self.training and skip.requires_grad and skip.is_cuda and self.inter_conv.conv.pooling is None and os.environ.get("VGTKB_GRAD_SLOT", "1") != "0":
+            slot = _ops.GradSlot((b, n, a, ci))
+            self.inter_conv.conv._grad_slot = slot
+        inter_idx, inter_w, sample_idx, y = self.inter_conv(x, inter_idx, inter_w)
+        self.inter_conv.conv._grad_slot = None
+        if slot is not None and not slot.armed:
+            slot = None                             # the conv did not take the fused path: ordinary autograd accumulation
+        # skip branch first, so that its result rides along as the residual of the last fused pass
         srows = skip.permute(0, 2, 3, 1)
         if self.stride > 1:
-            srows = _ops.RowGatherFn.apply(srows.reshape(b, n, a * ci), sample_idx.to(torch.int32).contiguous())
+            srows = _ops.RowGatherFn.apply(srows.reshape(b, n, a * ci), sample_idx.to(torch.int32).contiguous(), slot)
+            lin_slot = None
+        else:
+            lin_slot = slot
         p = srows.shape[1]
         srows = srows.reshape(b * p * a, ci)
         w = self.skip_conv.weight.view(self.skip_conv.out_channels, ci)
-        srows = _ops.LinearFn.apply(srows, w, self.skip_conv.bias)
+        srows = _ops.LinearFn.apply(srows, w, self.skip_conv.bias, None, lin_slot)
         srows = _apply_norm(self.norm, srows, b, self.slope)
         if self.use_intra:
             y = self.intra_conv(y, residual_rows=srows)

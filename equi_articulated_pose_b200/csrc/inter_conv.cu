@@ -78,6 +78,10 @@ extern "C" int vgtkb_inter_conv_backward(int b, int n, int p, int nn, int a, int
                                          const void* grad_out_hi, const void* grad_out_lo, float* grad_grouped,
                                          float* grad_feats, float* grad_w, float* workspace, int mode, void* stream) {
     VGTKB_REQUIRE(conv_shape_ok(b, n, p, nn, a, k, ci, co), "inter_conv_backward: unsupported shape");
+    // mode | 256: grad_feats already holds a gradient (the skip branch's) and the scatter ADDS to it -- no memset here, no
+    // separate add afterwards
+    const bool accumulate = (mode & 256) != 0;
+    mode &= 255;
     VGTKB_REQUIRE(mode == 3 || mode == 4, "inter_conv_backward: mode %d (3 = bf16x3, 4 = single-pass bf16)", mode);
     const int fast = mode == 4;
     cudaStream_t st = (cudaStream_t)stream;
@@ -102,7 +106,7 @@ extern "C" int vgtkb_inter_conv_backward(int b, int n, int p, int nn, int a, int
                  : tc_gemm_nt(rows, kc, co, grad_out, wt, nullptr, grad_grouped, fast ? 7 : 6, wsplit, st);
         if (rc == VGTKB_EUNSUP) set_error("inter_conv_backward: dG contraction shape not covered (co %% 8 == 0, aligned operands)");
         if (rc) return rc;
-        VGTKB_CUDA(cudaMemsetAsync(grad_feats, 0, sizeof(float) * (size_t)b * n * a * ci, st));
+        if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(grad_feats, 0, sizeof(float) * (size_t)b * n * a * ci, st));
         rc = inter_group_backward_gen(b, n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels, sigma, grad_grouped, grad_feats, fast, st);
         if (rc == VGTKB_EUNSUP)
             rc = vgtkb_inter_group_backward(b, n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels, sigma, grad_grouped, grad_feats,

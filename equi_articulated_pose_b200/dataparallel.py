@@ -95,9 +95,9 @@ class FlatGradBucket:
 
     def all_reduce_mean(self, group=None):
         """One collective for the whole model; averages over ranks like DDP does."""
-        self.collect()
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
-            return
+            return                              # one rank: nothing to exchange, the gradients stay where backward wrote them
+        self.collect()
         dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=group)
         self._flat.div_(dist.get_world_size(group))
 

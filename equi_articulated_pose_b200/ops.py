@@ -240,6 +240,25 @@ def inter_conv_supported(b, n, p, nn, a, k, ci, co):
     return _GEMM_MODE in (3, 4) and bool(_lib.load().vgtkb_inter_conv_supported(b, n, p, nn, a, k, ci, co))
 
 
+class GradSlot:
+    """Hand-over of a gradient between the two consumers of a block's input (the skip branch and the inter conv):
+    backward runs the skip branch first (it was recorded later), which DEPOSITS its input gradient here and returns None;
+    InterConvFn.backward then lets the scatter kernel add onto the deposited buffer (mode | 256) and returns the sum --
+    instead of a memset of its own buffer plus autograd's separate add.  `closed` is set once the inter conv's backward has
+    run: a later deposit attempt (other execution order, second backward over a retained graph) returns its gradient the
+    normal way."""
+
+    def __init__(self, shape):
+        self.shape, self.buf, self.closed, self.armed = tuple(shape), None, False, False
+
+    def deposit(self, g):
+        """g: contiguous fp32 tensor holding the gradient in [B,N,A,Ci] order; True if it was taken."""
+        if self.closed or not self.armed or self.buf is not None or g.numel() != self.shape[0] * self.shape[1] * self.shape[2] * self.shape[3]:
+            return False
+        self.buf = g.view(self.shape)
+        return True
+
+
 class InterConvFn(torch.autograd.Function):
     """InterSO3Conv in one call per direction (vgtkb_inter_conv_forward / _backward): feats X [B,N,A,Ci] channels-last,
     w_kc [Co, K*Ci] -> out [B*P*A, Co].  The grouped tensor exists only as the two bf16 operand planes the grouping
@@ -247,9 +266,12 @@ class InterConvFn(torch.autograd.Function):
     so3conv/modules.py:48-55."""
 
     @staticmethod
-    def forward(ctx, feats, w_kc, xyz, sample_xyz, idx, rot_kernels, sigma):
+    def forward(ctx, feats, w_kc, xyz, sample_xyz, idx, rot_kernels, sigma, slot=None):
         feats, w_kc = _f32(feats), _f32(w_kc)
         b, n, a, ci = feats.shape
+        ctx.slot = slot if (slot is not None and slot.shape == (b, n, a, ci) and feats.requires_grad) else None
+        if ctx.slot is not None:
+            ctx.slot.armed = True
         p, nn = idx.shape[1], idx.shape[2]
         k, co = rot_kernels.shape[1], w_kc.shape[0]
         dev = feats.device
@@ -273,14 +295,22 @@ class InterConvFn(torch.autograd.Function):
         dev = gy.device
         rows, kc = b * p * a, k * ci
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        gx = torch.empty((b, n, a, ci), dtype=torch.float32, device=dev) if need_x else None
+        acc = None
+        if ctx.slot is not None:
+            acc, ctx.slot.buf, ctx.slot.closed = ctx.slot.buf, None, True
+        if acc is not None and need_x:
+            gx, mode = acc, mode | 256                  # the skip branch's gradient: the scatter adds onto it
+        else:
+            gx = torch.empty((b, n, a, ci), dtype=torch.float32, device=dev) if need_x else None
         dg = torch.empty((rows, kc), dtype=torch.float32, device=dev) if need_x else None
         gw = torch.empty((co, kc), dtype=torch.float32, device=dev) if need_w else None
         ws = torch.empty(max(rows * co, 2 * kc * co), dtype=torch.float32, device=dev)
-        gy_hi, gy_lo = take_planes(gy) if mode == 3 else (None, None)
+        gy_hi, gy_lo = take_planes(gy) if (mode & 255) == 3 else (None, None)
         call("vgtkb_inter_conv_backward", dev, b, n, p, nn, a, k, ci, co, ptr(xyz), ptr(sample_xyz), ptr(idx), ptr(rot_kernels),
              sigma, ptr(w_kc), ptr(g_hi), ptr(g_lo), ptr(gy), ptr(gy_hi), ptr(gy_lo), ptr(dg), ptr(gx), ptr(gw), ptr(ws), mode)
-        return gx, gw, None, None, None, None, None
+        if acc is not None and not need_x:
+            raise _lib.VgtkbError("InterConvFn: a skip-branch gradient was deposited but the input gradient is not requested")
+        return gx, gw, None, None, None, None, None, None
 
 
 def pose_neighbourhood(xyz, pose, idx, anchors, with_perm=True, sample_xyz=None, sample_idx=None):
@@ -463,9 +493,10 @@ class LinearFn(torch.autograd.Function):
     """y[M,N] = x[M,K] @ w[N,K]^T + bias  (the BasicSO3Conv contraction / 1x1 skip conv)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, mode=None):
+    def forward(ctx, x, w, bias, mode=None, slot=None):
         x, w = _f32(x), _f32(w)
         ctx.save_for_backward(x, w)
+        ctx.slot = slot
         ctx.has_bias = bias is not None
         ctx.mode = _GEMM_MODE if mode is None else mode      # fixed here: backward uses the arithmetic of the forward
         return gemm_nt(x, w, bias, ctx.mode)
@@ -477,11 +508,13 @@ class LinearFn(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = gemm_nt(gy, w.t().contiguous(), None, ctx.mode)
+            if ctx.slot is not None and ctx.slot.deposit(gx):
+                gx = None                       # handed to the inter conv of the block (GradSlot)
         if ctx.needs_input_grad[1]:
             gw = gemm_tn(gy, x, ctx.mode)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = col_sum(gy)
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
 class PointnetPoolFn(torch.autograd.Function):
@@ -532,12 +565,13 @@ class RowGatherFn(torch.autograd.Function):
     """x [B,N,W] , idx [B,M] -> [B,M,W] (skip-connection sub-sampling by sample_idx)."""
 
     @staticmethod
-    def forward(ctx, x, idx):
+    def forward(ctx, x, idx, slot=None):
         x = _f32(x)
         b, n, w = x.shape
         m = idx.shape[1]
         out = torch.empty((b, m, w), dtype=torch.float32, device=x.device)
         call("vgtkb_row_gather_forward", x.device, b, n, m, w, ptr(x), ptr(idx), ptr(out))
+        ctx.slot = slot
         ctx.save_for_backward(idx)
         ctx.meta = (b, n, m, w)
         return out
@@ -549,7 +583,9 @@ class RowGatherFn(torch.autograd.Function):
         gout = _f32(gout)
         gx = torch.zeros((b, n, w), dtype=torch.float32, device=gout.device)
         call("vgtkb_row_gather_backward", gout.device, b, n, m, w, ptr(gout), ptr(idx), ptr(gx))
-        return gx, None
+        if ctx.slot is not None and ctx.slot.deposit(gx):
+            return None, None, None             # handed to the inter conv of the block (GradSlot)
+        return gx, None, None
 
 
 def _sync_world(group):

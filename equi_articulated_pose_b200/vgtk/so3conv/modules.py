@@ -80,9 +80,10 @@ class InterSO3Conv(nn.Module):
         return super()._load_from_state_dict(*args, **kwargs)
 
     def forward(self, x, inter_idx=None, inter_w=None):
+        slot, self._grad_slot = getattr(self, '_grad_slot', None), None     # one-shot hand-over set by the owning block
         fused = L.inter_so3conv(x.xyz, x.feats, self.basic_conv.weight_kc(), self.stride, self.n_neighbor, self.anchors,
                                 self.kernels, self.radius, self.sigma, inter_idx, inter_w, self.lazy_sample,
-                                pooling=self.pooling, rot_kernels=self.rot_kernels())
+                                pooling=self.pooling, rot_kernels=self.rot_kernels(), grad_slot=slot)
         if fused is not None:
             inter_idx, inter_w, xyz, feats, sample_idx = fused
             return inter_idx, inter_w, sample_idx, SphericalPointCloud(xyz, feats, self.anchors)

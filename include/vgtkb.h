@@ -357,6 +357,8 @@ int vgtkb_norm_act_backward_planes(int groups, int64_t rows, int c, const float*
  *             grad_out is split / converted here.
  *   mode:     3 = bf16x3 (fp32-parity: both planes), 4 = single-pass bf16 (BASELINE config 3 "bf16": operands rounded to bf16
  *             once, one tensor-core pass, ~2e-3 of the output maximum per conv; g_lo / grad_out_lo unused, may be NULL).
+ *             backward only: mode | 256 = grad_feats already holds a gradient (e.g. the skip branch's) and the scatter adds to it
+ *             (no memset of grad_feats).
  *   supported: 1 iff the shape is taken (k <= 24, nn <= 64, ci % 32 == 0, co % 8 == 0, co <= 1024, b*p*a >= 64, 32-bit offsets);
  *             other shapes run vgtkb_inter_group_* + vgtkb_gemm_*. */
 int vgtkb_inter_conv_supported(int b, int n, int p, int nn, int a, int k, int ci, int co);
