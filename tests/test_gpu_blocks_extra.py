@@ -105,3 +105,45 @@ def test_cached_tables_follow_a_reloaded_state_dict(dev):
     sd["intra_idx"] = sd["intra_idx"].flip(1)
     intra.load_state_dict(sd)
     assert torch.equal(intra.tables()[0], t0.flip(1))
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_gradient_hand_over_between_skip_branch_and_inter_conv(dev, monkeypatch, stride):
+    """ops.GradSlot: the skip branch deposits its input gradient and the inter conv's scatter adds onto it
+    (vgtkb_inter_conv_backward mode | 256).  Same block, same inputs, hand-over on / off: identical outputs, input and
+    parameter gradients equal up to the order of the floating-point additions; and the deposit really happened."""
+    from equi_articulated_pose_b200 import blocks, ops
+    from oracle import so3 as O
+    import vgtk.spconv as zptk
+    p = _params(0.0)
+    p['stride'] = stride
+    if stride > 1:
+        p['n_neighbor'] = 32
+    torch.manual_seed(1)
+    blk = blocks.SeparableSO3ConvBlock(p).to(dev).train()
+    xyz = O.synthetic_cloud(2, 128, 5).permute(0, 2, 1).contiguous().to(dev)
+    base = torch.randn(2, 128, 60, 64, device=dev)
+    taken = []
+    orig = ops.GradSlot.deposit
+
+    def spy(self, g):
+        ok = orig(self, g)
+        taken.append(ok)
+        return ok
+    monkeypatch.setattr(ops.GradSlot, "deposit", spy)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("VGTKB_GRAD_SLOT", flag)
+        blk.zero_grad(set_to_none=True)
+        x = base.clone().requires_grad_(True)
+        _, _, _, out = blk(zptk.SphericalPointCloud(xyz, x.permute(0, 3, 1, 2), None), None, None)
+        go = torch.randn(out.feats.shape, generator=torch.Generator().manual_seed(9)).to(dev)
+        (out.feats * go).sum().backward()
+        res[flag] = (out.feats.detach().clone(), x.grad.clone(), {k: v.grad.clone() for k, v in blk.named_parameters()})
+    assert taken == [True]                                   # one deposit with the hand-over on, none with it off
+    assert torch.equal(res["1"][0], res["0"][0])
+    s = float(res["0"][1].abs().max())
+    assert float((res["1"][1] - res["0"][1]).abs().max()) <= 2e-6 * s
+    for k in res["0"][2]:            # (the weight gradients are split-R atomic sums: equal up to the addition order)
+        a, b = res["1"][2][k], res["0"][2][k]
+        assert float((a - b).abs().max()) <= 1e-5 * max(float(b.abs().max()), 1e-30), k
