@@ -365,8 +365,9 @@ def dp_parity_check(dev, rank, world, sync_bn):
         rloss.backward()
         rb.collect()
         f = torch.cat(feats, 0)
-        e_f = float((f - rout.feats).abs().max() / rout.feats.abs().max())
-        e_l = abs(float(lsum) / world - float(rloss)) / abs(float(rloss))
+        rf = rout.feats.detach()
+        e_f = float((f - rf).abs().max() / rf.abs().max())
+        e_l = abs(float(lsum) / world - float(rloss.detach())) / abs(float(rloss.detach()))
         e_g = float((bucket.flat - rb.flat).abs().max() / rb.flat.abs().max())
         res.update(feats_rel_err=e_f, loss_rel_err=e_l, grad_rel_err=e_g, ok=bool(e_f < 1e-4 and e_l < 1e-4 and e_g < 3e-2),
                    bars="features 1e-4, loss 1e-4, gradients 3e-2 of the bucket maximum (fp32 gradient noise floor, DESIGN 4)")
