@@ -52,7 +52,7 @@ def run_blocks_case(device, seed=2001):
     loss.backward()
     err = {"out": rel_err(feats, torch.from_numpy(g["out_feats"])),
            "xyz": float((out.xyz.cpu() - torch.from_numpy(g["out_xyz"])).abs().max()),
-           "loss": abs(float(loss) - float(g["loss"])) / abs(float(g["loss"]))}
+           "loss": abs(float(loss.detach()) - float(g["loss"])) / abs(float(g["loss"]))}
     worst = 0.0
     named = dict(net.named_parameters())
     for k in g.files:
