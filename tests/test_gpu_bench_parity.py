@@ -51,7 +51,7 @@ def _run(dev, kind):
     out = net(pts)
     loss = _loss(out.feats, kind)
     loss.backward()
-    return net, out, float(loss)
+    return net, out, float(loss.detach())
 
 
 def test_config2_b8_forward_and_gradients_vs_oracle(dev, gold):
