@@ -221,7 +221,10 @@ class SeparableSO3ConvBlock(nn.Module):
         p = srows.shape[1]
         srows = srows.reshape(b * p * a, ci)
         w = self.skip_conv.weight.view(self.skip_conv.out_channels, ci)
-        srows = _ops.LinearFn.apply(srows, w, self.skip_conv.bias, None, lin_slot)
+        wp = getattr(self.skip_conv, '_wp', None)       # operand planes produced once per step (SO3Backbone)
+        if wp is not None and not (srows.is_cuda and wp.param is self.skip_conv.weight and wp.valid()):
+            wp = None
+        srows = _ops.LinearFn.apply(srows, w, self.skip_conv.bias, None, lin_slot, wp)
         srows = _apply_norm(self.norm, srows, b, self.slope)
         if self.use_intra:
             y = self.intra_conv(y, residual_rows=srows)
@@ -374,10 +377,46 @@ class SO3Backbone(nn.Module):
             self._nbt_flat = flat
         flat += 1
 
+    def _prepare_weight_planes(self):
+        """bf16 operand planes of every conv weight of the backbone (forward and data-gradient orders) in ONE launch per
+        step: ops.WeightPlanes.  The inter / intra / skip contractions then take their weight operand from the planes
+        instead of a permute (or transpose) copy and a split launch each -- ~70 small launches per step of the classic
+        backbone.  Only in the bf16 tensor-core modes; VGTKB_WEIGHT_PLANES=0 switches it off (A/B runs)."""
+        wps = getattr(self, '_wps', None)
+        if _ops.get_gemm_mode() not in (3, 4) or os.environ.get("VGTKB_WEIGHT_PLANES", "1") == "0":
+            if wps is not None:
+                for pw in wps[0].weights:
+                    pw.version = -1                     # planes of an earlier call must not be picked up
+            return
+        params = [p for p in self.parameters()]
+        if wps is None or wps[1] != [id(p) for p in params] or (params and params[0].device != wps[2]):
+            planes = _ops.WeightPlanes()
+            for m in self.modules():
+                if isinstance(m, sptk.InterSO3Conv):
+                    bc, role = m.basic_conv, "inter"
+                elif isinstance(m, sptk.IntraSO3Conv):
+                    bc, role = m.basic_conv, "intra"
+                else:
+                    bc = None
+                if bc is not None and isinstance(getattr(bc, 'W', None), nn.Parameter):
+                    ok = (bc.dim_in % 32 == 0 and bc.dim_out % 8 == 0) if role == "inter" else \
+                         (bc.dim_in % 64 == 0 and bc.dim_out % 64 == 0)
+                    bc._wp = planes.add(bc.W, bc.dim_out, bc.dim_in, bc.kernel_size, role) if ok else None
+                if isinstance(m, SeparableSO3ConvBlock):
+                    sc = m.skip_conv
+                    ok = sc.in_channels % 8 == 0 and sc.out_channels % 8 == 0
+                    sc._wp = planes.add(sc.weight, sc.out_channels, sc.in_channels, 1, "linear") if ok else None
+            wps = (planes, [id(p) for p in params], params[0].device if params else None)
+            self._wps = wps
+        if params and params[0].is_cuda:
+            wps[0].prepare()
+
     def forward(self, points):
         """points [B,N,3] -> SphericalPointCloud (xyz [B,3,P], feats logical [B,C,P,A])."""
         if self.training:
             self._bump_counters()
+        if points.is_cuda:
+            self._prepare_weight_planes()
         x = preprocess_input(points, self.na_in, False)
         for block in self.backbone:
             x = block(x)

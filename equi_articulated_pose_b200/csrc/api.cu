@@ -59,6 +59,9 @@ extern "C" int vgtkb_gemm_nt(int64_t M, int N, int K, const float* A, const floa
         const int rc = tc_gemm_nt(M, N, K, A, B, bias, C, passes_of(mode), workspace, st);
         if (rc != VGTKB_EUNSUP) return rc;
     }
+    // B == NULL: `workspace` holds the prepared bf16 planes of B (vgtkb_weight_planes) -- tensor-core path only
+    VGTKB_REQUIRE(B != nullptr, "gemm_nt: B is NULL (prepared planes in `workspace`) but the shape / mode is not taken by the "
+                                "bf16 tensor-core path (modes 3 / 4, K %% 8 == 0, 16-byte aligned operands)");
     return sgemm_nt(M, N, K, A, B, bias, C, st);
 }
 

@@ -7,7 +7,7 @@
 
 #include "../../include/vgtkb.h"
 
-#define VGTKB_ABI_VERSION 12
+#define VGTKB_ABI_VERSION 13
 
 namespace vgtkb {
 

@@ -1615,6 +1615,11 @@ static int tc_gemm_nt_impl(int64_t M, int N, int K, const float* A, const float*
         return VGTKB_EUNSUP;
     if (bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) != 0) return VGTKB_EUNSUP;
     if (M >= (int64_t)1 << 31) return VGTKB_EUNSUP;
+    // B == NULL: `workspace` already holds the bf16 hi | lo planes of B (vgtkb_weight_planes): bf16 modes only
+    const bool presplit = B == nullptr;
+    if (presplit && (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0 || K % 8 != 0 ||
+                     (passes != 6 && passes != 7)))
+        return VGTKB_EUNSUP;
     const int64_t nb = (int64_t)N * K;
     float* ws = nullptr;
     float* owned = nullptr;
@@ -1626,15 +1631,20 @@ static int tc_gemm_nt_impl(int64_t M, int N, int K, const float* A, const float*
     if (passes == 6) passes = 3;                  // K % 8 != 0: 3xTF32 instead
     if (passes == 3) {
         ws = workspace;
-        if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 15) != 0 || nb % 4 != 0) {
+        if (!presplit && (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 15) != 0 || nb % 4 != 0)) {
             VGTKB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&owned), sizeof(float) * 2 * (size_t)nb, st));
             ws = owned;
         }
         const int blocks = (int)(ceil_div64(nb, 256) < 1184 ? ceil_div64(nb, 256) : 1184);
-        if (bf) split_bf16_kernel<<<blocks, 256, 0, st>>>(nb, B, reinterpret_cast<uint16_t*>(ws), reinterpret_cast<uint16_t*>(ws + nb));
-        else split_tf32_kernel<<<blocks, 256, 0, st>>>(nb, B, ws, ws + nb);
+        // bf16: hi | lo planes contiguous (N*K floats in all -- callers such as vgtkb_inter_conv_backward size their scratch
+        // for that; the lo plane used to start at float offset N*K, which overran such a scratch by N*K floats whenever the
+        // activation operand came without planes); TF32: two fp32 arrays, 2*N*K floats
+        float* lo_at = bf ? reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(ws) + nb) : ws + nb;
+        if (presplit) {}
+        else if (bf) split_bf16_kernel<<<blocks, 256, 0, st>>>(nb, B, reinterpret_cast<uint16_t*>(ws), reinterpret_cast<uint16_t*>(lo_at));
+        else split_tf32_kernel<<<blocks, 256, 0, st>>>(nb, B, ws, lo_at);
         Bhi = ws;
-        Blo = ws + nb;
+        Blo = lo_at;
     }
     int rc;
     // CTA pairs (cta_group::2) are the default for the bf16x3 mode; VGTKB_CTA_PAIRS=0 selects the single-CTA kernels
@@ -1905,7 +1915,7 @@ int tc_gemm_nt_planes(int64_t M, int N, int K, const void* a_hi, const void* a_l
     const int blocks = (int)(ceil_div64(nb, 256) < 1184 ? ceil_div64(nb, 256) : 1184);
     uint16_t* bhi = reinterpret_cast<uint16_t*>(workspace);
     uint16_t* blo = bhi + nb;
-    split_bf16_kernel<<<blocks, 256, 0, st>>>(nb, B, bhi, blo);
+    if (B != nullptr) split_bf16_kernel<<<blocks, 256, 0, st>>>(nb, B, bhi, blo);   // NULL: the planes are already there
     const TcGather none{0, 0, 0, nullptr};
     if (N <= 64) return launch_nt_pair<64, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo, fast);
     if (N <= 128) return launch_nt_pair<128, true>(M, N, K, a_hi, bhi, blo, bias, C, st, none, a_lo, fast);
@@ -1975,7 +1985,7 @@ int tc_gemm_nt_gather_planes(int64_t points, int anchors, int kk_n, int c_n, int
     const int blocks = (int)(ceil_div64(nb, 256) < 1184 ? ceil_div64(nb, 256) : 1184);
     uint16_t* bhi = reinterpret_cast<uint16_t*>(workspace);
     uint16_t* blo = bhi + nb;
-    split_bf16_kernel<<<blocks, 256, 0, st>>>(nb, B, bhi, blo);
+    if (B != nullptr) split_bf16_kernel<<<blocks, 256, 0, st>>>(nb, B, bhi, blo);   // NULL: the planes are already there
     const TcGather ga{anchors, kk_n, c_n, table};
     if (N <= 64) return launch_nt_pair<64, true>(points, N, K, x_hi, bhi, blo, bias, C, st, ga, x_lo);
     if (N <= 128) return launch_nt_pair<128, true>(points, N, K, x_hi, bhi, blo, bias, C, st, ga, x_lo);
@@ -2054,4 +2064,55 @@ extern "C" int vgtkb_gather_gemm_tn_planes(int64_t points, int anchors, int kk, 
     if (rc == VGTKB_EUNSUP)
         set_error("gather_gemm_tn_planes: unsupported shape (needs c %% 64 == 0, m %% 8 == 0, points >= 64, aligned operands)");
     return rc;
+}
+
+// ---------------------------------------------------------------------------------- weight planes, one launch per step
+// Every contraction of the block takes its weight operand as two bf16 planes in its own index order: the forward conv
+// W [co, (k, c)] (the stored parameter is [co, (c, k)]: so3conv/modules.py:31-36 of the reference), the data gradients the
+// transposes [(k, c), co] (inter) and [c, (k, co)] (intra), the 1x1 skip conv [co, ci] and [ci, co].  All of them are 3-D
+// index permutations of the parameter followed by the hi / lo split, so ONE kernel serves a whole model from a table of items
+// (the weights change once per step: ~70 small permute / transpose / split launches per step become one).
+//   item (10 x int64): src (fp32), hi, lo (bf16 planes, dense in destination order), n0, n1, n2 (destination extents),
+//   s0, s1, s2 (source strides in elements of the three destination indices), first block of the item in the grid.
+namespace vgtkb {
+constexpr int WP_ELEMS_PER_BLOCK = 2048;
+__global__ void __launch_bounds__(256) weight_planes_kernel(int n_items, const int64_t* __restrict__ items) {
+    __shared__ int s_item;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = n_items - 1;                       // last item whose first block is <= blockIdx.x
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (items[(size_t)mid * 10 + 9] <= (int64_t)blockIdx.x) lo = mid;
+            else hi = mid - 1;
+        }
+        s_item = lo;
+    }
+    __syncthreads();
+    const int64_t* it = items + (size_t)s_item * 10;
+    const float* src = reinterpret_cast<const float*>(it[0]);
+    uint16_t* hi = reinterpret_cast<uint16_t*>(it[1]);
+    uint16_t* lo = reinterpret_cast<uint16_t*>(it[2]);
+    const int64_t n1 = it[4], n2 = it[5], s0 = it[6], s1 = it[7], s2 = it[8];
+    const int64_t total = it[3] * n1 * n2;
+    const int64_t base = ((int64_t)blockIdx.x - it[9]) * WP_ELEMS_PER_BLOCK;
+#pragma unroll 4
+    for (int j = 0; j < WP_ELEMS_PER_BLOCK / 256; ++j) {
+        const int64_t i = base + j * 256 + threadIdx.x;
+        if (i >= total) break;
+        const int64_t i2 = i % n2, r = i / n2, i1 = r % n1, i0 = r / n1;
+        const float v = __ldg(src + i0 * s0 + i1 * s1 + i2 * s2);
+        const uint32_t h = pack_bf16x2(v, 0.f) & 0xFFFFu;
+        hi[i] = (uint16_t)h;
+        lo[i] = (uint16_t)(pack_bf16x2(v - __uint_as_float(h << 16), 0.f) & 0xFFFFu);
+    }
+}
+}  // namespace vgtkb
+
+extern "C" int vgtkb_weight_planes(int n_items, const int64_t* items, int total_blocks, void* stream) {
+    using namespace vgtkb;
+    VGTKB_REQUIRE(n_items >= 0 && total_blocks >= 0, "weight_planes: bad size");
+    if (n_items == 0 || total_blocks == 0) return VGTKB_OK;
+    VGTKB_REQUIRE(items != nullptr, "weight_planes: item table is NULL");
+    weight_planes_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(n_items, items);
+    return check_launch("weight_planes");
 }

@@ -795,8 +795,8 @@ inter_group_bwd_tma_kernel(int n, int p, int nn, int a, int k, int ci, const flo
 // map_lo = lo plane, both [rows*k, ci] bf16 with boxes of k rows x 32 channels (64 bytes, no swizzle).  A staging buffer
 // holds the hi tile (24 x 64 B) followed by the lo tile; the 8-byte fragment stores alternate between the even and the
 // odd kernel-point row across the quad pairs so that one store instruction covers all 32 banks (2 wavefronts).
-template <int KS, bool PL = false>
-__global__ void __launch_bounds__(IG_WARPS * 32, 2)
+template <int KS, bool PL = false, int NW = IG_WARPS, int MINB = 2>
+__global__ void __launch_bounds__(NW * 32, MINB)
 inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p, int nn, int a, int k, int ci,
                               const float* __restrict__ xyz, const float* __restrict__ sxyz, const int32_t* __restrict__ idx,
                               const float* __restrict__ rk, float inv_sigma, const float* __restrict__ feats,
@@ -839,7 +839,7 @@ inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[s][j] = make_float4(1.f, 2.f, 3.f, 4.f);
     }
-    for (int ai = warp; ai < a; ai += IG_WARPS) {
+    for (int ai = warp; ai < a; ai += NW) {
         uint32_t bh[KS][3][2], bl[KS][3][2];
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
@@ -889,8 +889,8 @@ inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p
             {   // prefetch the next chunk (same anchor, or the first chunk of the warp's next anchor): the barriers of the
                 // store sequence below would otherwise keep these loads from overlapping it
                 const bool more_c = c0 + 32 < ci;
-                const float* nf = more_c ? fa + c0 + 32 : fa + (size_t)IG_WARPS * ci;
-                if ((more_c || ai + IG_WARPS < a) && !(dbg & 2)) {
+                const float* nf = more_c ? fa + c0 + 32 : fa + (size_t)NW * ci;
+                if ((more_c || ai + NW < a) && !(dbg & 2)) {
 #pragma unroll
                     for (int s = 0; s < KS; ++s)
 #pragma unroll
@@ -958,8 +958,8 @@ inter_group_fwd_mma_ts_kernel(const __grid_constant__ TmaMap map_g, int n, int p
     if (tc::elect_one()) bulk_wait_all();
 }
 
-template <int KS>
-__global__ void __launch_bounds__(IG_WARPS * 32, 2)
+template <int KS, int NW = IG_WARPS, int MINB = 2>
+__global__ void __launch_bounds__(NW * 32, MINB)
 inter_group_bwd_mma_tl_kernel(const __grid_constant__ TmaMap map_dg, int n, int p, int nn, int a, int k, int ci,
                               const float* __restrict__ xyz, const float* __restrict__ sxyz, const int32_t* __restrict__ idx,
                               const float* __restrict__ rk, float inv_sigma, float* __restrict__ gfeats) {
@@ -967,7 +967,7 @@ inter_group_bwd_mma_tl_kernel(const __grid_constant__ TmaMap map_dg, int n, int 
     extern __shared__ unsigned char smem_raw[];
     __shared__ float s_g[16 * KS * 3];
     __shared__ uint32_t s_off[16 * KS];
-    __shared__ __align__(8) uint64_t s_bar[IG_WARPS][2];
+    __shared__ __align__(8) uint64_t s_bar[NW][2];
     const int pi = blockIdx.x, b = blockIdx.y;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
     const int gid = lane >> 2, tig = lane & 3;
@@ -999,12 +999,12 @@ inter_group_bwd_mma_tl_kernel(const __grid_constant__ TmaMap map_dg, int n, int 
     kps[5] = 17 + 2 * tig;
     float* gb = gfeats + (size_t)b * n * a * ci + 4 * gid;
     const int chunks = ci / 32;
-    const int my_anchors = (a - warp + IG_WARPS - 1) / IG_WARPS;
+    const int my_anchors = (a - warp + NW - 1) / NW;
     const int items = my_anchors * chunks;                          // item -> (anchor slot, 32-channel chunk)
     const int dbg = c_dbg_group;
     auto issue = [&](int item) {
         if (!(dbg & 1) && tc::elect_one()) {
-            const int ai = warp + (item / chunks) * IG_WARPS, c0 = (item % chunks) * 32, buf = item & 1;
+            const int ai = warp + (item / chunks) * NW, c0 = (item % chunks) * 32, buf = item & 1;
             mbar_arrive_expect_tx(&s_bar[warp][buf], (uint32_t)k * 128u);
             tma_load_2d(stage + buf * (24 * 32), &map_dg, c0, (((b * p + pi) * a) + ai) * k, &s_bar[warp][buf]);
         }
@@ -1012,7 +1012,7 @@ inter_group_bwd_mma_tl_kernel(const __grid_constant__ TmaMap map_dg, int n, int 
     if (items > 0) issue(0);
     uint32_t bh[NT][3], bl[NT][3];
     for (int item = 0; item < items; ++item) {
-        const int ai = warp + (item / chunks) * IG_WARPS, c0 = (item % chunks) * 32, buf = item & 1;
+        const int ai = warp + (item / chunks) * NW, c0 = (item % chunks) * 32, buf = item & 1;
         __syncwarp();                                   // every lane is done reading the tile the next load overwrites
         if (item + 1 < items) issue(item + 1);
         if (c0 == 0) {
@@ -1697,16 +1697,30 @@ int inter_group_forward_planes(int b, int n, int p, int nn, int a, int k, int ci
     }
     const int ks = (nn + 15) / 16;
     if (!fast && ks <= 2) {       // the tuned kernels (prefetch, two CTAs per SM)
-        const size_t smem = (size_t)IG_WARPS * 2 * 24 * 128 + 1024;
+        // warps per CTA / CTAs per SM of the tuned kernels: VGTKB_IG_FWD1 / _FWD2 pick another compiled geometry (A/B runs)
+#define VGTKB_FWD_PL(KS_, NW_, MB_)                                                                                              \
+    do {                                                                                                                         \
+        const size_t smem = (size_t)(NW_) * 2 * 24 * 128 + 1024;                                                                 \
+        auto kern = inter_group_fwd_mma_ts_kernel<KS_, true, NW_, MB_>;                                                           \
+        VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
+        kern<<<dim3(p, b), (NW_) * 32, smem, st>>>(mh, n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels, 1.0f / sigma, feats, ml); \
+    } while (0)
+        static const int g1 = getenv("VGTKB_IG_FWD1") ? atoi(getenv("VGTKB_IG_FWD1")) : 0;
+        static const int g2 = getenv("VGTKB_IG_FWD2") ? atoi(getenv("VGTKB_IG_FWD2")) : 0;
         if (ks == 1) {
-            VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_mma_ts_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            inter_group_fwd_mma_ts_kernel<1, true><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(mh, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
-                                                                                            rot_kernels, 1.0f / sigma, feats, ml);
+            if (g1 == 63) VGTKB_FWD_PL(1, 6, 3);
+            else if (g1 == 44) VGTKB_FWD_PL(1, 4, 4);
+            else if (g1 == 102) VGTKB_FWD_PL(1, 10, 2);
+            else if (g1 == 53) VGTKB_FWD_PL(1, 5, 3);
+            else VGTKB_FWD_PL(1, IG_WARPS, 2);
         } else {
-            VGTKB_CUDA(cudaFuncSetAttribute(inter_group_fwd_mma_ts_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            inter_group_fwd_mma_ts_kernel<2, true><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(mh, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
-                                                                                            rot_kernels, 1.0f / sigma, feats, ml);
+            if (g2 == 62) VGTKB_FWD_PL(2, 6, 2);
+            else if (g2 == 53) VGTKB_FWD_PL(2, 5, 3);
+            else if (g2 == 43) VGTKB_FWD_PL(2, 4, 3);
+            else if (g2 == 44) VGTKB_FWD_PL(2, 4, 4);
+            else VGTKB_FWD_PL(2, IG_WARPS, 2);
         }
+#undef VGTKB_FWD_PL
         return check_launch("inter_group_forward(mma, bf16 planes)");
     }
 #define VGTKB_GEN_FWD(KS_, F_) \
@@ -1840,16 +1854,29 @@ extern "C" int vgtkb_inter_group_backward(int b, int n, int p, int nn, int a, in
         g_rows < ((int64_t)1 << 31)) {
         TmaMap map;
         if (make_rows_map(&map, grad_grouped, g_rows, ci, k) == VGTKB_OK) {
-            const size_t smem = (size_t)IG_WARPS * 2 * 24 * 128 + 1024;
+#define VGTKB_BWD_TL(KS_, NW_, MB_)                                                                                              \
+    do {                                                                                                                         \
+        const size_t smem = (size_t)(NW_) * 2 * 24 * 128 + 1024;                                                                 \
+        auto kern = inter_group_bwd_mma_tl_kernel<KS_, NW_, MB_>;                                                                 \
+        VGTKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
+        kern<<<dim3(p, b), (NW_) * 32, smem, st>>>(map, n, p, nn, a, k, ci, xyz, sample_xyz, idx, rot_kernels, 1.0f / sigma, grad_feats); \
+    } while (0)
+            static const int g1 = getenv("VGTKB_IG_BWD1") ? atoi(getenv("VGTKB_IG_BWD1")) : 0;
+            static const int g2 = getenv("VGTKB_IG_BWD2") ? atoi(getenv("VGTKB_IG_BWD2")) : 0;
             if (nn <= 16) {
-                VGTKB_CUDA(cudaFuncSetAttribute(inter_group_bwd_mma_tl_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                inter_group_bwd_mma_tl_kernel<1><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(map, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
-                                                                                          rot_kernels, 1.0f / sigma, grad_feats);
+                if (g1 == 63) VGTKB_BWD_TL(1, 6, 3);
+                else if (g1 == 44) VGTKB_BWD_TL(1, 4, 4);
+                else if (g1 == 102) VGTKB_BWD_TL(1, 10, 2);
+                else if (g1 == 53) VGTKB_BWD_TL(1, 5, 3);
+                else VGTKB_BWD_TL(1, IG_WARPS, 2);
             } else {
-                VGTKB_CUDA(cudaFuncSetAttribute(inter_group_bwd_mma_tl_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                inter_group_bwd_mma_tl_kernel<2><<<dim3(p, b), IG_WARPS * 32, smem, st>>>(map, n, p, nn, a, k, ci, xyz, sample_xyz, idx,
-                                                                                          rot_kernels, 1.0f / sigma, grad_feats);
+                if (g2 == 63) VGTKB_BWD_TL(2, 6, 3);
+                else if (g2 == 53) VGTKB_BWD_TL(2, 5, 3);
+                else if (g2 == 44) VGTKB_BWD_TL(2, 4, 4);
+                else if (g2 == 102) VGTKB_BWD_TL(2, 10, 2);
+                else VGTKB_BWD_TL(2, IG_WARPS, 2);
             }
+#undef VGTKB_BWD_TL
             return check_launch("inter_group_backward(mma, tensor-map load)");
         }
     }

@@ -88,6 +88,9 @@ extern "C" int vgtkb_inter_conv_backward(int b, int n, int p, int nn, int a, int
     const int64_t rows = (int64_t)b * p * a;
     const int kc = k * ci;
     int rc;
+    // w_kc == NULL (prepared W^T planes in `workspace`): the workspace must not be used as split scratch
+    VGTKB_REQUIRE(w_kc != nullptr || grad_w == nullptr || (grad_out_hi != nullptr && (grad_out_lo != nullptr || fast)),
+                  "inter_conv_backward: prepared weight planes (w_kc == NULL) need the planes of grad_out for the weight gradient");
     if (grad_w != nullptr) {
         // dW [co, k*ci] = grad_out^T G: wide operand G straight from its planes; workspace = split of grad_out
         rc = tc_gemm_tn_planes(co, kc, rows, grad_out, grad_out_hi, grad_out_lo, nullptr, g_hi, g_lo, grad_w, 0, workspace, st, fast);
@@ -97,13 +100,19 @@ extern "C" int vgtkb_inter_conv_backward(int b, int n, int p, int nn, int a, int
     if (grad_feats != nullptr) {
         VGTKB_REQUIRE(grad_grouped != nullptr, "inter_conv_backward: grad_grouped scratch [rows, k*ci] needed for grad_feats");
         // dG = grad_out W  (B operand = W^T [k*ci, co]), then the scatter through the neighbourhoods
+        const bool gy_planes = grad_out_hi != nullptr && (grad_out_lo != nullptr || fast) && co >= 64;
+        if (w_kc == nullptr) {
+            // prepared weights: `workspace` holds the bf16 planes of W^T [kc, co] (vgtkb_weight_planes) -- no transpose, no split
+            rc = gy_planes ? tc_gemm_nt_planes(rows, kc, co, grad_out_hi, grad_out_lo, nullptr, nullptr, grad_grouped, workspace, st, fast)
+                           : tc_gemm_nt(rows, kc, co, grad_out, nullptr, nullptr, grad_grouped, fast ? 7 : 6, workspace, st);
+        } else {
         float* wt = workspace;                       // [kc, co]
         float* wsplit = workspace + (size_t)kc * co; // hi/lo split of W^T (kc*co floats)
         transpose_kernel<<<dim3(ceil_div(kc, 32), ceil_div(co, 32)), dim3(32, 8), 0, st>>>(co, kc, w_kc, wt);
         // (the planes of grad_out, when the producer wrote them, feed the contraction without conversion)
-        rc = (grad_out_hi != nullptr && (grad_out_lo != nullptr || fast) && co >= 64)
-                 ? tc_gemm_nt_planes(rows, kc, co, grad_out_hi, grad_out_lo, wt, nullptr, grad_grouped, wsplit, st, fast)
-                 : tc_gemm_nt(rows, kc, co, grad_out, wt, nullptr, grad_grouped, fast ? 7 : 6, wsplit, st);
+        rc = gy_planes ? tc_gemm_nt_planes(rows, kc, co, grad_out_hi, grad_out_lo, wt, nullptr, grad_grouped, wsplit, st, fast)
+                       : tc_gemm_nt(rows, kc, co, grad_out, wt, nullptr, grad_grouped, fast ? 7 : 6, wsplit, st);
+        }
         if (rc == VGTKB_EUNSUP) set_error("inter_conv_backward: dG contraction shape not covered (co %% 8 == 0, aligned operands)");
         if (rc) return rc;
         if (!accumulate) VGTKB_CUDA(cudaMemsetAsync(grad_feats, 0, sizeof(float) * (size_t)b * n * a * ci, st));

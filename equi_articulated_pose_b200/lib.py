@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgtkb200.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _lib = None
 _device_ok = set()
@@ -82,6 +82,7 @@ SIGNATURES = {
     "vgtkb_peer_allreduce_f64": [c_int, c_vp, c_int, c_int, c_vp, ctypes.c_uint64, c_vp],
     "vgtkb_norm_finalize_peer": [c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_int, c_vp, ctypes.c_uint64, c_vp],
     "vgtkb_peer_status": [c_vp, c_int, ctypes.POINTER(c_i64), c_vp],
+    "vgtkb_weight_planes": [c_int, c_vp, c_int, c_vp],
 }
 # entry points without a stream argument (setup of the peer mailboxes); status int like the others
 SETUP_SIGNATURES = {
@@ -173,10 +174,17 @@ def call(name, device, *args):
     if rc != 0:
         raise VgtkbError(f"{name} failed ({rc}): {lib.vgtkb_last_error().decode()}")
     COUNTERS["launch_calls"] += 1
-    COUNTERS["kernels"] += KERNELS_PER_CALL.get(name, 1)
+    kernels = KERNELS_PER_CALL.get(name, 1)
+    w = PREPARED_WEIGHT_ARG.get(name)
+    if w is not None and args[w[0]] is None:         # prepared weight planes: no transpose / split launches in this call
+        kernels -= w[1]
+    COUNTERS["kernels"] += kernels
 
 
 COUNTERS = {"launch_calls": 0, "kernels": 0}
+# entry point -> (index of its fp32 weight argument, kernels saved when it is NULL = planes prepared by vgtkb_weight_planes)
+PREPARED_WEIGHT_ARG = {"vgtkb_gemm_nt": (4, 1), "vgtkb_gemm_nt_presplit": (5, 1), "vgtkb_gather_gemm_nt_planes": (8, 1),
+                       "vgtkb_inter_conv_forward": (14, 1), "vgtkb_inter_conv_backward": (13, 2)}
 PROFILE = None  # set to a list to record (entry point, args, start event, end event) per call
 # device kernels launched per entry point (memsets not counted); used for bench.py's gpu_launches
 KERNELS_PER_CALL = {"vgtkb_gemm_nt": 2, "vgtkb_gemm_tn": 2, "vgtkb_gather_gemm_nt": 2, "vgtkb_gather_gemm_tn": 2,

@@ -125,14 +125,23 @@ def inter_weights(xyz, sample_xyz, idx, rot_kernels, sigma):
 
 
 # ----------------------------------------------------------------------------- raw fused ops
-def gemm_nt(a, b, bias=None, mode=None):
-    """C[M,N] = A[M,K] @ B[N,K]^T (+ bias)."""
-    a, b = _f32(a), _f32(b)
+def gemm_nt(a, b, bias=None, mode=None, b_planes=None):
+    """C[M,N] = A[M,K] @ B[N,K]^T (+ bias).  b_planes: the prepared bf16 hi | lo planes of B (WeightPlanes; modes 3 / 4,
+    K % 8 == 0) -- B itself is then not read and may be given as its shape (N, K)."""
+    a = _f32(a)
     m, k = a.shape
+    mode = _GEMM_MODE if mode is None else mode
+    if b_planes is not None:
+        n = b_planes.numel() // (2 * k)
+        assert mode in (3, 4) and k % 8 == 0 and b_planes.numel() == 2 * n * k
+        c = torch.empty((m, n), dtype=torch.float32, device=a.device)
+        call("vgtkb_gemm_nt", a.device, m, n, k, ptr(a), None, ptr(bias.contiguous()) if bias is not None else None,
+             ptr(c), mode, ptr(b_planes))
+        return c
+    b = _f32(b)
     n = b.shape[0]
     assert b.shape[1] == k
     c = torch.empty((m, n), dtype=torch.float32, device=a.device)
-    mode = _GEMM_MODE if mode is None else mode
     ws = torch.empty(2 * n * k, dtype=torch.float32, device=a.device) if mode in (1, 3, 4) else None   # hi/lo split of b
     call("vgtkb_gemm_nt", a.device, m, n, k, ptr(a), ptr(b), ptr(bias.contiguous()) if bias is not None else None,
          ptr(c), mode, ptr(ws))
@@ -240,6 +249,102 @@ def inter_conv_supported(b, n, p, nn, a, k, ci, co):
     return _GEMM_MODE in (3, 4) and bool(_lib.load().vgtkb_inter_conv_supported(b, n, p, nn, a, k, ci, co))
 
 
+class PreparedWeight:
+    """One conv weight of a model whose operand planes are produced by WeightPlanes.prepare(): `param` is the parameter in the
+    reference's layout ([co, ci*k] with column c*k + kp, or the 1x1 conv's [co, ci, 1, 1]); `fwd` / `bwd` are the bf16 hi | lo
+    planes (uint16 [2 * co*ci*k]) of the forward operand and of the data-gradient operand.  valid(): the planes were
+    computed from the parameter's current value (its version counter has not moved since prepare())."""
+    __slots__ = ("param", "co", "ci", "k", "role", "fwd", "bwd", "version")
+
+    def __init__(self, param, co, ci, k, role):
+        self.param, self.co, self.ci, self.k, self.role = param, co, ci, k, role
+        self.fwd = self.bwd = None
+        self.version = -1
+
+    def valid(self):
+        return self.fwd is not None and self.param._version == self.version and _GEMM_MODE in (3, 4)
+
+    def matrix(self):
+        """The parameter as the [co, ci*k] matrix of the reference layout (a view)."""
+        return self.param.view(self.co, self.ci * self.k)
+
+    def kc(self):
+        """[co, k*ci] with column kp*ci + c: the column order of the kernels (autograd-tracked copy)."""
+        return self.param.view(self.co, self.ci, self.k).transpose(1, 2).reshape(self.co, -1)
+
+    def grad_from_kc(self, gw_kc):
+        """Gradient w.r.t. kc() -> gradient w.r.t. matrix() (the parameter's own column order)."""
+        return gw_kc.view(self.co, self.k, self.ci).transpose(1, 2).reshape(self.co, self.ci * self.k)
+
+
+class WeightPlanes:
+    """bf16 hi / lo operand planes of ALL conv weights of a model, produced by ONE launch per step (vgtkb_weight_planes)
+    instead of a permute / transpose copy plus a split launch per contraction (the weights change once per step).
+    roles: 'inter' / 'intra' (BasicSO3Conv.W [co, ci*k], column c*k + kp; vgtk/vgtk/so3conv/modules.py:31-36 of the
+    reference) and 'linear' (1x1 conv).  Destination orders: forward [co][k][ci]; data gradient [k][ci][co] (inter: W^T of the
+    kernel-order matrix), [ci][k][co] (intra: IntraConvFn.backward's operand), [ci][co] (linear)."""
+
+    ELEMS_PER_BLOCK = 2048
+
+    def __init__(self):
+        self.weights, self._table, self._ptrs, self._blocks, self._buf = [], None, None, 0, None
+
+    def add(self, param, co, ci, k, role):
+        assert role in ("inter", "intra", "linear") and param.numel() == co * ci * k and (co * ci * k) % 8 == 0
+        pw = PreparedWeight(param, co, ci, k, role)
+        self.weights.append(pw)
+        self._table = None
+        return pw
+
+    @staticmethod
+    def _items(pw):
+        co, ci, k = pw.co, pw.ci, pw.k
+        fwd = ((co, k, ci), (ci * k, 1, k))
+        if pw.role == "inter":
+            bwd = ((k, ci, co), (1, k, ci * k))
+        elif pw.role == "intra":
+            bwd = ((ci, k, co), (k, 1, ci * k))
+        else:
+            bwd = ((1, ci, co), (0, 1, ci))
+        return fwd, bwd
+
+    def _build(self, dev):
+        offs, total = [], 0
+        for pw in self.weights:                          # two plane pairs (hi | lo) per weight, each 128-byte aligned
+            n = pw.co * pw.ci * pw.k
+            for _ in range(2):
+                offs.append(total)
+                total += (2 * n + 63) // 64 * 64
+        self._buf = torch.empty(max(total, 64), dtype=torch.bfloat16, device=dev)
+        base, rows, blocks = self._buf.data_ptr(), [], 0
+        for i, pw in enumerate(self.weights):
+            n = pw.co * pw.ci * pw.k
+            for j, (sizes, strides) in enumerate(self._items(pw)):
+                o = offs[2 * i + j]
+                rows.append([pw.param.data_ptr(), base + 2 * o, base + 2 * (o + n), *sizes, *strides, blocks])
+                blocks += (n + self.ELEMS_PER_BLOCK - 1) // self.ELEMS_PER_BLOCK
+                if j == 0:
+                    pw.fwd = self._buf[o:o + 2 * n]
+                else:
+                    pw.bwd = self._buf[o:o + 2 * n]
+        self._table = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self._ptrs = [pw.param.data_ptr() for pw in self.weights]
+        self._blocks = blocks
+
+    def prepare(self):
+        """Recompute every plane from the current parameter values: one launch on the current stream."""
+        if not self.weights:
+            return
+        dev = self.weights[0].param.device
+        if not dev.type == "cuda":
+            raise _lib.VgtkbError("WeightPlanes.prepare: parameters are not on a CUDA device (there is no CPU path)")
+        if self._table is None or self._table.device != dev or self._ptrs != [pw.param.data_ptr() for pw in self.weights]:
+            self._build(dev)
+        call("vgtkb_weight_planes", dev, len(self.weights) * 2, ptr(self._table), self._blocks)
+        for pw in self.weights:
+            pw.version = pw.param._version
+
+
 class GradSlot:
     """Hand-over of a gradient between the two consumers of a block's input (the skip branch and the inter conv):
     backward runs the skip branch first (it was recorded later), which DEPOSITS its input gradient here and returns None;
@@ -266,8 +371,13 @@ class InterConvFn(torch.autograd.Function):
     so3conv/modules.py:48-55."""
 
     @staticmethod
-    def forward(ctx, feats, w_kc, xyz, sample_xyz, idx, rot_kernels, sigma, slot=None):
-        feats, w_kc = _f32(feats), _f32(w_kc)
+    def forward(ctx, feats, w_kc, xyz, sample_xyz, idx, rot_kernels, sigma, slot=None, wp=None):
+        # wp (PreparedWeight, valid): `w_kc` is the PARAMETER in its own layout; the kernels read the prepared planes and the
+        # weight gradient is returned in the parameter's layout (no permute copy, no transpose, no split launches)
+        feats = _f32(feats)
+        ctx.wp = wp
+        if wp is None:
+            w_kc = _f32(w_kc)
         b, n, a, ci = feats.shape
         ctx.slot = slot if (slot is not None and slot.shape == (b, n, a, ci) and feats.requires_grad) else None
         if ctx.slot is not None:
@@ -279,10 +389,16 @@ class InterConvFn(torch.autograd.Function):
         mode = _GEMM_MODE                      # 3 = bf16x3 (both planes), 4 = single-pass bf16 (hi plane only)
         g_hi = torch.empty((rows, k * ci), dtype=torch.bfloat16, device=dev)
         g_lo = torch.empty((rows, k * ci), dtype=torch.bfloat16, device=dev) if mode == 3 else None
-        ws = torch.empty(co * k * ci, dtype=torch.float32, device=dev)
         out = torch.empty((rows, co), dtype=torch.float32, device=dev)
-        call("vgtkb_inter_conv_forward", dev, b, n, p, nn, a, k, ci, co, ptr(xyz), ptr(sample_xyz), ptr(idx), ptr(rot_kernels),
-             float(sigma), ptr(feats), ptr(w_kc), ptr(g_hi), ptr(g_lo), ptr(ws), ptr(out), mode)
+        if wp is not None:
+            assert (wp.co, wp.ci, wp.k) == (co, ci, k) and wp.valid()
+            call("vgtkb_inter_conv_forward", dev, b, n, p, nn, a, k, ci, co, ptr(xyz), ptr(sample_xyz), ptr(idx), ptr(rot_kernels),
+                 float(sigma), ptr(feats), None, ptr(g_hi), ptr(g_lo), ptr(wp.fwd), ptr(out), mode)
+            ctx.wp_bwd = wp.bwd
+        else:
+            ws = torch.empty(co * k * ci, dtype=torch.float32, device=dev)
+            call("vgtkb_inter_conv_forward", dev, b, n, p, nn, a, k, ci, co, ptr(xyz), ptr(sample_xyz), ptr(idx), ptr(rot_kernels),
+                 float(sigma), ptr(feats), ptr(w_kc), ptr(g_hi), ptr(g_lo), ptr(ws), ptr(out), mode)
         ctx.save_for_backward(xyz, sample_xyz, idx, rot_kernels, w_kc, g_hi, g_lo)
         ctx.meta = (b, n, p, nn, a, k, ci, co, float(sigma), mode)
         return out
@@ -304,13 +420,25 @@ class InterConvFn(torch.autograd.Function):
             gx = torch.empty((b, n, a, ci), dtype=torch.float32, device=dev) if need_x else None
         dg = torch.empty((rows, kc), dtype=torch.float32, device=dev) if need_x else None
         gw = torch.empty((co, kc), dtype=torch.float32, device=dev) if need_w else None
-        ws = torch.empty(max(rows * co, 2 * kc * co), dtype=torch.float32, device=dev)
         gy_hi, gy_lo = take_planes(gy) if (mode & 255) == 3 else (None, None)
-        call("vgtkb_inter_conv_backward", dev, b, n, p, nn, a, k, ci, co, ptr(xyz), ptr(sample_xyz), ptr(idx), ptr(rot_kernels),
-             sigma, ptr(w_kc), ptr(g_hi), ptr(g_lo), ptr(gy), ptr(gy_hi), ptr(gy_lo), ptr(dg), ptr(gx), ptr(gw), ptr(ws), mode)
+        wp = ctx.wp
+        if wp is not None and (gy_hi is not None or not need_w):
+            # prepared planes of W^T: the workspace argument carries them (w_kc = NULL)
+            call("vgtkb_inter_conv_backward", dev, b, n, p, nn, a, k, ci, co, ptr(xyz), ptr(sample_xyz), ptr(idx),
+                 ptr(rot_kernels), sigma, None, ptr(g_hi), ptr(g_lo), ptr(gy), ptr(gy_hi), ptr(gy_lo), ptr(dg), ptr(gx), ptr(gw),
+                 ptr(ctx.wp_bwd), mode)
+        else:
+            if wp is not None:
+                w_kc = wp.kc().detach().contiguous()
+            ws = torch.empty(max(rows * co, 2 * kc * co), dtype=torch.float32, device=dev)
+            call("vgtkb_inter_conv_backward", dev, b, n, p, nn, a, k, ci, co, ptr(xyz), ptr(sample_xyz), ptr(idx),
+                 ptr(rot_kernels), sigma, ptr(w_kc), ptr(g_hi), ptr(g_lo), ptr(gy), ptr(gy_hi), ptr(gy_lo), ptr(dg), ptr(gx),
+                 ptr(gw), ptr(ws), mode)
         if acc is not None and not need_x:
             raise _lib.VgtkbError("InterConvFn: a skip-branch gradient was deposited but the input gradient is not requested")
-        return gx, gw, None, None, None, None, None, None
+        if wp is not None and gw is not None:
+            gw = wp.grad_from_kc(gw)                    # the parameter's own layout
+        return gx, gw, None, None, None, None, None, None, None
 
 
 def pose_neighbourhood(xyz, pose, idx, anchors, with_perm=True, sample_xyz=None, sample_idx=None):
@@ -419,15 +547,26 @@ def gather_gemm_supported(c_in, c_out, points):
     return _GEMM_MODE != 0 and c_in % 64 == 0 and c_out % 64 == 0 and points >= 64
 
 
-def gather_gemm_nt_planes(x_hi, x_lo, table, w, bias=None):
-    """gather_gemm_nt with x [points, A, C] given as bf16 planes (no operand conversion in the kernel)."""
-    w = _f32(w)
+def gather_gemm_nt_planes(x_hi, x_lo, table, w, bias=None, w_planes=None):
+    """gather_gemm_nt with x [points, A, C] given as bf16 planes (no operand conversion in the kernel).
+    w_planes: prepared bf16 hi | lo planes of w [n, kk*C] (WeightPlanes); w is then not read (may be None)."""
     pts, a, c = x_hi.shape
-    kk, n = table.shape[1], w.shape[0]
-    assert w.shape[1] == kk * c and table.shape[0] == a and table.dtype == torch.int32
-    out = torch.empty((pts * a, n), dtype=torch.float32, device=w.device)
-    ws = torch.empty(n * kk * c, dtype=torch.float32, device=w.device)
-    call("vgtkb_gather_gemm_nt_planes", w.device, pts, a, kk, c, n, ptr(table), ptr(x_hi), ptr(x_lo), ptr(w),
+    kk = table.shape[1]
+    assert table.shape[0] == a and table.dtype == torch.int32
+    dev = x_hi.device
+    if w_planes is not None:
+        n = w_planes.numel() // (2 * kk * c)
+        assert w_planes.numel() == 2 * n * kk * c
+        out = torch.empty((pts * a, n), dtype=torch.float32, device=dev)
+        call("vgtkb_gather_gemm_nt_planes", dev, pts, a, kk, c, n, ptr(table), ptr(x_hi), ptr(x_lo), None,
+             ptr(bias.contiguous()) if bias is not None else None, ptr(out), ptr(w_planes))
+        return out
+    w = _f32(w)
+    n = w.shape[0]
+    assert w.shape[1] == kk * c
+    out = torch.empty((pts * a, n), dtype=torch.float32, device=dev)
+    ws = torch.empty(n * kk * c, dtype=torch.float32, device=dev)
+    call("vgtkb_gather_gemm_nt_planes", dev, pts, a, kk, c, n, ptr(table), ptr(x_hi), ptr(x_lo), ptr(w),
          ptr(bias.contiguous()) if bias is not None else None, ptr(out), ptr(ws))
     return out
 
@@ -450,14 +589,24 @@ class IntraConvFn(torch.autograd.Function):
     them instead of converting the fp32 tensors k-block by k-block (the intra conv re-reads every element 12 times)."""
 
     @staticmethod
-    def forward(ctx, x, w_kc, table, table_inv):
-        x, w_kc = _f32(x), _f32(w_kc)
+    def forward(ctx, x, w_kc, table, table_inv, wp=None):
+        # wp (PreparedWeight, valid): `w_kc` is the PARAMETER in its own layout (column c*kk + k); see InterConvFn
+        x = _f32(x)
         x_hi, x_lo = take_planes(x) if planes_enabled() and x.shape[2] % 64 == 0 else (None, None)
         ctx.planes = x_hi is not None
         ctx.mode = _GEMM_MODE                        # backward runs in the arithmetic of the forward
+        ctx.wp = wp
+        if wp is not None and not ctx.planes:        # prepared weights only serve the plane-fed kernels
+            w_kc = wp.kc()
+        if wp is None or not ctx.planes:
+            w_kc = _f32(w_kc)
         if ctx.planes:
             x_hi, x_lo = x_hi.view(x.shape), x_lo.view(x.shape)
             ctx.save_for_backward(x_hi, x_lo, w_kc, table, table_inv)
+            if wp is not None:
+                assert wp.valid() and wp.ci == x.shape[2]
+                ctx.wp_bwd = wp.bwd
+                return gather_gemm_nt_planes(x_hi, x_lo, table, None, None, wp.fwd)
             return gather_gemm_nt_planes(x_hi, x_lo, table, w_kc)
         ctx.save_for_backward(x, w_kc, table, table_inv)
         return gather_gemm_nt(x, table, w_kc)
@@ -474,31 +623,45 @@ class IntraConvFn(torch.autograd.Function):
         gy = _f32(gy)
         gy_hi, gy_lo = take_planes(gy) if ctx.mode == 3 and planes_enabled() and co % 64 == 0 else (None, None)
         gx = gw = None
+        wp = ctx.wp if ctx.planes else None          # (without planes the forward already went through wp.kc(): autograd permutes)
         if ctx.needs_input_grad[0]:
             # gx[(pt,a'), c] = sum_{kk,o} gy[pt, inv[a',kk], o] * w_kc[o, kk*C + c]
-            wt = w_kc.view(co, kk, c).permute(2, 1, 0).reshape(c, kk * co).contiguous()
-            if gy_hi is not None:
-                gx = gather_gemm_nt_planes(gy_hi.view(pts, a, co), gy_lo.view(pts, a, co), table_inv, wt).view(pts, a, c)
+            if wp is not None and gy_hi is not None:
+                gx = gather_gemm_nt_planes(gy_hi.view(pts, a, co), gy_lo.view(pts, a, co), table_inv, None, None,
+                                           ctx.wp_bwd).view(pts, a, c)
             else:
-                gx = gather_gemm_nt(gy.view(pts, a, co), table_inv, wt, mode=ctx.mode).view(pts, a, c)
+                if wp is not None:
+                    w_kc = wp.kc().detach()
+                wt = w_kc.view(co, kk, c).permute(2, 1, 0).reshape(c, kk * co).contiguous()
+                if gy_hi is not None:
+                    gx = gather_gemm_nt_planes(gy_hi.view(pts, a, co), gy_lo.view(pts, a, co), table_inv, wt).view(pts, a, c)
+                else:
+                    gx = gather_gemm_nt(gy.view(pts, a, co), table_inv, wt, mode=ctx.mode).view(pts, a, c)
         if ctx.needs_input_grad[1]:
             if ctx.planes:
                 gw = gather_gemm_tn_planes(x_hi, x_lo, table, gy, gy_hi, gy_lo)
             else:
                 gw = gather_gemm_tn(x, table, gy, mode=ctx.mode)
-        return gx, gw, None, None
+            if ctx.wp is not None:
+                gw = ctx.wp.grad_from_kc(gw)         # the parameter's own layout
+        return gx, gw, None, None, None
 
 
 class LinearFn(torch.autograd.Function):
     """y[M,N] = x[M,K] @ w[N,K]^T + bias  (the BasicSO3Conv contraction / 1x1 skip conv)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, mode=None, slot=None):
+    def forward(ctx, x, w, bias, mode=None, slot=None, wp=None):
+        # wp (PreparedWeight of a 1x1 conv, valid): the contractions read the prepared planes of w / w^T
         x, w = _f32(x), _f32(w)
         ctx.save_for_backward(x, w)
         ctx.slot = slot
         ctx.has_bias = bias is not None
         ctx.mode = _GEMM_MODE if mode is None else mode      # fixed here: backward uses the arithmetic of the forward
+        ctx.wp_bwd = None
+        if wp is not None and ctx.mode in (3, 4) and wp.valid() and (wp.co, wp.ci * wp.k) == tuple(w.shape):
+            ctx.wp_bwd = wp.bwd
+            return gemm_nt(x, None, bias, ctx.mode, wp.fwd)
         return gemm_nt(x, w, bias, ctx.mode)
 
     @staticmethod
@@ -507,14 +670,17 @@ class LinearFn(torch.autograd.Function):
         gy = _f32(gy)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = gemm_nt(gy, w.t().contiguous(), None, ctx.mode)
+            if ctx.wp_bwd is not None:
+                gx = gemm_nt(gy, None, None, ctx.mode, ctx.wp_bwd)
+            else:
+                gx = gemm_nt(gy, w.t().contiguous(), None, ctx.mode)
             if ctx.slot is not None and ctx.slot.deposit(gx):
                 gx = None                       # handed to the inter conv of the block (GradSlot)
         if ctx.needs_input_grad[1]:
             gw = gemm_tn(gy, x, ctx.mode)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = col_sum(gy)
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
 class PointnetPoolFn(torch.autograd.Function):

@@ -157,7 +157,7 @@ def inter_so3conv_grouping(xyz, feats, stride, n_neighbor, anchors, kernels, rad
 
 
 def inter_so3conv(xyz, feats, w_kc, stride, n_neighbor, anchors, kernels, radius, sigma, inter_idx=None, inter_w=None,
-                  lazy_sample=True, radius_expansion=1.0, pooling=None, rot_kernels=None, grad_slot=None):
+                  lazy_sample=True, radius_expansion=1.0, pooling=None, rot_kernels=None, grad_slot=None, wp=None):
     """inter_so3conv_grouping + BasicSO3Conv in one call (vgtkb_inter_conv_forward) when the shape is taken: the grouped
     tensor of the reference (:192-203) only exists as the contraction's bf16 operand planes.
     -> (inter_idx, inter_w, new_xyz, out_feats logical [b,co,p2,a], sample_idx), or None when the caller has to take the
@@ -170,11 +170,19 @@ def inter_so3conv(xyz, feats, w_kc, stride, n_neighbor, anchors, kernels, radius
     w = inter_w
     b, ci, n, a = feats.shape
     p, nn = w.idx.shape[1], w.idx.shape[2]
-    k, co = w.rot_kernels.shape[1], w_kc.shape[0]
+    # wp: ops.PreparedWeight of the conv weight (operand planes produced once per step); w_kc may then be None
+    k, co = w.rot_kernels.shape[1], (wp.co if wp is not None else w_kc.shape[0])
     if not _ops.inter_conv_supported(b, n, p, nn, a, k, ci, co):
+        if w_kc is None:
+            w_kc = wp.kc()
         g = _ops.InterGroupFn.apply(_channels_last(feats), w.xyz, w.sample_xyz, w.idx, w.rot_kernels, w.sigma)
         rows = _ops.LinearFn.apply(g.view(b * p * a, k * ci), w_kc, None)
+    elif wp is not None and (wp.ci, wp.k) == (ci, k):
+        rows = _ops.InterConvFn.apply(_channels_last(feats), wp.matrix(), w.xyz, w.sample_xyz, w.idx, w.rot_kernels, w.sigma,
+                                      grad_slot if pooling is None else None, wp)
     else:
+        if w_kc is None:
+            w_kc = wp.kc()
         rows = _ops.InterConvFn.apply(_channels_last(feats), w_kc, w.xyz, w.sample_xyz, w.idx, w.rot_kernels, w.sigma,
                                       grad_slot if pooling is None else None)
     out = rows.view(b, p, a, co).permute(0, 3, 1, 2)

@@ -35,6 +35,12 @@ class BasicSO3Conv(nn.Module):
         """W re-indexed to the kernels' column order k*Ci + c (autograd-tracked view+copy, tiny)."""
         return self.W.view(self.dim_out, self.dim_in, self.kernel_size).transpose(1, 2).reshape(self.dim_out, -1)
 
+    def prepared(self):
+        """The PreparedWeight of W when the owning model produced its operand planes for the current parameter value
+        (ops.WeightPlanes, one launch per step), else None: callers then re-index / split W per call."""
+        wp = getattr(self, '_wp', None)
+        return wp if (wp is not None and wp.param is self.W and wp.valid()) else None
+
     def forward_rows(self, rows):
         """rows [M, K*Ci] (column k*Ci + c) -> [M, dim_out] on the tensor-core GEMM."""
         return _ops.LinearFn.apply(rows, self.weight_kc(), None)
@@ -81,9 +87,10 @@ class InterSO3Conv(nn.Module):
 
     def forward(self, x, inter_idx=None, inter_w=None):
         slot, self._grad_slot = getattr(self, '_grad_slot', None), None     # one-shot hand-over set by the owning block
-        fused = L.inter_so3conv(x.xyz, x.feats, self.basic_conv.weight_kc(), self.stride, self.n_neighbor, self.anchors,
-                                self.kernels, self.radius, self.sigma, inter_idx, inter_w, self.lazy_sample,
-                                pooling=self.pooling, rot_kernels=self.rot_kernels(), grad_slot=slot)
+        wp = self.basic_conv.prepared() if x.feats.is_cuda else None
+        fused = L.inter_so3conv(x.xyz, x.feats, None if wp is not None else self.basic_conv.weight_kc(), self.stride,
+                                self.n_neighbor, self.anchors, self.kernels, self.radius, self.sigma, inter_idx, inter_w,
+                                self.lazy_sample, pooling=self.pooling, rot_kernels=self.rot_kernels(), grad_slot=slot, wp=wp)
         if fused is not None:
             inter_idx, inter_w, xyz, feats, sample_idx = fused
             return inter_idx, inter_w, sample_idx, SphericalPointCloud(xyz, feats, self.anchors)
@@ -181,8 +188,9 @@ class IntraSO3Conv(nn.Module):
         t, inv, is_perm = self.tables()
         if x.feats.is_cuda and is_perm and _ops.gather_gemm_supported(c, self.dim_out, nb * npt):
             # fused: the [b,c,12,p,a] gather of the reference (functional.py:2565-2567) is never materialised
+            wp = self.basic_conv.prepared()
             rows = _ops.IntraConvFn.apply(x.feats.permute(0, 2, 3, 1).contiguous().view(nb * npt, na, c),
-                                          self.basic_conv.weight_kc(), t, inv)
+                                          self.basic_conv.W if wp is not None else self.basic_conv.weight_kc(), t, inv, wp)
             feats = rows.view(nb, npt, na, self.dim_out).permute(0, 3, 1, 2)
         else:
             feats = L.intra_so3conv_grouping(self.intra_idx, x.feats)

@@ -372,6 +372,19 @@ int vgtkb_inter_conv_backward(int b, int n, int p, int nn, int a, int k, int ci,
                               const void* grad_out_hi, const void* grad_out_lo, float* grad_grouped, float* grad_feats,
                               float* grad_w, float* workspace, int mode, void* stream);
 
+/* Weight operand planes for a whole model in ONE launch per step (csrc/gemm_tc.cu).  Every contraction of a block takes
+ * its weight operand as two bf16 planes in its own index order -- forward W [co, (k, c)] (the reference stores the
+ * parameter as [co, (c, k)], vgtk/vgtk/so3conv/modules.py:31-36), data gradients W^T [(k, c), co] (inter) and
+ * [c, (k, co)] (intra), the 1x1 skip conv [co, ci] / [ci, co] -- each a 3-D index permutation of the parameter followed
+ * by the hi / lo split.  `items` [n_items][10] int64 (device): src (const float*), hi, lo (bf16 planes, dense in
+ * destination order), n0, n1, n2 (destination extents), s0, s1, s2 (source strides, in elements, of the three
+ * destination indices), first grid block of the item (2048 elements per block; `total_blocks` = blocks of all items).
+ * CONSUMERS: an entry point whose fp32 weight argument is NULL reads the prepared planes (hi | lo, contiguous) from its
+ * `workspace` argument instead of splitting the weights itself: vgtkb_gemm_nt (B, modes 3 / 4, K % 8 == 0),
+ * vgtkb_gemm_nt_presplit (B), vgtkb_gather_gemm_nt_planes (w), vgtkb_inter_conv_forward (w_kc; planes of W [co, k*ci]),
+ * vgtkb_inter_conv_backward (w_kc; planes of W^T [k*ci, co]; needs grad_out_hi / _lo when grad_w is requested). */
+int vgtkb_weight_planes(int n_items, const int64_t* items, int total_blocks, void* stream);
+
 /* column sums of a row-major [rows, c] matrix (bias gradient of the skip conv) */
 int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream);
 

@@ -173,3 +173,37 @@ def test_operand_planes_block_matches_fp32_operands(dev):
     assert float((g1 - g0).abs().max()) <= 2e-5 * float(g0.abs().max())
     for k in p0:
         assert float((p1[k] - p0[k]).abs().max()) <= 2e-5 * float(p0[k].abs().max()) + 1e-9, k
+
+
+@pytest.mark.parametrize("mode,planes", [(3, False), (4, False), (3, True)])
+def test_inter_conv_backward_stays_inside_its_workspace(dev, mode, planes):
+    """vgtkb_inter_conv_backward with a workspace of EXACTLY the documented size (max(rows*co, 2*k*ci*co) floats) followed by a
+    canary: few rows, so the weight split is the larger term.  Regression: without planes of grad_out the dG contraction
+    split W^T with the lo plane at float offset k*ci*co of its scratch and overran the workspace by k*ci*co floats (silent
+    inside torch's cached pool; an illegal address otherwise)."""
+    from equi_articulated_pose_b200 import ops
+    from equi_articulated_pose_b200.lib import call, ptr
+    b, n, p, nn, ci, co = 1, 32, 16, 16, 64, 128
+    xyz, sxyz, idx, rk, feats, w_kc, gy, sigma = _case(dev, b, n, p, nn, ci, co, 0.8, 0.2, 3)
+    a, k = rk.shape[0], rk.shape[1]
+    rows, kc = b * p * a, k * ci
+    g_hi = torch.empty((rows, kc), dtype=torch.bfloat16, device=dev)
+    g_lo = torch.empty((rows, kc), dtype=torch.bfloat16, device=dev)
+    out = torch.empty((rows, co), dtype=torch.float32, device=dev)
+    ws_f = torch.empty(co * kc, dtype=torch.float32, device=dev)
+    call("vgtkb_inter_conv_forward", dev, b, n, p, nn, a, k, ci, co, ptr(xyz), ptr(sxyz), ptr(idx), ptr(rk), float(sigma),
+         ptr(feats), ptr(w_kc), ptr(g_hi), ptr(g_lo if mode == 3 else None), ptr(ws_f), ptr(out), mode)
+    size = max(rows * co, 2 * kc * co)
+    assert size == 2 * kc * co                               # the case the regression needs
+    pad = 2 * kc * co
+    buf = torch.full((size + pad,), 12345.0, dtype=torch.float32, device=dev)
+    gy_hi, gy_lo = ops.split_bf16(gy) if planes else (None, None)
+    dg = torch.empty((rows, kc), dtype=torch.float32, device=dev)
+    gx = torch.empty((b, n, a, ci), dtype=torch.float32, device=dev)
+    gw = torch.empty((co, kc), dtype=torch.float32, device=dev)
+    call("vgtkb_inter_conv_backward", dev, b, n, p, nn, a, k, ci, co, ptr(xyz), ptr(sxyz), ptr(idx), ptr(rk), float(sigma),
+         ptr(w_kc), ptr(g_hi), ptr(g_lo if mode == 3 else None), ptr(gy), ptr(gy_hi), ptr(gy_lo), ptr(dg), ptr(gx), ptr(gw),
+         ptr(buf[:size]), mode)
+    torch.cuda.synchronize()
+    assert bool((buf[size:] == 12345.0).all()), "vgtkb_inter_conv_backward wrote past its workspace"
+    assert bool(torch.isfinite(gx).all()) and bool(torch.isfinite(gw).all())
