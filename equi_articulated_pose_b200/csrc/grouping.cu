@@ -1707,12 +1707,16 @@ int inter_group_forward_planes(int b, int n, int p, int nn, int a, int k, int ci
     } while (0)
         static const int g1 = getenv("VGTKB_IG_FWD1") ? atoi(getenv("VGTKB_IG_FWD1")) : 0;
         static const int g2 = getenv("VGTKB_IG_FWD2") ? atoi(getenv("VGTKB_IG_FWD2")) : 0;
+        // measured on bench.py (same box, per-entry-point CUDA events; profiles/r2_grouping_geometry_ab.txt): 10 warps x 2 CTAs
+        // per SM (20 warps, 6 anchors per warp: no ragged last round as with 8 warps on 60 anchors) beats 8 x 2, 6 x 3, 5 x 3
+        // and 4 x 4 for the 16-neighbour kernels (forward 2.12 -> 2.03 ms per step, backward 2.92 -> 2.87) and for the
+        // 32-neighbour backward (1.90 -> 1.87); the 32-neighbour forward needs 128 registers and stays at 8 x 2
         if (ks == 1) {
             if (g1 == 63) VGTKB_FWD_PL(1, 6, 3);
             else if (g1 == 44) VGTKB_FWD_PL(1, 4, 4);
-            else if (g1 == 102) VGTKB_FWD_PL(1, 10, 2);
+            else if (g1 == 82) VGTKB_FWD_PL(1, IG_WARPS, 2);
             else if (g1 == 53) VGTKB_FWD_PL(1, 5, 3);
-            else VGTKB_FWD_PL(1, IG_WARPS, 2);
+            else VGTKB_FWD_PL(1, 10, 2);
         } else {
             if (g2 == 62) VGTKB_FWD_PL(2, 6, 2);
             else if (g2 == 53) VGTKB_FWD_PL(2, 5, 3);
@@ -1866,15 +1870,15 @@ extern "C" int vgtkb_inter_group_backward(int b, int n, int p, int nn, int a, in
             if (nn <= 16) {
                 if (g1 == 63) VGTKB_BWD_TL(1, 6, 3);
                 else if (g1 == 44) VGTKB_BWD_TL(1, 4, 4);
-                else if (g1 == 102) VGTKB_BWD_TL(1, 10, 2);
+                else if (g1 == 82) VGTKB_BWD_TL(1, IG_WARPS, 2);
                 else if (g1 == 53) VGTKB_BWD_TL(1, 5, 3);
-                else VGTKB_BWD_TL(1, IG_WARPS, 2);
+                else VGTKB_BWD_TL(1, 10, 2);
             } else {
                 if (g2 == 63) VGTKB_BWD_TL(2, 6, 3);
                 else if (g2 == 53) VGTKB_BWD_TL(2, 5, 3);
                 else if (g2 == 44) VGTKB_BWD_TL(2, 4, 4);
-                else if (g2 == 102) VGTKB_BWD_TL(2, 10, 2);
-                else VGTKB_BWD_TL(2, IG_WARPS, 2);
+                else if (g2 == 82) VGTKB_BWD_TL(2, IG_WARPS, 2);
+                else VGTKB_BWD_TL(2, 10, 2);
             }
 #undef VGTKB_BWD_TL
             return check_launch("inter_group_backward(mma, tensor-map load)");
