@@ -66,14 +66,36 @@ class FusedBatchNorm2d(nn.BatchNorm2d):
     planes_bwd = False      # the input comes from a contraction: write the planes of its gradient in backward
     counter_managed = False # num_batches_tracked is a view of the owning model's flat counter, bumped once per step there
 
-    def forward_rows(self, rows, slope, residual=None):
-        training = self.training or not self.track_running_stats
+    def _step_momentum(self, training):
+        """Bump the batch counter (unless the owning model does it) and return the running-average factor of this step."""
         if training and self.track_running_stats and self.num_batches_tracked is not None and not self.counter_managed:
             self.num_batches_tracked += 1
         if self.momentum is None:       # torch: cumulative moving average when momentum is None
-            mom = 1.0 / max(float(self.num_batches_tracked), 1.0) if training and self.num_batches_tracked is not None else 0.0
-        else:
-            mom = self.momentum
+            return 1.0 / max(float(self.num_batches_tracked), 1.0) if training and self.num_batches_tracked is not None else 0.0
+        return self.momentum
+
+    @staticmethod
+    def pair_ok(n1, n2):
+        """Both are training-mode SyncBatchNorm layers over the same ranks and channel count: their statistics can share one
+        exchange per direction (ops.SyncNormPairFn).  VGTKB_SYNCBN_PAIR=0 keeps one exchange per norm (A/B runs)."""
+        return (isinstance(n1, FusedBatchNorm2d) and isinstance(n2, FusedBatchNorm2d) and n1.training and n2.training
+                and n1.sync_group is not None and n1.sync_group is n2.sync_group and _ops._sync_world(n1.sync_group) > 1
+                and n1.num_features == n2.num_features and n1.eps == n2.eps and n1.affine == n2.affine
+                and os.environ.get("VGTKB_SYNCBN_PAIR", "1") != "0")
+
+    @staticmethod
+    def forward_rows_pair(n1, rows1, slope1, n2, rows2, slope2):
+        """(leaky_relu(n1(rows1)), leaky_relu(n2(rows2))) with one statistics exchange for both (pair_ok must hold)."""
+        m1, m2 = n1._step_momentum(True), n2._step_momentum(True)
+        y1, y2 = _ops.SyncNormPairFn.apply(
+            rows1.unsqueeze(0), n1.weight, n1.bias, n1.running_mean, n1.running_var, m1, slope1, n1.planes_fwd, n1.planes_bwd,
+            rows2.unsqueeze(0), n2.weight, n2.bias, n2.running_mean, n2.running_var, m2, slope2, n2.planes_fwd, n2.planes_bwd,
+            n1.eps, n1.sync_group)
+        return y1.squeeze(0), y2.squeeze(0)
+
+    def forward_rows(self, rows, slope, residual=None):
+        training = self.training or not self.track_running_stats
+        mom = self._step_momentum(training)
         return _ops.norm_act(rows.unsqueeze(0), self.weight, self.bias, None if residual is None else residual.unsqueeze(0),
                              self.running_mean if training else self.running_mean,
                              self.running_var if training else self.running_var,
@@ -207,7 +229,13 @@ class SeparableSO3ConvBlock(nn.Module):
         if self.training and skip.requires_grad and skip.is_cuda and self.inter_conv.conv.pooling is None and os.environ.get("VGTKB_GRAD_SLOT", "1") != "0":
             slot = _ops.GradSlot((b, n, a, ci))
             self.inter_conv.conv._grad_slot = slot
-        inter_idx, inter_w, sample_idx, y = self.inter_conv(x, inter_idx, inter_w)
+        # SyncBatchNorm: the inter conv's norm and the skip branch's norm share ONE statistics exchange per direction
+        pair = (self.use_intra and self.inter_conv.dropout is None and skip.is_cuda
+                and FusedBatchNorm2d.pair_ok(self.inter_conv.norm, self.norm))
+        if pair:
+            inter_idx, inter_w, sample_idx, y = self.inter_conv.conv(x, inter_idx, inter_w)      # norm applied below
+        else:
+            inter_idx, inter_w, sample_idx, y = self.inter_conv(x, inter_idx, inter_w)
         self.inter_conv.conv._grad_slot = None
         if slot is not None and not slot.armed:
             slot = None                             # the conv did not take the fused path: ordinary autograd accumulation
@@ -225,7 +253,13 @@ class SeparableSO3ConvBlock(nn.Module):
         if wp is not None and not (srows.is_cuda and wp.param is self.skip_conv.weight and wp.valid()):
             wp = None
         srows = _ops.LinearFn.apply(srows, w, self.skip_conv.bias, None, lin_slot, wp)
-        srows = _apply_norm(self.norm, srows, b, self.slope)
+        if pair:
+            yrows, (yb, yp, ya, _) = _rows(y.feats)
+            yrows, srows = FusedBatchNorm2d.forward_rows_pair(self.inter_conv.norm, yrows, self.inter_conv.slope,
+                                                             self.norm, srows, self.slope)
+            y = zptk.SphericalPointCloud(y.xyz, _unrows(yrows, yb, yp, ya), y.anchors)
+        else:
+            srows = _apply_norm(self.norm, srows, b, self.slope)
         if self.use_intra:
             y = self.intra_conv(y, residual_rows=srows)
             out = y.feats
