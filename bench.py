@@ -80,8 +80,47 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self._stop = None, None
+
+    def _start_nvml(self):
+        """NVML directly (what nvidia-smi reads), sampled every ~5 ms from a thread: the 10-step timed region lasts ~150 ms,
+        in which `nvidia-smi -lms 100` delivers one or two samples (often its first one, taken while it starts up)."""
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(self.index).uuid))
+        except Exception:  # noqa: BLE001  (older torch without .uuid, or remapped devices: plain index)
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [(pynvml.nvmlClocksEventReasonHwSlowdown, 3), (pynvml.nvmlClocksEventReasonHwThermalSlowdown, 4),
+                (pynvml.nvmlClocksEventReasonSwThermalSlowdown, 5), (pynvml.nvmlClocksEventReasonSwPowerCap, 6)]
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)       # fail here, not in the thread
+        self._stop = threading.Event()
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    r = get_reasons(h)
+                    row = [str(sm), str(mx), "", "", "", "", ""]
+                    for bit, col in bits:
+                        row[col] = "Active" if (r & bit) else "Not Active"
+                    self.rows.append(row)
+                except Exception:  # noqa: BLE001
+                    pass
+                self._stop.wait(0.005)
+        self.t = threading.Thread(target=loop, daemon=True)
+        self.t.start()
+        self.nvml = pynvml
 
     def start(self):
+        try:
+            self._start_nvml()
+            return self
+        except Exception:  # noqa: BLE001  (no pynvml / NVML error: the nvidia-smi process below)
+            self.nvml, self._stop = None, None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -97,16 +136,21 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=2)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
+        else:
+            self.proc.terminate()
+            self.t.join(timeout=2)
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace('.', '').isdigit())
         mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "sm_mhz_min": sm[0] if sm else None,
+                "source": "nvml, 5 ms period" if self.nvml is not None else "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------- CPU oracle leg
