@@ -252,7 +252,7 @@ def inter_conv_supported(b, n, p, nn, a, k, ci, co):
 class PreparedWeight:
     """One conv weight of a model whose operand planes are produced by WeightPlanes.prepare(): `param` is the parameter in the
     reference's layout ([co, ci*k] with column c*k + kp, or the 1x1 conv's [co, ci, 1, 1]); `fwd` / `bwd` are the bf16 hi | lo
-    planes (uint16 [2 * co*ci*k]) of the forward operand and of the data-gradient operand.  valid(): the planes were
+    planes (one bf16 tensor [2 * co*ci*k], hi then lo) of the forward operand and of the data-gradient operand.  valid(): the planes were
     computed from the parameter's current value (its version counter has not moved since prepare())."""
     __slots__ = ("param", "co", "ci", "k", "role", "fwd", "bwd", "version")
 
@@ -291,6 +291,7 @@ class WeightPlanes:
 
     def add(self, param, co, ci, k, role):
         assert role in ("inter", "intra", "linear") and param.numel() == co * ci * k and (co * ci * k) % 8 == 0
+        assert param.is_contiguous() and param.dtype == torch.float32
         pw = PreparedWeight(param, co, ci, k, role)
         self.weights.append(pw)
         self._table = None
