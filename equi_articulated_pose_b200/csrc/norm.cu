@@ -442,8 +442,21 @@ template <int U>
 __global__ void __launch_bounds__(NT, 3)
 norm_act_bwd_apply4b_kernel(int64_t rows4, int64_t rows, int64_t nrows, int c4, const float4* __restrict__ x, OpBwd bw,
                             const double* __restrict__ scratch, float4* __restrict__ gx, uint2* __restrict__ gx_hi,
-                            uint2* __restrict__ gx_lo) {
+                            uint2* __restrict__ gx_lo, float* __restrict__ ggamma = nullptr, float* __restrict__ gbeta = nullptr) {
     const int c = c4 * 4, g = blockIdx.y;
+    // affine gradients (sum dyp * xhat, sum dyp: the two sums themselves, over all groups) written by one CTA of this launch
+    // instead of a launch of their own (affine_grad_kernel) -- single-process statistics only, where scratch holds local sums
+    if ((ggamma != nullptr || gbeta != nullptr) && blockIdx.x == 0 && blockIdx.y == 0) {
+        for (int cc = threadIdx.x; cc < c; cc += NT) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int gg = 0; gg < (int)gridDim.y; ++gg) {
+                s1 += scratch[((size_t)gg * 2 + 0) * c + cc];
+                s2 += scratch[((size_t)gg * 2 + 1) * c + cc];
+            }
+            if (gbeta) gbeta[cc] = (float)s1;
+            if (ggamma) ggamma[cc] = (float)s2;
+        }
+    }
     const int64_t t0 = (int64_t)blockIdx.x * NT + threadIdx.x, stride = (int64_t)gridDim.x * NT;
     const int ch = (int)(t0 % c4) * 4;
     const size_t base = (size_t)g * rows4;
@@ -617,9 +630,26 @@ extern "C" int vgtkb_norm_bwd_apply(int groups, int64_t rows, int64_t total_rows
                                        nullptr, stream);
 }
 
+// fused: 1 = the 4b kernel ran and also wrote grad_gamma / grad_beta (when given); 0 = another kernel ran, the caller launches
+// affine_grad_kernel itself
+static int norm_bwd_apply_impl(int groups, int64_t rows, int64_t total_rows, int c, const float* x, const float* stats,
+                               const float* gamma, const float* beta, float slope, const float* grad_y, const double* scratch,
+                               float* grad_x, void* gx_hi, void* gx_lo, float* grad_gamma, float* grad_beta, int* fused,
+                               void* stream);
+
 extern "C" int vgtkb_norm_bwd_apply_planes(int groups, int64_t rows, int64_t total_rows, int c, const float* x, const float* stats,
                                            const float* gamma, const float* beta, float slope, const float* grad_y,
                                            const double* scratch, float* grad_x, void* gx_hi, void* gx_lo, void* stream) {
+    int fused = 0;
+    return norm_bwd_apply_impl(groups, rows, total_rows, c, x, stats, gamma, beta, slope, grad_y, scratch, grad_x, gx_hi, gx_lo,
+                               nullptr, nullptr, &fused, stream);
+}
+
+static int norm_bwd_apply_impl(int groups, int64_t rows, int64_t total_rows, int c, const float* x, const float* stats,
+                               const float* gamma, const float* beta, float slope, const float* grad_y, const double* scratch,
+                               float* grad_x, void* gx_hi, void* gx_lo, float* grad_gamma, float* grad_beta, int* fused,
+                               void* stream) {
+    *fused = 0;
     VGTKB_REQUIRE(groups > 0 && rows > 0 && (total_rows <= 0 || total_rows >= rows) && c > 0, "norm_bwd_apply: bad size");
     VGTKB_REQUIRE((gx_hi == nullptr) == (gx_lo == nullptr), "norm_bwd_apply: both planes or none");
     VGTKB_REQUIRE(groups <= 65535, "norm_bwd_apply: too many groups");
@@ -633,7 +663,9 @@ extern "C" int vgtkb_norm_bwd_apply_planes(int groups, int64_t rows, int64_t tot
         const int64_t cap = ceil_div64((int64_t)kNumSMs * 6, groups);
         if (gx4 > cap) gx4 = cap;
         norm_act_bwd_apply4b_kernel<4><<<dim3((unsigned)gx4, groups), NT, 0, st>>>(rows4, rows, total_rows, c / 4, (const float4*)x, bw,
-                                                                                  scratch, (float4*)grad_x, (uint2*)gx_hi, (uint2*)gx_lo);
+                                                                                  scratch, (float4*)grad_x, (uint2*)gx_hi, (uint2*)gx_lo,
+                                                                                  grad_gamma, grad_beta);
+        *fused = 1;
     } else if (gx_hi != nullptr) {
         set_error("norm_bwd_apply: planes need c %% 4 == 0, 256 %% (c/4) == 0 and 16-byte aligned tensors");
         return VGTKB_EINVAL;
@@ -660,10 +692,18 @@ extern "C" int vgtkb_norm_act_backward_planes(int groups, int64_t rows, int c, c
                                               const float* gamma, const float* beta, float slope, const float* grad_y,
                                               double* scratch, float* grad_x, float* grad_gamma, float* grad_beta,
                                               void* gx_hi, void* gx_lo, void* stream) {
-    const int rc = vgtkb_norm_bwd_sums(groups, rows, c, x, stats, gamma, beta, slope, grad_y, scratch, grad_gamma, grad_beta, stream);
+    // the affine gradients are the two local sums: written by the apply kernel (one launch less per BatchNorm backward)
+    int rc = vgtkb_norm_bwd_sums(groups, rows, c, x, stats, gamma, beta, slope, grad_y, scratch, nullptr, nullptr, stream);
     if (rc != 0) return rc;
-    return vgtkb_norm_bwd_apply_planes(groups, rows, rows, c, x, stats, gamma, beta, slope, grad_y, scratch, grad_x, gx_hi, gx_lo,
-                                       stream);
+    int fused = 0;
+    rc = norm_bwd_apply_impl(groups, rows, rows, c, x, stats, gamma, beta, slope, grad_y, scratch, grad_x, gx_hi, gx_lo, grad_gamma,
+                             grad_beta, &fused, stream);
+    if (rc != 0) return rc;
+    if (!fused && (grad_gamma || grad_beta)) {
+        affine_grad_kernel<<<ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(groups, c, scratch, grad_gamma, grad_beta);
+        return check_launch("norm_act_backward");
+    }
+    return VGTKB_OK;
 }
 
 extern "C" int vgtkb_col_sum(int64_t rows, int c, const float* x, double* scratch, float* out, void* stream) {

@@ -189,7 +189,7 @@ PROFILE = None  # set to a list to record (entry point, args, start event, end e
 # device kernels launched per entry point (memsets not counted); used for bench.py's gpu_launches
 KERNELS_PER_CALL = {"vgtkb_gemm_nt": 2, "vgtkb_gemm_tn": 2, "vgtkb_gather_gemm_nt": 2, "vgtkb_gather_gemm_tn": 2,
                     "vgtkb_chamfer_forward": 2, "vgtkb_chamfer_backward": 4, "vgtkb_anchor_chamfer_forward": 2, "vgtkb_anchor_chamfer_backward": 2, "vgtkb_norm_stats": 2,
-                    "vgtkb_norm_act_backward": 3, "vgtkb_norm_bwd_sums": 2, "vgtkb_col_sum": 2,
+                    "vgtkb_norm_act_backward": 2, "vgtkb_norm_bwd_sums": 2, "vgtkb_col_sum": 2,
                     "vgtkb_inter_conv_forward": 3, "vgtkb_inter_conv_backward": 6, "vgtkb_gemm_nt_presplit": 2,
                     "vgtkb_gemm_tn_presplit": 2, "vgtkb_gemm_tn_planes": 1, "vgtkb_gather_gemm_nt_planes": 2,
-                    "vgtkb_gather_gemm_tn_planes": 1, "vgtkb_norm_act_backward_planes": 3}
+                    "vgtkb_gather_gemm_tn_planes": 1, "vgtkb_norm_act_backward_planes": 2}
