@@ -72,85 +72,104 @@ def parse():
 
 
 # ---------------------------------------------------------------------------------- clocks
+_NVML_SAMPLER = r"""
+import sys, time
+import pynvml as N
+N.nvmlInit()
+arg = sys.argv[1]
+h = N.nvmlDeviceGetHandleByUUID(arg) if arg.startswith("GPU-") else N.nvmlDeviceGetHandleByIndex(int(arg))
+mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+get = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+bits = [N.nvmlClocksEventReasonHwSlowdown, N.nvmlClocksEventReasonHwThermalSlowdown,
+        N.nvmlClocksEventReasonSwThermalSlowdown, N.nvmlClocksEventReasonSwPowerCap]
+period = float(sys.argv[2])
+while True:
+    sm, r = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), get(h)
+    print("%.6f,%d,%d,,%s" % (time.time(), sm, mx, ",".join("Active" if r & b else "Not Active" for b in bits)), flush=True)
+    time.sleep(period)
+"""
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe: nvidia-smi's clocks line).
+    Default: a helper PROCESS reads the same NVML counters every 10 ms and timestamps them; the rows between mark_begin() and
+    mark_end() count (the 10-step timed region lasts ~150 ms, in which `nvidia-smi -lms 100` delivers one or two samples).
+    The helper is started, and has delivered its first row, BEFORE the region: NVML initialisation in another process while the
+    steps run costs time -- `nvidia-smi -lms 100` launched at the region's start measured 523-533 k points/s where the helper
+    measures 538-540 k on the same box (the end-to-end region, which runs with no sampler at all, reads 519-536 k either way).
+    VGTKB_CLOCK_SAMPLER=smi (or no pynvml): the `nvidia-smi -lms 100` process."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-        self.nvml, self._stop = None, None
+        self.index, self.rows, self.proc, self.source = index, [], None, None
+        self.t_begin, self.t_end = None, None
 
-    def _start_nvml(self):
-        """NVML directly (what nvidia-smi reads), sampled every ~5 ms from a thread: the 10-step timed region lasts ~150 ms,
-        in which `nvidia-smi -lms 100` delivers one or two samples (often its first one, taken while it starts up)."""
-        import pynvml
-        pynvml.nvmlInit()
-        try:
-            import torch
-            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(self.index).uuid))
-        except Exception:  # noqa: BLE001  (older torch without .uuid, or remapped devices: plain index)
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
-        bits = [(pynvml.nvmlClocksEventReasonHwSlowdown, 3), (pynvml.nvmlClocksEventReasonHwThermalSlowdown, 4),
-                (pynvml.nvmlClocksEventReasonSwThermalSlowdown, 5), (pynvml.nvmlClocksEventReasonSwPowerCap, 6)]
-        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)       # fail here, not in the thread
-        self._stop = threading.Event()
+    def _spawn(self, cmd, stamped):
+        self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
 
-        def loop():
-            while not self._stop.is_set():
-                try:
-                    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                    r = get_reasons(h)
-                    row = [str(sm), str(mx), "", "", "", "", ""]
-                    for bit, col in bits:
-                        row[col] = "Active" if (r & bit) else "Not Active"
-                    self.rows.append(row)
-                except Exception:  # noqa: BLE001
-                    pass
-                self._stop.wait(0.005)
-        self.t = threading.Thread(target=loop, daemon=True)
+        def read():
+            for line in self.proc.stdout:
+                cols = [c.strip() for c in line.split(",")]
+                if stamped:
+                    try:
+                        self.rows.append((float(cols[0]), cols[1:]))
+                    except ValueError:
+                        pass
+                else:
+                    self.rows.append((time.time(), cols))
+        self.t = threading.Thread(target=read, daemon=True)
         self.t.start()
-        self.nvml = pynvml
 
     def start(self):
+        if os.environ.get("VGTKB_CLOCK_SAMPLER", "nvml") == "nvml":
+            try:
+                import pynvml  # noqa: F401  (only to know the helper can import it)
+                try:
+                    import torch
+                    dev = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+                except Exception:  # noqa: BLE001  (older torch without .uuid: plain index)
+                    dev = str(self.index)
+                self._spawn([sys.executable, "-c", _NVML_SAMPLER, dev, "0.01"], True)
+                t0 = time.time()
+                while not self.rows and time.time() - t0 < 5.0 and self.proc.poll() is None:
+                    time.sleep(0.01)                      # the helper needs ~0.3 s to start: wait for its first row HERE
+                if self.rows:
+                    self.source = "nvml helper process, 10 ms period"
+                    return self
+                self.proc.terminate()
+            except Exception:  # noqa: BLE001
+                pass
+            self.proc, self.rows = None, []
         try:
-            self._start_nvml()
-            return self
-        except Exception:  # noqa: BLE001  (no pynvml / NVML error: the nvidia-smi process below)
-            self.nvml, self._stop = None, None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self._spawn(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                         "-lms", "100"], False)
+            self.source = "nvidia-smi -lms 100"
         except OSError:
             self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
-        if self.nvml is not None:
-            self._stop.set()
-            self.t.join(timeout=2)
-        elif self.proc is None:
+        if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        else:
-            self.proc.terminate()
-            self.t.join(timeout=2)
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace('.', '').isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        rows = [r for ts, r in self.rows if (self.t_begin is None or ts >= self.t_begin) and (self.t_end is None or ts <= self.t_end)]
+        if not rows:                                       # region shorter than one period: the nearest samples
+            rows = [r for _, r in self.rows[-2:]]
+        sm = sorted(int(float(r[0])) for r in rows if r and r[0].replace('.', '').isdigit())
+        mx = [int(float(r[1])) for r in rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm), "sm_mhz_min": sm[0] if sm else None,
-                "source": "nvml, 5 ms period" if self.nvml is not None else "nvidia-smi -lms 100"}
+                "reasons": reasons, "samples": len(sm), "sm_mhz_min": sm[0] if sm else None, "source": self.source}
 
 
 # ---------------------------------------------------------------------------------- CPU oracle leg
@@ -552,12 +571,14 @@ def run_ours(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         run_step(dev_in)
         flush.zero_()
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
