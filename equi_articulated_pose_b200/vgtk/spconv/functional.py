@@ -179,7 +179,7 @@ def inter_zpconv_grouping_ball(xyz, stride, radius, n_neighbor, lazy_sample=True
         idx, sample_xyz = pctk.furthest_sample(xyz, n_sample, lazy_sample)
     else:
         sample_xyz = xyz
-        idx = torch.arange(xyz.shape[2], dtype=torch.long, device=xyz.device).unsqueeze(0).repeat(xyz.shape[0], 1)
+        idx = pctk.identity_index(xyz.shape[0], xyz.shape[2], xyz.device, torch.long)
     ball_idx, grouped_xyz = ball_query(sample_xyz, xyz, radius, n_neighbor)
     grouped_xyz = grouped_xyz - sample_xyz.unsqueeze(3)
     return grouped_xyz, ball_idx, idx, sample_xyz
@@ -193,6 +193,6 @@ def ball_indices(xyz, stride, radius, n_neighbor, lazy_sample=True):
         idx, sample_xyz = pctk.furthest_sample(xyz, n_sample, lazy_sample)
     else:
         sample_xyz = xyz
-        idx = torch.arange(xyz.shape[2], dtype=torch.long, device=xyz.device).unsqueeze(0).repeat(xyz.shape[0], 1)
+        idx = pctk.identity_index(xyz.shape[0], xyz.shape[2], xyz.device, torch.long)
     ball_idx = pctk.ball_query_index(sample_xyz, xyz, radius, n_neighbor)
     return ball_idx, idx, sample_xyz
